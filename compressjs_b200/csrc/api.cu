@@ -1,0 +1,386 @@
+// api.cu -- the C ABI declared in include/b2bz.h.  Thin: argument checks, H2D/D2H staging,
+// error translation.  All compute is in the CUDA stages (rle1.cu, bwt.cu, mtf.cu, huff.cu,
+// decode.cu).  There is no CPU fallback anywhere: without a CUDA device every call fails.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "ctx.h"
+
+// stages implemented in the other translation units
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx);
+u32 crc32_device(Ctx& c, const u8* d_p, size_t n);
+void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n,
+                           size_t first_block, size_t block_count, int bit_phase, bool whole_file, u64* out_bits,
+                           std::vector<u32>* crcs_out, size_t* total_blocks);
+int bzip2_decompress_device(Ctx& c, const u8* d_in, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n,
+                            bool single_block, u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len,
+                            u8** d_out_alloc);
+
+static std::mutex g_mu;
+static Ctx* g_ctx = nullptr;
+static thread_local std::string g_err;
+static std::map<void*, size_t> g_pinned_live;                  // pointers handed to the caller
+static std::multimap<size_t, void*> g_pinned_free;             // cached pinned buffers by capacity
+
+void Ctx::collect() {
+  float acc[ST_COUNT];
+  for (int i = 0; i < ST_COUNT; i++) acc[i] = 0.f;
+  for (auto& t : ev_tags) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_pool[t.second].a, ev_pool[t.second].b) == cudaSuccess) acc[t.first] += ms;
+  }
+  stats.ms_total = acc[ST_TOTAL]; stats.ms_h2d = acc[ST_H2D]; stats.ms_d2h = acc[ST_D2H];
+  stats.ms_rle1 = acc[ST_RLE1]; stats.ms_bwt = acc[ST_BWT]; stats.ms_mtf = acc[ST_MTF];
+  stats.ms_huff = acc[ST_HUFF]; stats.ms_pack = acc[ST_PACK]; stats.ms_scan = acc[ST_SCAN];
+  stats.ms_hdec = acc[ST_HDEC]; stats.ms_unmtf = acc[ST_UNMTF]; stats.ms_ibwt = acc[ST_IBWT];
+  stats.ms_unrle = acc[ST_UNRLE]; stats.ms_radix = acc[ST_RADIX];
+}
+
+static int pick_device() {
+  const char* e = getenv("B2_DEVICE");
+  if (e && *e) return atoi(e);
+  e = getenv("LOCAL_RANK");
+  if (e && *e) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) return atoi(e) % cnt;
+  }
+  return 0;
+}
+
+static Ctx& ctx_locked() {
+  if (!g_ctx) {
+    int dev = pick_device();
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+      throw B2Error{B2_ERR_CUDA, std::string("no CUDA device available (libb2bz has no CPU fallback): ") + cudaGetErrorString(e)};
+    if (dev >= cnt) throw B2Error{B2_ERR_CUDA, "requested CUDA device does not exist"};
+    CUDA_CHECK(cudaSetDevice(dev));
+    Ctx* c = new Ctx();
+    c->device = dev;
+    memset(&c->stats, 0, sizeof c->stats);
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    const char* b = getenv("B2_BWT_BATCH");
+    if (b && atoi(b) > 0) c->bwt_batch = (u32)atoi(b);
+    g_ctx = c;
+  } else {
+    CUDA_CHECK(cudaSetDevice(g_ctx->device));
+  }
+  return *g_ctx;
+}
+
+static void* pinned_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  auto it = g_pinned_free.lower_bound(bytes);
+  if (it != g_pinned_free.end() && it->first <= bytes * 2 + 4096) {
+    void* p = it->second; size_t cap = it->first;
+    g_pinned_free.erase(it);
+    g_pinned_live[p] = cap;
+    return p;
+  }
+  void* p = nullptr;
+  size_t cap = (bytes + 4095) & ~(size_t)4095;
+  CUDA_CHECK(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+  g_pinned_live[p] = cap;
+  return p;
+}
+
+template <typename F>
+static int guarded(F f) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  try {
+    g_err.clear();
+    return f();
+  } catch (const B2Error& e) {
+    g_err = e.msg;
+    if (g_ctx && e.code == B2_ERR_CUDA) { cudaStreamSynchronize(g_ctx->stream); cudaGetLastError(); }
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return B2_ERR_CUDA;
+  }
+}
+
+extern "C" {
+
+int b2_init(int device) {
+  return guarded([&]() {
+    if (g_ctx && g_ctx->device != device) throw B2Error{B2_ERR_BAD_ARG, "b2_init: context already bound to another device"};
+    if (!g_ctx) {
+      char buf[16]; snprintf(buf, sizeof buf, "%d", device);
+      setenv("B2_DEVICE", buf, 1);
+    }
+    ctx_locked();
+    return 0;
+  });
+}
+
+void b2_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_ctx) return;
+  cudaSetDevice(g_ctx->device);
+  cudaStreamSynchronize(g_ctx->stream);
+  for (auto& kv : g_pinned_free) cudaFreeHost(kv.second);
+  g_pinned_free.clear();
+  for (auto& e : g_ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  cudaStreamDestroy(g_ctx->stream);
+  delete g_ctx;
+  g_ctx = nullptr;
+}
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+void b2_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_pinned_live.find(p);
+  if (it == g_pinned_live.end()) { free(p); return; }
+  size_t cap = it->second;
+  g_pinned_live.erase(it);
+  size_t cached = 0;
+  for (auto& kv : g_pinned_free) cached += kv.first;
+  if (cached + cap > ((size_t)8 << 30)) cudaFreeHost(p);
+  else g_pinned_free.insert({cap, p});
+}
+
+void b2_get_stats(b2_stats* s) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ctx) *s = g_ctx->stats; else memset(s, 0, sizeof *s);
+}
+
+size_t b2_last_trace(b2_block_trace* out, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_ctx) return 0;
+  size_t n = g_ctx->trace.size();
+  if (out) for (size_t i = 0; i < n && i < cap; i++) out[i] = g_ctx->trace[i];
+  return n;
+}
+
+// ---- BWT ---------------------------------------------------------------------------------
+int b2_bwt_cyclic_batch(const uint8_t* T, uint8_t* U, const uint64_t* offs, const int32_t* lens, int32_t* pidx, size_t nblocks) {
+  return guarded([&]() {
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    for (size_t k = 0; k < nblocks; k++)
+      if (lens[k] < 0 || lens[k] > 900000) throw B2Error{B2_ERR_BAD_ARG, "block length out of range (0..900000)"};
+    {
+      StageScope tot(c, ST_TOTAL);
+      for (size_t k0 = 0; k0 < nblocks; k0 += c.bwt_batch) {
+        const u32 nb = (u32)std::min<size_t>(c.bwt_batch, nblocks - k0);
+        DBuf<u8> dT(c, (size_t)nb << SEG_SHIFT), dU(c, (size_t)nb << SEG_SHIFT);
+        DBuf<u32> dn(c, nb), dp(c, nb);
+        std::vector<u32> hn(nb);
+        for (u32 b = 0; b < nb; b++) {
+          hn[b] = (u32)lens[k0 + b];
+          if (hn[b]) CUDA_CHECK(cudaMemcpyAsync(dT.p + ((size_t)b << SEG_SHIFT), T + offs[k0 + b], hn[b], cudaMemcpyHostToDevice, c.stream));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(dn, hn.data(), nb * 4, cudaMemcpyHostToDevice, c.stream));
+        CUDA_CHECK(cudaMemsetAsync(dp, 0, nb * 4, c.stream));
+        {
+          StageScope s(c, ST_BWT);
+          bwt_forward_batch(c, dT, dU, dn, hn.data(), nb, dp);
+        }
+        std::vector<u32> hp(nb);
+        CUDA_CHECK(cudaMemcpyAsync(hp.data(), dp, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+        for (u32 b = 0; b < nb; b++)
+          if (hn[b]) CUDA_CHECK(cudaMemcpyAsync(U + offs[k0 + b], dU.p + ((size_t)b << SEG_SHIFT), hn[b], cudaMemcpyDeviceToHost, c.stream));
+        CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        for (u32 b = 0; b < nb; b++) pidx[k0 + b] = (int32_t)hp[b];
+        c.stats.blocks += nb;
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.collect();
+    return 0;
+  });
+}
+
+int32_t b2_bwt_cyclic(const uint8_t* T, uint8_t* U, int32_t n) {
+  if (n <= 1) {  // lib/BWT.js:376-379
+    if (n == 1) U[0] = T[0];
+    return 0;
+  }
+  uint64_t off = 0;
+  int32_t pidx = 0;
+  int rc = b2_bwt_cyclic_batch(T, U, &off, &n, &pidx, 1);
+  return rc < 0 ? rc : pidx;
+}
+
+uint32_t b2_crc32_bzip2(const uint8_t* p, size_t n) {
+  uint32_t crc = 0;
+  int rc = guarded([&]() {
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    DBuf<u8> d(c, n ? n : 1);
+    if (n) CUDA_CHECK(cudaMemcpyAsync(d, p, n, cudaMemcpyHostToDevice, c.stream));
+    crc = crc32_device(c, d, n);
+    return 0;
+  });
+  (void)rc;
+  return crc;
+}
+
+// ---- bzip2 -------------------------------------------------------------------------------
+size_t b2_bzip2_bound(size_t n) {
+  // worst case per block: Huffman codes up to 20 bits for <= n+1 symbols would be 2.5x, but the
+  // flat 2nd table bounds every 50-group at 50*ceil(log2(258)) = 450 bits = 9 bits/symbol;
+  // RLE1 can expand the block stream by 5/4.  Use a comfortable 1.5x + per-block headers.
+  size_t blocks = n / 99981 + 2;
+  return n + n / 2 + blocks * 4096 + 64;
+}
+
+int b2_bzip2_compress_dev(const void* d_in, size_t n, int level, void* d_out, size_t out_cap, size_t* out_n) {
+  return guarded([&]() {
+    if (level < 1 || level > 9) throw B2Error{B2_ERR_BAD_LEVEL, "Invalid block size multiplier"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    {
+      StageScope tot(c, ST_TOTAL);
+      bzip2_compress_device(c, (const u8*)d_in, n, level, (u8*)d_out, out_cap, out_n, 0, (size_t)-1, 0, true, nullptr, nullptr, nullptr);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.collect();
+    c.stats.raw_bytes = n; c.stats.comp_bytes = *out_n;
+    return 0;
+  });
+}
+
+int b2_bzip2_compress(const uint8_t* in, size_t n, int level, uint8_t** out, size_t* out_n) {
+  return guarded([&]() {
+    if (level < 1 || level > 9) throw B2Error{B2_ERR_BAD_LEVEL, "Invalid block size multiplier"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    size_t cap = b2_bzip2_bound(n), produced = 0;
+    void* host = nullptr;
+    {
+      StageScope tot(c, ST_TOTAL);
+      DBuf<u8> din(c, n ? n : 1), dout(c, cap);
+      {
+        StageScope s(c, ST_H2D);
+        if (n) CUDA_CHECK(cudaMemcpyAsync(din, in, n, cudaMemcpyHostToDevice, c.stream));
+      }
+      bzip2_compress_device(c, din, n, level, dout, cap, &produced, 0, (size_t)-1, 0, true, nullptr, nullptr, nullptr);
+      host = pinned_alloc(produced);
+      {
+        StageScope s(c, ST_D2H);
+        CUDA_CHECK(cudaMemcpyAsync(host, dout, produced, cudaMemcpyDeviceToHost, c.stream));
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.collect();
+    c.stats.raw_bytes = n; c.stats.comp_bytes = produced;
+    *out = (uint8_t*)host; *out_n = produced;
+    return 0;
+  });
+}
+
+int b2_bzip2_plan(const void* d_in, size_t n, int level, size_t* total_blocks) {
+  return guarded([&]() {
+    if (level < 1 || level > 9) throw B2Error{B2_ERR_BAD_LEVEL, "Invalid block size multiplier"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    size_t dummy = 0;
+    bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, total_blocks);
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return 0;
+  });
+}
+
+int b2_bzip2_encode_range_dev(const void* d_in, size_t n, int level, size_t first, size_t count, int bit_phase, void* d_out,
+                              size_t out_cap, uint64_t* out_bits, uint32_t* block_crcs) {
+  return guarded([&]() {
+    if (level < 1 || level > 9) throw B2Error{B2_ERR_BAD_LEVEL, "Invalid block size multiplier"};
+    if (bit_phase < 0 || bit_phase > 7) throw B2Error{B2_ERR_BAD_ARG, "bit_phase must be 0..7"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    size_t bytes = 0;
+    std::vector<u32> crcs;
+    {
+      StageScope tot(c, ST_TOTAL);
+      bzip2_compress_device(c, (const u8*)d_in, n, level, (u8*)d_out, out_cap, &bytes, first, count, bit_phase, false, out_bits, &crcs, nullptr);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.collect();
+    if (block_crcs) for (size_t i = 0; i < crcs.size(); i++) block_crcs[i] = crcs[i];
+    return 0;
+  });
+}
+
+static int decode_common(const uint8_t* in, size_t n, int multistream, bool single, u64 bitpos, uint8_t** out, size_t* out_n,
+                         std::vector<u64>* tp, std::vector<u32>* tl) {
+  Ctx& c = ctx_locked();
+  c.reset_call();
+  size_t produced = 0;
+  void* host = nullptr;
+  int rc = 0;
+  {
+    StageScope tot(c, ST_TOTAL);
+    DBuf<u8> din(c, n + 16);
+    {
+      StageScope s(c, ST_H2D);
+      CUDA_CHECK(cudaMemsetAsync(din.p + n, 0, 16, c.stream));
+      if (n) CUDA_CHECK(cudaMemcpyAsync(din, in, n, cudaMemcpyHostToDevice, c.stream));
+    }
+    u8* dres = nullptr;
+    rc = bzip2_decompress_device(c, din, n, multistream, nullptr, 0, &produced, single, bitpos, tp, tl, &dres);
+    if (rc == 0 && out) {
+      host = pinned_alloc(produced);
+      StageScope s(c, ST_D2H);
+      if (produced) CUDA_CHECK(cudaMemcpyAsync(host, dres, produced, cudaMemcpyDeviceToHost, c.stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (dres) c.dfree(dres);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.collect();
+  c.stats.raw_bytes = produced; c.stats.comp_bytes = n;
+  if (rc) return rc;
+  if (out) { *out = (uint8_t*)host; *out_n = produced; }
+  return 0;
+}
+
+int b2_bzip2_decompress(const uint8_t* in, size_t n, int multistream, uint8_t** out, size_t* out_n) {
+  return guarded([&]() { return decode_common(in, n, multistream, false, 0, out, out_n, nullptr, nullptr); });
+}
+
+int b2_bzip2_decompress_block(const uint8_t* in, size_t n, uint64_t bitpos, uint8_t** out, size_t* out_n) {
+  return guarded([&]() { return decode_common(in, n, 0, true, bitpos, out, out_n, nullptr, nullptr); });
+}
+
+int b2_bzip2_table(const uint8_t* in, size_t n, int multistream, uint64_t** bitpos, uint32_t** sizes, size_t* count) {
+  return guarded([&]() {
+    std::vector<u64> tp; std::vector<u32> tl;
+    int rc = decode_common(in, n, multistream, false, 0, nullptr, nullptr, &tp, &tl);
+    if (rc) return rc;
+    *count = tp.size();
+    *bitpos = (uint64_t*)malloc(sizeof(uint64_t) * (tp.size() + 1));
+    *sizes = (uint32_t*)malloc(sizeof(uint32_t) * (tp.size() + 1));
+    for (size_t i = 0; i < tp.size(); i++) { (*bitpos)[i] = tp[i]; (*sizes)[i] = tl[i]; }
+    return 0;
+  });
+}
+
+int b2_bzip2_decompress_dev(const void* d_in, size_t n, int multistream, void* d_out, size_t out_cap, size_t* out_n) {
+  return guarded([&]() {
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    int rc;
+    {
+      StageScope tot(c, ST_TOTAL);
+      rc = bzip2_decompress_device(c, (const u8*)d_in, n, multistream, (u8*)d_out, out_cap, out_n, false, 0, nullptr, nullptr, nullptr);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.collect();
+    c.stats.raw_bytes = *out_n; c.stats.comp_bytes = n;
+    return rc;
+  });
+}
+
+}  // extern "C"

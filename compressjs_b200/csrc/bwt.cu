@@ -1,0 +1,301 @@
+// bwt.cu -- batched forward cyclic Burrows-Wheeler transform on the GPU.
+//
+// Replaces lib/BWT.js:372-417 (BWT.bwtransform2: SA-IS over the doubled block, one block
+// at a time) with a segmented prefix-doubling suffix sort over MANY bzip2 blocks at once:
+//
+//   1. key32[g] = first 4 bytes of rotation g (cyclic), g = block<<20 | i
+//   2. segmented LSD radix sort of (key32, g) per block           (radix.cuh, 4 passes)
+//   3. k_rerank<INIT>: group heads -> rank[g], SA, compact the suffixes whose group is
+//      not yet a singleton into (head, g) records
+//   4. rounds h = 4, 8, 16, ...: for the still-unsorted suffixes only
+//        key64 = head << 20 | rank[(i+h) mod n]   (k_gather)
+//        flat radix sort of (key64, g)           (radix.cuh)
+//        k_rerank<ROUND>: scatter back into SA[head + j], refine ranks, re-compact
+//      until nothing is left or h >= n (then the remaining ties are equal rotations of a
+//      periodic block, ordered by DESCENDING start index -- what sorting the doubled
+//      string yields in the reference)
+//   5. k_emit: U[p] = T[SA[p]-1], pidx = row of rotation 0
+//
+// All arrays use the slot layout g = block << 20 | position (max block 900000 < 2^20).
+#include "ctx.h"
+#include "radix.cuh"
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 nslots, u32* __restrict__ key32) {
+  u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nslots) return;
+  u32 b = g >> SEG_SHIFT, i = g & SEG_MASK, n = seg_n[b];
+  if (i >= n) return;
+  const u8* t = T + ((size_t)b << SEG_SHIFT);
+  u32 i1 = i + 1; if (i1 >= n) i1 -= n;
+  u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
+  u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
+  key32[g] = ((u32)t[i] << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3];
+}
+
+// ---------------------------------------------------------------------------------------
+#define RR_THREADS 256
+#define RR_ITEMS 8
+#define RR_TILE (RR_THREADS * RR_ITEMS)
+
+// Exclusive max over the threads before this one (0 when none). ws: RR_THREADS/32+1 entries.
+__device__ __forceinline__ u32 block_excl_max_u32(u32 v, u32* ws, u32* total) {
+  u32 inc = warp_incl_max(v);
+  u32 exw = __shfl_up_sync(FULL_MASK, inc, 1);
+  if (lane_id() == 0) exw = 0;
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) ws[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    u32 x = (lane_id() < RR_THREADS / 32) ? ws[lane_id()] : 0u;
+    u32 xi = warp_incl_max(x);
+    u32 xe = __shfl_up_sync(FULL_MASK, xi, 1);
+    if (lane_id() == 0) xe = 0;
+    if (lane_id() < RR_THREADS / 32) ws[lane_id()] = xe;
+    if (lane_id() == RR_THREADS / 32 - 1) ws[RR_THREADS / 32] = xi;
+  }
+  __syncthreads();
+  u32 c = ws[w];
+  *total = ws[RR_THREADS / 32];
+  __syncthreads();
+  return exw > c ? exw : c;
+}
+
+// One kernel for both "after the initial sort" (INIT: records live in the slot layout, key =
+// 4-byte prefix, every block is one old group) and "after a doubling round" (records are the
+// flat sorted (key64 = head<<20|r2, g) array).
+template <bool INIT>
+__global__ void __launch_bounds__(RR_THREADS)
+k_rerank(const u32* __restrict__ key32, const u64* __restrict__ key64, const u32* __restrict__ vals,
+         const u32* __restrict__ seg_n, u32 total, u32* __restrict__ SA, u32* __restrict__ rank,
+         u32* __restrict__ next_head, u32* __restrict__ next_idx, u32* next_count, u32* ticket, u64* st_first,
+         u64* st_new, u64* st_cnt, u32 ntiles) {
+  __shared__ u64 sk[RR_TILE + 2];      // composite keys, sk[0] = predecessor of the tile, sk[TILE+1] = successor
+  __shared__ u8 sv[RR_TILE + 2];       // validity of the same
+  __shared__ u32 ws[RR_THREADS / 32 + 1];
+  __shared__ u32 s_tile, s_cf, s_cn, s_cc;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 q0 = tile * RR_TILE;
+  // ---- stage composite keys (with a halo of one on each side) ----
+  for (u32 j = tid; j < RR_TILE + 2; j += RR_THREADS) {
+    long long q = (long long)q0 + (long long)j - 1;
+    u64 ck = 0; u8 v = 0;
+    if (q >= 0 && q < (long long)total) {
+      if (INIT) {
+        u32 b = (u32)q >> SEG_SHIFT, i = (u32)q & SEG_MASK;
+        if (i < seg_n[b]) { v = 1; ck = ((u64)(b + 1) << 32) | key32[q]; }
+      } else {
+        v = 1; ck = key64[q];
+      }
+    }
+    sk[j] = ck; sv[j] = v;
+  }
+  __syncthreads();
+  // ---- per item flags ----
+  u32 vf[RR_ITEMS], vn[RR_ITEMS], nc[RR_ITEMS];
+  u32 mf = 0, mn = 0, cs = 0;
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; j++) {
+    const u32 l = tid * RR_ITEMS + j + 1;  // index into sk
+    const u32 q = q0 + tid * RR_ITEMS + j;
+    const bool valid = sv[l];
+    const u64 ck = sk[l];
+    bool hc, nh, single;
+    if (INIT) {
+      hc = (q & SEG_MASK) == 0;
+      nh = !sv[l - 1] || sk[l - 1] != ck;
+    } else {
+      hc = !sv[l - 1] || (sk[l - 1] >> SEG_SHIFT) != (ck >> SEG_SHIFT);
+      nh = !sv[l - 1] || sk[l - 1] != ck;
+    }
+    single = nh && (!sv[l + 1] || sk[l + 1] != ck);
+    vf[j] = (valid && hc) ? q + 1 : 0;
+    vn[j] = (valid && nh) ? q + 1 : 0;
+    nc[j] = (valid && !single) ? 1u : 0u;
+    mf = max(mf, vf[j]); mn = max(mn, vn[j]); cs += nc[j];
+  }
+  // ---- block scans of the thread aggregates ----
+  u32 tot_f, tot_n, tot_c;
+  u32 ex_f = block_excl_max_u32(mf, ws, &tot_f);
+  u32 ex_n = block_excl_max_u32(mn, ws, &tot_n);
+  u32 ex_c = block_excl_add<RR_THREADS, u32>(cs, ws, &tot_c);
+  // ---- chained scans across tiles: warps 0,1,2 each run one look-back ----
+  {
+    const u32 w = tid >> 5;
+    if (w == 0) { u32 r = lookback_warp(st_first, tile, tot_f, OpMax()); if (lane_id() == 0) s_cf = r; }
+    else if (w == 1) { u32 r = lookback_warp(st_new, tile, tot_n, OpMax()); if (lane_id() == 0) s_cn = r; }
+    else if (w == 2) { u32 r = lookback_warp(st_cnt, tile, tot_c, OpAdd()); if (lane_id() == 0) s_cc = r; }
+  }
+  __syncthreads();
+  u32 run_f = max(s_cf, ex_f), run_n = max(s_cn, ex_n), run_c = s_cc + ex_c;
+  if (tile == ntiles - 1 && tid == 0) *next_count = s_cc + tot_c;
+  // ---- outputs ----
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; j++) {
+    const u32 l = tid * RR_ITEMS + j + 1;
+    const u32 q = q0 + tid * RR_ITEMS + j;
+    run_f = max(run_f, vf[j]);
+    run_n = max(run_n, vn[j]);
+    if (sv[l]) {
+      const u32 firstq = run_f - 1, lastnew = run_n - 1;
+      const u32 g = vals[q];
+      u32 ghead;
+      if (INIT) ghead = q & ~SEG_MASK; else ghead = (u32)(sk[l] >> SEG_SHIFT);
+      const u32 newhead = ghead + (lastnew - firstq);
+      if (!INIT) SA[ghead + (q - firstq)] = g;  // INIT: SA is the sorted value array itself
+      rank[g] = newhead & SEG_MASK;
+      if (nc[j]) { next_head[run_c] = newhead; next_idx[run_c] = g; }
+    }
+    run_c += nc[j];
+  }
+}
+
+// key64 = head << 20 | rank of the rotation h further on (or n-1-i for the final tie-break).
+__global__ void k_gather(const u32* __restrict__ head, const u32* __restrict__ idx, u32 M, const u32* __restrict__ rank,
+                         const u32* __restrict__ seg_n, u32 h, int tiebreak, u64* __restrict__ key_out, u32* __restrict__ val_out) {
+  u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= M) return;
+  const u32 g = idx[q];
+  const u32 b = g >> SEG_SHIFT, i = g & SEG_MASK, n = seg_n[b];
+  u32 r2;
+  if (tiebreak) r2 = n - 1 - i;
+  else r2 = rank[(b << SEG_SHIFT) | ((i + h) % n)];
+  key_out[q] = ((u64)head[q] << SEG_SHIFT) | r2;
+  val_out[q] = g;
+}
+
+__global__ void k_emit(const u32* __restrict__ SA, const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 nslots,
+                       u8* __restrict__ U, u32* __restrict__ pidx) {
+  u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nslots) return;
+  const u32 b = q >> SEG_SHIFT, p = q & SEG_MASK, n = seg_n[b];
+  if (p >= n) return;
+  const u32 i = SA[q] & SEG_MASK;
+  U[q] = T[((size_t)b << SEG_SHIFT) | (i ? i - 1 : n - 1)];
+  if (i == 0) pidx[b] = p;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+struct RadixScratch {
+  DBuf<u32> hist, status, ticket;
+};
+
+template <typename KeyT>
+static void radix_sort(Ctx& c, KeyT*& kin, u32*& vin, KeyT*& kout, u32*& vout, const u32* d_seg_n, u32 nseg, u32 seg_shift,
+                       u32 max_seg_n, u32 begin_bit, u32 npass, bool iota_first, u64 total_elems) {
+  if (npass == 0 || total_elems == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<u32>)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<u64>)));
+    attr_set = true;
+  }
+  const u32 tps = (max_seg_n + RP_TILE - 1) / RP_TILE;
+  const u32 htps = (max_seg_n + RH_TILE - 1) / RH_TILE;
+  const size_t ntiles = (size_t)tps * nseg;
+  DBuf<u32> hist(c, (size_t)nseg * npass * RADIX), status(c, ntiles * RADIX), ticket(c, 1);
+  CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)nseg * npass * RADIX * 4, c.stream));
+  k_radix_hist<KeyT><<<htps * nseg, RH_THREADS, 0, c.stream>>>(kin, d_seg_n, htps, seg_shift, hist, npass, begin_bit);
+  KLAUNCH(c); KCHECK();
+  c.stats.bwt_bytes += total_elems * sizeof(KeyT);
+  for (u32 p = 0; p < npass; p++) {
+    CUDA_CHECK(cudaMemsetAsync(status, 0, ntiles * RADIX * 4, c.stream));
+    CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+    const int iota = (iota_first && p == 0) ? 1 : 0;
+    size_t ev = c.begin(ST_RADIX);
+    k_radix_pass<KeyT><<<(unsigned)ntiles, RP_THREADS, sizeof(RadixSmem<KeyT>), c.stream>>>(
+        kin, vin, kout, vout, d_seg_n, tps, seg_shift, hist, npass, p, begin_bit + p * RADIX_BITS, ticket, status, iota);
+    c.end(ev);
+    KLAUNCH(c); KCHECK();
+    const u64 bytes = total_elems * (2 * sizeof(KeyT) + (iota ? 4 : 8));
+    c.stats.radix_launches++;
+    c.stats.radix_bytes += bytes;
+    c.stats.bwt_bytes += bytes;
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  // result is in (kin, vin) after the swaps
+}
+
+static u32 bits_for(u32 maxval) {  // number of bits needed to represent values 0..maxval
+  u32 b = 0;
+  while (maxval) { b++; maxval >>= 1; }
+  return b;
+}
+
+// Forward cyclic BWT of `nblk` blocks in the slot layout.  d_T/d_U: u8[nblk << 20];
+// d_n: device u32[nblk]; h_n: host copy; d_pidx: device u32[nblk].
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx) {
+  if (nblk == 0) return;
+  u32 n_max = 0; u64 n_total = 0;
+  for (u32 b = 0; b < nblk; b++) { n_max = h_n[b] > n_max ? h_n[b] : n_max; n_total += h_n[b]; }
+  if (n_total == 0) return;
+  const u32 nslots = nblk << SEG_SHIFT;
+  DBuf<u32> keyA(c, nslots), keyB(c, nslots), valA(c, nslots), valB(c, nslots), rank(c, nslots);
+  DBuf<u32> headA(c, n_total), idxA(c, n_total), cnt(c, 1), ticket(c, 1);
+  const u32 rr_tiles_init = (nslots + RR_TILE - 1) / RR_TILE;
+  DBuf<u64> st(c, (size_t)3 * rr_tiles_init);
+  u32 *kin = keyA, *kout = keyB, *vin = valA, *vout = valB;
+
+  k_build_keys<<<(nslots + 255) / 256, 256, 0, c.stream>>>(d_T, d_n, nslots, kin);
+  KLAUNCH(c); KCHECK();
+  c.stats.bwt_bytes += n_total * 5;
+  radix_sort<u32>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 0, 4, true, n_total);
+  // kin/vin now hold the sorted keys / suffix ids; vin doubles as the suffix array
+  u32* SA = vin;
+  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4, c.stream));
+  k_rerank<true><<<rr_tiles_init, RR_THREADS, 0, c.stream>>>(kin, nullptr, vin, d_n, nslots, SA, rank, headA, idxA, cnt, ticket,
+                                                            st.p, st.p + rr_tiles_init, st.p + 2 * (size_t)rr_tiles_init, rr_tiles_init);
+  KLAUNCH(c); KCHECK();
+  c.stats.bwt_bytes += n_total * (8 + 4);
+  u32 M = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&M, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+
+  if (M > 0) {
+    // the initial-sort key buffers are free now; the rounds need 64-bit keys for at most M records
+    DBuf<u64> k64A(c, M), k64B(c, M);
+    DBuf<u32> v64A(c, M), v64B(c, M), headB(c, M), idxB(c, M);
+    u32 *hcur = headA, *icur = idxA, *hnext = headB, *inext = idxB;
+    const u32 keybits = SEG_SHIFT + bits_for(nslots - 1);
+    const u32 npass = (keybits + RADIX_BITS - 1) / RADIX_BITS;
+    DBuf<u32> dM(c, 1);
+    u32 h = 4, rounds = 0;
+    while (M > 0) {
+      const int tiebreak = h >= n_max ? 1 : 0;
+      rounds++;
+      u64* kin64 = k64A; u64* kout64 = k64B; u32* vin64 = v64A; u32* vout64 = v64B;
+      k_gather<<<(M + 255) / 256, 256, 0, c.stream>>>(hcur, icur, M, rank, d_n, h, tiebreak, kin64, vin64);
+      KLAUNCH(c); KCHECK();
+      c.stats.bwt_bytes += (u64)M * (8 + 4 + 12);
+      CUDA_CHECK(cudaMemcpyAsync(dM, &M, 4, cudaMemcpyHostToDevice, c.stream));
+      radix_sort<u64>(c, kin64, vin64, kout64, vout64, dM, 1, 31, M, 0, npass, false, M);
+      const u32 tiles = (M + RR_TILE - 1) / RR_TILE;
+      CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
+      CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+      CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4, c.stream));
+      k_rerank<false><<<tiles, RR_THREADS, 0, c.stream>>>(nullptr, kin64, vin64, d_n, M, SA, rank, hnext, inext, cnt, ticket, st.p,
+                                                         st.p + rr_tiles_init, st.p + 2 * (size_t)rr_tiles_init, tiles);
+      KLAUNCH(c); KCHECK();
+      c.stats.bwt_bytes += (u64)M * (12 + 4 + 4 + 8);
+      u32 Mn = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&Mn, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      if (tiebreak && Mn != 0) throw B2Error{-200, "internal error: suffix sort did not converge"};
+      M = Mn;
+      std::swap(hcur, hnext);
+      std::swap(icur, inext);
+      if (h < (1u << 30)) h <<= 1;
+    }
+    if (rounds > c.stats.bwt_rounds) c.stats.bwt_rounds = rounds;
+  }
+  k_emit<<<(nslots + 255) / 256, 256, 0, c.stream>>>(SA, d_T, d_n, nslots, d_U, d_pidx);
+  KLAUNCH(c); KCHECK();
+  c.stats.bwt_bytes += n_total * 6;
+}

@@ -1,0 +1,90 @@
+// ctx.h -- per-process library context: device, stream, stream-ordered allocations, timers.
+#pragma once
+#include <vector>
+#include <utility>
+#include <mutex>
+#include "common.cuh"
+#include "../../include/b2bz.h"
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  b2_stats stats;
+  std::vector<EventPair> ev_pool;   // reusable events
+  size_t ev_used = 0;
+  std::vector<std::pair<int, size_t>> ev_tags;  // (stage id, pool index) recorded in the current call
+  std::vector<b2_block_trace> trace;
+  u32 bwt_batch = 64;  // bzip2 blocks sorted together in one segmented batch
+  bool timing = true;
+
+  void* dalloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    CUDA_CHECK(cudaMallocAsync(&p, bytes, stream));
+    return p;
+  }
+  void dfree(void* p) {
+    if (p) cudaFreeAsync(p, stream);
+  }
+  template <typename T>
+  T* dalloc_t(size_t count) { return (T*)dalloc(count * sizeof(T)); }
+
+  // stage timing with CUDA events on the library stream
+  size_t begin(int stage) {
+    if (!timing) return 0;
+    if (ev_used >= ev_pool.size()) {
+      EventPair e;
+      CUDA_CHECK(cudaEventCreate(&e.a));
+      CUDA_CHECK(cudaEventCreate(&e.b));
+      ev_pool.push_back(e);
+    }
+    size_t i = ev_used++;
+    ev_tags.push_back({stage, i});
+    CUDA_CHECK(cudaEventRecord(ev_pool[i].a, stream));
+    return i;
+  }
+  void end(size_t i) {
+    if (!timing) return;
+    CUDA_CHECK(cudaEventRecord(ev_pool[i].b, stream));
+  }
+  void reset_call() {
+    ev_used = 0;
+    ev_tags.clear();
+    memset(&stats, 0, sizeof stats);
+  }
+  void collect();  // after the final sync: fold event pairs into stats
+};
+
+enum Stage {
+  ST_TOTAL = 0, ST_H2D, ST_D2H, ST_RLE1, ST_BWT, ST_MTF, ST_HUFF, ST_PACK,
+  ST_SCAN, ST_HDEC, ST_UNMTF, ST_IBWT, ST_UNRLE, ST_RADIX, ST_COUNT
+};
+
+struct StageScope {
+  Ctx& c; size_t i;
+  StageScope(Ctx& c_, int stage) : c(c_), i(c_.begin(stage)) {}
+  ~StageScope() { try { c.end(i); } catch (...) {} }
+};
+
+// RAII device buffer (stream-ordered)
+template <typename T>
+struct DBuf {
+  Ctx* c = nullptr; T* p = nullptr; size_t n = 0;
+  DBuf() {}
+  DBuf(Ctx& c_, size_t count) : c(&c_), p(c_.dalloc_t<T>(count)), n(count) {}
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) : c(o.c), p(o.p), n(o.n) { o.p = nullptr; }
+  DBuf& operator=(DBuf&& o) { release(); c = o.c; p = o.p; n = o.n; o.p = nullptr; return *this; }
+  void alloc(Ctx& c_, size_t count) { release(); c = &c_; p = c_.dalloc_t<T>(count); n = count; }
+  void release() { if (p && c) c->dfree(p); p = nullptr; }
+  ~DBuf() { release(); }
+  operator T*() const { return p; }
+};
+
+#define KLAUNCH(ctx) ((ctx).stats.kernel_launches++)
+#define KCHECK() CUDA_CHECK(cudaGetLastError())

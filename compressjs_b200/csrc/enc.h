@@ -1,0 +1,49 @@
+// enc.h -- shared declarations of the encode stages.
+#pragma once
+#include "ctx.h"
+
+// One bzip2 block as cut by the RLE1 stage (lib/Bzip2.js:636-667 readBlock).
+struct BlkInfo {
+  u64 s;    // first raw byte
+  u64 e;    // one past the last raw byte consumed
+  u64 b;    // end of the (re-phased) run the block starts in; == s when the block starts on a run start
+  u64 Wb;   // RLE1 output bytes produced by raw[0,b) under maximal-run phases
+  u32 ofs;  // RLE1 bytes produced by raw[s,b) with a fresh run state at s
+  u32 n;    // post-RLE1 length of the block (<= blockSize)
+};
+
+struct Rle1Plan {
+  DBuf<u32> tile_carry;   // per raw tile: length (mod 255) of the run entering the tile
+  DBuf<u64> tile_prefix;  // per raw tile: W(tile start)
+  DBuf<BlkInfo> blocks;   // device block table
+  std::vector<BlkInfo> h_blocks;
+  size_t nblocks = 0;
+  u64 ntiles = 0;
+};
+
+#define RLE_TILE 4096
+
+void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan);
+// materialise blocks [first, first+count) of the plan into the slot layout at d_T (u8[count<<20]);
+// d_n receives their lengths, d_crc their CRCs.
+void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc);
+
+// MTF + RLE2 (lib/Bzip2.js:743-815): U (slot layout) -> symbols u16 (slot layout), m, freq, used map
+void mtf_rle2_batch(Ctx& c, const u8* d_T, const u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u16* d_sym, u32* d_m, u32* d_freq /*[nblk][258]*/,
+                    u32* d_used /*[nblk][8]*/);
+
+#define HUFF_MAXSYM 258
+#define HUFF_MAXGROUPS 6
+#define HUFF_GROUP 50
+// per-block result of the Huffman stage
+struct HuffBlk {
+  u32 ngroups, nsel, alpha, m;
+  u64 body_bits;  // bits of the block from the 48-bit magic through the last Huffman code
+  u8 len[HUFF_MAXGROUPS][HUFF_MAXSYM + 6];
+};
+// Table optimisation (lib/Bzip2.js:671-733, 826-843 + HuffmanAllocator.js): selectors u8 (slot layout >> 0, stride SEL_STRIDE)
+#define SEL_STRIDE 18432
+void huffman_batch(Ctx& c, const u16* d_sym, const u32* d_m, const u32* d_freq, const u32* d_used, u32 nblk, u8* d_sel, HuffBlk* d_hb);
+// bit packing of blocks at their final bit offsets (lib/Bzip2.js:740-741,749-758,847-874)
+void pack_batch(Ctx& c, const u16* d_sym, const u8* d_sel, const HuffBlk* d_hb, const u32* d_used, const u32* d_pidx, const u32* d_crc,
+                const u64* d_bitoff, u32 nblk, u32* d_out_words);

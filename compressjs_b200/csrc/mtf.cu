@@ -1,0 +1,307 @@
+// mtf.cu -- symbol map, move-to-front and zero-run (RUNA/RUNB) coding of the BWT output.
+//
+// Reference: lib/Bzip2.js:743-815 (compressBlock: used[] map, MTF list M, RLE2 emit) and
+// lib/Bzip2.js:53-60 (mtf()).  The reference walks the block byte by byte with a linear
+// search in M.  Parallel form:
+//   k_used        : 256-bit "byte occurs in block" map per block
+//   k_mtf_lastpos : per 4 KiB chunk, last position of every byte value inside the chunk
+//   k_mtf_prefix  : per block, running max over the chunks -> last occurrence BEFORE each chunk;
+//                   the MTF list at a chunk start is "bytes by most recent occurrence, then the
+//                   not-yet-seen used bytes in ascending order" (the initial list M)
+//   k_mtf_ranks   : one warp per chunk keeps the 256-entry list in registers (8 entries per
+//                   lane), finds a byte with byte-wise SIMD compares + ballot and rotates the
+//                   prefix with shuffles -> MTF rank per byte
+//   k_rle2        : zero ranks form runs -> bijective base-2 RUNA/RUNB digits; chained scans
+//                   (run starts, output offsets) across tiles; symbols u16 + histogram + EOB
+#include "enc.h"
+
+#define MTF_CHUNK 4096
+
+__global__ void __launch_bounds__(256) k_used(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 tiles_per_seg, u32* __restrict__ used) {
+  __shared__ u32 f[8];
+  if (threadIdx.x < 8) f[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 seg = blockIdx.x / tiles_per_seg, lt = blockIdx.x % tiles_per_seg;
+  const u32 n = seg_n[seg];
+  const u32 start = lt * (256 * 64);
+  if (start >= n) return;
+  const u8* p = U + ((size_t)seg << SEG_SHIFT);
+  u32 loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (u32 i = start + threadIdx.x; i < min(n, start + 256 * 64); i += 256) {
+    u8 c = p[i];
+    loc[c >> 5] |= 1u << (c & 31);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (loc[k]) atomicOr(&f[k], loc[k]);
+  __syncthreads();
+  if (threadIdx.x < 8 && f[threadIdx.x]) atomicOr(&used[seg * 8 + threadIdx.x], f[threadIdx.x]);
+}
+
+// lastpos[(seg*cps + chunk)*256 + c] = (last position of byte c inside the chunk) + 1, 0 if none
+__global__ void __launch_bounds__(256) k_mtf_lastpos(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, u32* __restrict__ lastpos) {
+  __shared__ u32 last[256];
+  last[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 seg = blockIdx.x / cps, ch = blockIdx.x % cps;
+  const u32 n = seg_n[seg];
+  const u32 start = ch * MTF_CHUNK;
+  if (start < n) {
+    const u8* p = U + ((size_t)seg << SEG_SHIFT);
+    const u32 end = min(n, start + MTF_CHUNK);
+    for (u32 i = start + threadIdx.x; i < end; i += 256) atomicMax(&last[p[i]], i + 1);
+  }
+  __syncthreads();
+  lastpos[(size_t)blockIdx.x * 256 + threadIdx.x] = last[threadIdx.x];
+}
+
+// in place: lastpos[chunk] := max over earlier chunks (exclusive)
+__global__ void __launch_bounds__(256) k_mtf_prefix(const u32* __restrict__ seg_n, u32 cps, u32* __restrict__ lastpos) {
+  const u32 seg = blockIdx.x;
+  const u32 n = seg_n[seg];
+  const u32 nch = (n + MTF_CHUNK - 1) / MTF_CHUNK;
+  u32 run = 0;
+  for (u32 ch = 0; ch < nch; ch++) {
+    u32* p = lastpos + ((size_t)seg * cps + ch) * 256 + threadIdx.x;
+    u32 t = *p;
+    *p = run;
+    run = max(run, t);
+  }
+}
+
+#define MR_WARPS 8
+__global__ void __launch_bounds__(MR_WARPS * 32)
+k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, const u32* __restrict__ lastpos,
+            const u32* __restrict__ used, u8* __restrict__ R, u32 nblk) {
+  __shared__ u32 skey[MR_WARPS][256];
+  __shared__ __align__(8) u8 slist[MR_WARPS][256];
+  const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 gchunk = blockIdx.x * MR_WARPS + w;
+  const u32 seg = gchunk / cps, ch = gchunk % cps;
+  // (every warp of the grid maps to a valid (seg, chunk) pair or exits as a whole)
+  if (seg >= nblk) return;
+  const u32 n = seg_n[seg];
+  const u32 start = ch * MTF_CHUNK;
+  if (start >= n) return;
+  const u32 count = min((u32)MTF_CHUNK, n - start);
+  // ---- list at the chunk start ----
+  const u32* lp = lastpos + (size_t)gchunk * 256;
+  u32 mykey[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const u32 c = lane * 8 + i;
+    const u32 l = lp[c];
+    const bool isused = (used[seg * 8 + (c >> 5)] >> (c & 31)) & 1;
+    u32 key;
+    if (l) key = 0x40000000u | l;          // seen: most recent first
+    else if (isused) key = 0x200u + (255u - c);  // not seen yet: ascending byte value
+    else key = 255u - c;                    // never occurs: behind everything
+    mykey[i] = key;
+    skey[w][c] = key;
+  }
+  __syncwarp();
+  u32 rk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (u32 c2 = 0; c2 < 256; c2++) {
+    const u32 k2 = skey[w][c2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rk[i] += (k2 > mykey[i]) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) slist[w][rk[i]] = (u8)(lane * 8 + i);
+  __syncwarp();
+  u32 lo = reinterpret_cast<const u32*>(&slist[w][0])[lane * 2];
+  u32 hi = reinterpret_cast<const u32*>(&slist[w][0])[lane * 2 + 1];
+  // ---- walk the chunk, 128 bytes per outer step ----
+  const u8* src = U + ((size_t)seg << SEG_SHIFT) + start;
+  u8* dst = R + ((size_t)seg << SEG_SHIFT) + start;
+  for (u32 base = 0; base < count; base += 128) {
+    u32 word = 0;
+    {
+      const u32 o = base + lane * 4;
+      if (o + 4 <= count) word = *reinterpret_cast<const u32*>(src + o);  // start and slots are 4-aligned
+      else {
+        for (u32 b = 0; b < 4; b++) if (o + b < count) word |= (u32)src[o + b] << (8 * b);
+      }
+    }
+    u32 outw = 0;
+    const u32 lim = min(128u, count - base);
+    for (u32 idx = 0; idx < lim; idx++) {
+      const u32 wsrc = __shfl_sync(FULL_MASK, word, idx >> 2);
+      const u32 c = (wsrc >> ((idx & 3) * 8)) & 255u;
+      const u32 cc = c * 0x01010101u;
+      const u32 m0 = __vcmpeq4(lo, cc), m1 = __vcmpeq4(hi, cc);
+      const u32 bal = __ballot_sync(FULL_MASK, (m0 | m1) != 0);
+      const u32 fl = __ffs(bal) - 1;
+      const u32 mypos = m0 ? ((__ffs(m0) - 1) >> 3) : (4 + ((__ffs(m1) - 1) >> 3));
+      const u32 pos = __shfl_sync(FULL_MASK, mypos, fl);
+      const u32 j = fl * 8 + pos;
+      if (j != 0) {
+        u32 carry = __shfl_up_sync(FULL_MASK, hi >> 24, 1);
+        if (lane == 0) carry = c;
+        u64 v = ((u64)hi << 32) | lo;
+        if (lane < fl) {
+          v = (v << 8) | carry;
+        } else if (lane == fl) {
+          const u64 lowmask = (1ull << (8 * pos)) - 1;
+          const u64 highmask = pos == 7 ? 0ull : ~((1ull << (8 * (pos + 1))) - 1);
+          v = (v & highmask) | (((v & lowmask) << 8) | carry);
+        }
+        lo = (u32)v; hi = (u32)(v >> 32);
+      }
+      if (lane == (idx >> 2)) outw |= j << ((idx & 3) * 8);
+    }
+    {
+      const u32 o = base + lane * 4;
+      if (o + 4 <= count) *reinterpret_cast<u32*>(dst + o) = outw;
+      else {
+        for (u32 b = 0; b < 4; b++) if (o + b < count) dst[o + b] = (u8)(outw >> (8 * b));
+      }
+    }
+  }
+}
+
+// ---- RLE2 ---------------------------------------------------------------------------------
+#define R2_THREADS 256
+#define R2_ITEMS 8
+#define R2_TILE (R2_THREADS * R2_ITEMS)
+
+__global__ void __launch_bounds__(R2_THREADS)
+k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const u32* __restrict__ used, u16* __restrict__ A,
+       u32* __restrict__ m_out, u32* __restrict__ freq, u32* ticket, u64* st_run, u64* st_off) {
+  __shared__ u32 hist[HUFF_MAXSYM];
+  __shared__ u32 ws[R2_THREADS / 32 + 1];
+  __shared__ u32 s_tile, s_crun, s_coff;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (u32 i = tid; i < HUFF_MAXSYM; i += R2_THREADS) hist[i] = 0;
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 seg = tile / tps, lt = tile % tps;
+  const u32 n = seg_n[seg];
+  const u32 start = lt * R2_TILE;
+  if (start >= n) return;
+  const u8* r = R + ((size_t)seg << SEG_SHIFT);
+  u16* a = A + ((size_t)seg << SEG_SHIFT);
+  const u32 p0 = start + tid * R2_ITEMS;
+  u8 v[R2_ITEMS + 1];
+#pragma unroll
+  for (int j = 0; j <= R2_ITEMS; j++) v[j] = (p0 + j < n) ? r[p0 + j] : 1;  // beyond the end behaves like "non zero"
+  // last non-zero position (+1) among this thread's items
+  u32 lastnz = 0;
+#pragma unroll
+  for (int j = 0; j < R2_ITEMS; j++)
+    if (p0 + j < n && v[j] != 0) lastnz = p0 + j + 1;
+  // exclusive max scan over threads
+  u32 inc = warp_incl_max(lastnz);
+  u32 exw = __shfl_up_sync(FULL_MASK, inc, 1);
+  if (lane_id() == 0) exw = 0;
+  if (lane_id() == 31) ws[tid >> 5] = inc;
+  __syncthreads();
+  if (tid < 32) {
+    u32 x = (tid < R2_THREADS / 32) ? ws[tid] : 0u;
+    u32 xi = warp_incl_max(x);
+    u32 xe = __shfl_up_sync(FULL_MASK, xi, 1);
+    if (tid == 0) xe = 0;
+    if (tid < R2_THREADS / 32) ws[tid] = xe;
+    if (tid == R2_THREADS / 32 - 1) ws[R2_THREADS / 32] = xi;
+  }
+  __syncthreads();
+  const u32 ex_run = max(exw, ws[tid >> 5]);
+  const u32 tot_run = ws[R2_THREADS / 32];
+  __syncthreads();
+  if (tid < 32) {
+    u32 rr = lookback_warp(st_run + (size_t)seg * tps, lt, tot_run, OpMax());
+    if (tid == 0) s_crun = rr;
+  }
+  __syncthreads();
+  u32 rs = max(s_crun, ex_run);  // run start candidate = position after the last non-zero before p
+  // per item emission counts
+  u32 cnt[R2_ITEMS];
+  u32 rlen[R2_ITEMS];
+  u32 sum = 0;
+#pragma unroll
+  for (int j = 0; j < R2_ITEMS; j++) {
+    const u32 p = p0 + j;
+    cnt[j] = 0; rlen[j] = 0;
+    if (p < n) {
+      if (v[j] != 0) { cnt[j] = 1; rs = p + 1; }
+      else if (v[j + 1] != 0 || p + 1 == n) {  // the zero run ends here
+        const u32 L = p - rs + 1;
+        rlen[j] = L;
+        cnt[j] = 31 - __clz(L + 1);
+      }
+    }
+    sum += cnt[j];
+  }
+  u32 tot_off;
+  const u32 ex_off = block_excl_add<R2_THREADS, u32>(sum, ws, &tot_off);
+  if (tid < 32) {
+    u32 oo = lookback_warp(st_off + (size_t)seg * tps, lt, tot_off, OpAdd());
+    if (tid == 0) s_coff = oo;
+  }
+  __syncthreads();
+  u32 o = s_coff + ex_off;
+  u32 alpha = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) alpha += __popc(used[seg * 8 + k]);
+#pragma unroll
+  for (int j = 0; j < R2_ITEMS; j++) {
+    const u32 p = p0 + j;
+    if (p < n) {
+      if (v[j] != 0) {
+        const u32 s = (u32)v[j] + 1;
+        a[o] = (u16)s;
+        atomicAdd(&hist[s], 1u);
+      } else if (rlen[j]) {
+        u32 L = rlen[j], oo = o;
+        while (L) {  // lib/Bzip2.js:783-794 emitLastRun
+          if (L & 1) { a[oo++] = 0; atomicAdd(&hist[0], 1u); L -= 1; }
+          else { a[oo++] = 1; atomicAdd(&hist[1], 1u); L -= 2; }
+          L >>= 1;
+        }
+      }
+      o += cnt[j];
+      if (p + 1 == n) {  // end of block symbol
+        a[o] = (u16)(alpha + 1);
+        atomicAdd(&hist[alpha + 1], 1u);
+        m_out[seg] = o + 1;
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 i = tid; i < HUFF_MAXSYM; i += R2_THREADS)
+    if (hist[i]) atomicAdd(&freq[(size_t)seg * HUFF_MAXSYM + i], hist[i]);
+}
+
+void mtf_rle2_batch(Ctx& c, const u8* d_T, const u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u16* d_sym, u32* d_m, u32* d_freq,
+                    u32* d_used) {
+  (void)d_T;
+  u32 n_max = 0;
+  for (u32 b = 0; b < nblk; b++) n_max = h_n[b] > n_max ? h_n[b] : n_max;
+  if (n_max == 0) return;
+  const u32 utiles = (n_max + 256 * 64 - 1) / (256 * 64);
+  CUDA_CHECK(cudaMemsetAsync(d_used, 0, (size_t)nblk * 8 * 4, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(d_freq, 0, (size_t)nblk * HUFF_MAXSYM * 4, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(d_m, 0, (size_t)nblk * 4, c.stream));
+  k_used<<<utiles * nblk, 256, 0, c.stream>>>(d_U, d_n, utiles, d_used);
+  KLAUNCH(c); KCHECK();
+  const u32 cps = (n_max + MTF_CHUNK - 1) / MTF_CHUNK;
+  DBuf<u32> lastpos(c, (size_t)nblk * cps * 256);
+  DBuf<u8> R(c, (size_t)nblk << SEG_SHIFT);
+  k_mtf_lastpos<<<cps * nblk, 256, 0, c.stream>>>(d_U, d_n, cps, lastpos);
+  KLAUNCH(c); KCHECK();
+  k_mtf_prefix<<<nblk, 256, 0, c.stream>>>(d_n, cps, lastpos);
+  KLAUNCH(c); KCHECK();
+  {
+    const u32 chunks = cps * nblk;
+    k_mtf_ranks<<<(chunks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, c.stream>>>(d_U, d_n, cps, lastpos, d_used, R, nblk);
+    KLAUNCH(c); KCHECK();
+  }
+  const u32 tps = (n_max + R2_TILE - 1) / R2_TILE;
+  DBuf<u64> st(c, (size_t)2 * nblk * tps);
+  DBuf<u32> ticket(c, 1);
+  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)2 * nblk * tps * 8, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+  k_rle2<<<tps * nblk, R2_THREADS, 0, c.stream>>>(R, d_n, tps, d_used, d_sym, d_m, d_freq, ticket, st.p, st.p + (size_t)nblk * tps);
+  KLAUNCH(c); KCHECK();
+}

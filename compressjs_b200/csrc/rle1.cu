@@ -1,0 +1,627 @@
+// rle1.cu -- bzip2 initial run-length encoding, block cutting and per-block CRC32 on the GPU.
+//
+// Reference: lib/Bzip2.js:636-667 (readBlock) + lib/CRC32.js:72-103.  The reference is a
+// byte-serial state machine whose run state resets at every block boundary, and the boundary
+// is measured in OUTPUT bytes.  Parallel form used here:
+//
+//   w(i) = RLE1 bytes emitted when raw byte i is consumed = 1,1,1,2,0,0,... for run phases
+//          1,2,3,4,5..255 (the 4th byte also emits the count byte), phases restart every 255.
+//   A  k_rle_summary : per 4 KiB raw tile, assuming maximal runs: first/last byte, leading /
+//                      trailing run length, sum of w behind the leading run.
+//   B  k_rle_scan    : one CTA scans the tile summaries -> per tile the run length carried in
+//                      (mod 255) and W(tile start) = total output before the tile.
+//   C  k_rle_blocks  : one CTA walks the blocks: a block that starts in the middle of a run
+//                      re-phases that run (fresh state), everything behind it follows W; the
+//                      end is found by a 256-ary search over W(tile) plus one in-tile scan.
+//   D  k_rle_emit    : all blocks in parallel: every raw byte computes its output position and
+//                      writes its literal (+ count byte) into the slot layout.
+//   CRC k_crc_pieces : 256-byte pieces, pure polynomial remainders shifted by x^(8*bytes after)
+//                      and XOR-combined per block (CRC is linear), then the init/final XOR.
+#include "enc.h"
+
+#define RT_THREADS 256
+#define RT_PER 16  // RLE_TILE / RT_THREADS
+
+struct TileSum {
+  u32 lead, trail, rest;
+  u8 fc, lc, allsame, pad;
+};
+
+// RLE1 bytes produced by c bytes of one run consumed from a fresh state.
+__host__ __device__ __forceinline__ u64 outfresh(u64 c) {
+  u64 q = c / 255, r = c % 255;
+  return 5 * q + (r <= 3 ? r : 5);
+}
+// smallest c with outfresh(c) >= target (target >= 1)
+__host__ __device__ __forceinline__ u64 cneed(u64 target) {
+  u64 q = (target - 1) / 5, rem = target - 5 * q;  // rem in 1..5
+  return 255 * q + (rem <= 3 ? rem : 4);
+}
+__device__ __forceinline__ u32 w_of_dist(u32 d) {
+  u32 r = d % 255 + 1;
+  return r <= 3 ? 1u : (r == 4 ? 2u : 0u);
+}
+
+// Per-thread view of one raw tile under maximal-run phases.
+struct TileView {
+  u8 by[RT_PER];
+  u8 w[RT_PER];
+  u32 cnt;    // valid bytes of this thread
+  u32 excl;   // sum of w over the tile positions before this thread's first byte
+  u32 total;  // sum of w over the tile
+  u32 first_start;  // smallest position > 0 that starts a run (tile length when none)
+  u32 last_start;   // largest position that starts a run (0 when the tile is one run)
+  u32 len;          // valid bytes in the tile
+};
+
+struct TileScratch {
+  u32 ws[RT_THREADS / 32 + 1];
+  u8 lastb[RT_THREADS];
+  u32 red[RT_THREADS / 32];
+};
+
+__device__ __forceinline__ u32 block_excl_max256(u32 v, u32* ws) {
+  u32 inc = warp_incl_max(v);
+  u32 exw = __shfl_up_sync(FULL_MASK, inc, 1);
+  if (lane_id() == 0) exw = 0;
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) ws[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    u32 x = (lane_id() < RT_THREADS / 32) ? ws[lane_id()] : 0u;
+    u32 xi = warp_incl_max(x);
+    u32 xe = __shfl_up_sync(FULL_MASK, xi, 1);
+    if (lane_id() == 0) xe = 0;
+    if (lane_id() < RT_THREADS / 32) ws[lane_id()] = xe;
+  }
+  __syncthreads();
+  u32 c = ws[w];
+  __syncthreads();
+  return exw > c ? exw : c;
+}
+__device__ __forceinline__ u32 block_min256(u32 v, u32* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL_MASK, v, o));
+  if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  u32 r = red[0];
+#pragma unroll
+  for (int i = 1; i < RT_THREADS / 32; i++) r = min(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ u32 block_max256(u32 v, u32* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, o));
+  if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  u32 r = red[0];
+#pragma unroll
+  for (int i = 1; i < RT_THREADS / 32; i++) r = max(r, red[i]);
+  __syncthreads();
+  return r;
+}
+
+// Whole CTA (RT_THREADS threads).  carry = run length (mod 255) entering the tile.
+__device__ void tile_view(const u8* __restrict__ in, u64 N, u64 tstart, u32 carry, TileScratch& sc, TileView& v) {
+  const u32 tid = threadIdx.x;
+  const u64 remain = N - tstart;
+  v.len = remain < RLE_TILE ? (u32)remain : RLE_TILE;
+  const u32 pos0 = tid * RT_PER;
+  v.cnt = pos0 >= v.len ? 0 : min((u32)RT_PER, v.len - pos0);
+  const u8* p = in + tstart + pos0;
+  if (v.cnt == RT_PER && (((size_t)p) & 15) == 0) {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    u32 a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < RT_PER; j++) v.by[j] = (u8)(a[j >> 2] >> ((j & 3) * 8));
+  } else {
+#pragma unroll
+    for (int j = 0; j < RT_PER; j++) v.by[j] = (j < (int)v.cnt) ? p[j] : 0;
+  }
+  sc.lastb[tid] = v.by[RT_PER - 1];
+  __syncthreads();
+  const u8 prev0 = tid ? sc.lastb[tid - 1] : 0;
+  // run starts inside the tile (position 0 always counts as one; its phase comes from `carry`)
+  u32 smask = 0, last_local = 0, first_local = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < RT_PER; j++) {
+    if (j < (int)v.cnt) {
+      const u32 pos = pos0 + j;
+      const u8 pb = j ? v.by[j - 1] : prev0;
+      const bool st = (pos == 0) || (v.by[j] != pb);
+      if (st) {
+        smask |= 1u << j;
+        last_local = pos + 1;
+        if (pos > 0 && first_local == 0xffffffffu) first_local = pos;
+      }
+    }
+  }
+  const u32 ex = block_excl_max256(last_local, sc.ws);  // (last start before this thread) + 1
+  u32 rs = ex ? ex - 1 : 0;
+  u32 sum = 0;
+#pragma unroll
+  for (int j = 0; j < RT_PER; j++) {
+    u32 ww = 0;
+    if (j < (int)v.cnt) {
+      const u32 pos = pos0 + j;
+      if (smask & (1u << j)) rs = pos;
+      const u32 d = pos - rs + (rs == 0 ? carry : 0);
+      ww = w_of_dist(d);
+    }
+    v.w[j] = (u8)ww;
+    sum += ww;
+  }
+  u32 total;
+  v.excl = block_excl_add<RT_THREADS, u32>(sum, sc.ws, &total);
+  v.total = total;
+  u32 fs = block_min256(first_local, sc.red);
+  v.first_start = fs == 0xffffffffu ? v.len : fs;
+  u32 ls = block_max256(last_local, sc.red);
+  v.last_start = ls ? ls - 1 : 0;
+}
+
+// ---- A ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_THREADS) k_rle_summary(const u8* __restrict__ in, u64 N, TileSum* __restrict__ sums) {
+  __shared__ TileScratch sc;
+  TileView v;
+  const u64 t = blockIdx.x;
+  const u64 tstart = t * RLE_TILE;
+  tile_view(in, N, tstart, 0, sc, v);
+  if (threadIdx.x == 0) {
+    TileSum s;
+    s.fc = in[tstart];
+    s.lc = in[tstart + v.len - 1];
+    s.lead = v.first_start;
+    s.allsame = v.first_start == v.len;
+    s.trail = v.len - v.last_start;
+    // total was computed with carry 0, so its leading run contributed outfresh(lead)
+    s.rest = v.total - (u32)outfresh(v.first_start);
+    s.pad = 0;
+    sums[t] = s;
+  }
+}
+
+// ---- B ---------------------------------------------------------------------------------
+// scan state: bit 63 nonempty | bit 62 allsame | fc<<24 | lc<<16 | trail255<<8 | len255
+__device__ __forceinline__ u64 rs_make(bool allsame, u32 fc, u32 lc, u32 trail, u32 len) {
+  return (1ull << 63) | ((u64)allsame << 62) | ((u64)fc << 24) | ((u64)lc << 16) | ((u64)trail << 8) | (u64)len;
+}
+__device__ __forceinline__ u64 rs_combine(u64 A, u64 B) {
+  if (!(A >> 63)) return B;
+  if (!(B >> 63)) return A;
+  const bool Aall = (A >> 62) & 1, Ball = (B >> 62) & 1;
+  const u32 Afc = (A >> 24) & 255, Alc = (A >> 16) & 255, Atr = (A >> 8) & 255, Alen = A & 255;
+  const u32 Bfc = (B >> 24) & 255, Blc = (B >> 16) & 255, Btr = (B >> 8) & 255, Blen = B & 255;
+  const bool join = Alc == Bfc;
+  const u32 trail = (Ball && join) ? (Atr + Blen) % 255 : Btr;
+  return rs_make(Aall && Ball && join, Afc, Blc, trail, (Alen + Blen) % 255);
+}
+
+#define RS_THREADS 1024
+__global__ void __launch_bounds__(RS_THREADS)
+k_rle_scan(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u32* __restrict__ carry, u64* __restrict__ prefix) {
+  __shared__ u64 sa[RS_THREADS], sb[RS_THREADS];
+  const u32 tid = threadIdx.x;
+  const u64 per = (ntiles + RS_THREADS - 1) / RS_THREADS;
+  const u64 t0 = (u64)tid * per, t1 = min(ntiles, t0 + per);
+  // 1. aggregate of this thread's tiles
+  u64 agg = 0;
+  for (u64 t = t0; t < t1; t++) {
+    const TileSum s = sums[t];
+    const u64 tl = min((u64)RLE_TILE, N - t * RLE_TILE);
+    agg = rs_combine(agg, rs_make(s.allsame, s.fc, s.lc, s.trail % 255, (u32)(tl % 255)));
+  }
+  // 2. exclusive scan over threads (Hillis-Steele, operator is not commutative)
+  sa[tid] = agg;
+  __syncthreads();
+  u64* src = sa; u64* dst = sb;
+  for (u32 o = 1; o < RS_THREADS; o <<= 1) {
+    u64 x = src[tid];
+    if (tid >= o) x = rs_combine(src[tid - o], x);
+    dst[tid] = x;
+    __syncthreads();
+    u64* tmp = src; src = dst; dst = tmp;
+  }
+  u64 st = tid ? src[tid - 1] : 0;
+  __syncthreads();
+  // 3. carries + per-tile output sums (stored in prefix[] for now)
+  u64 mysum = 0;
+  for (u64 t = t0; t < t1; t++) {
+    const TileSum s = sums[t];
+    const u64 tl = min((u64)RLE_TILE, N - t * RLE_TILE);
+    u32 c = 0;
+    if ((st >> 63) && ((st >> 16) & 255) == s.fc) c = (st >> 8) & 255;
+    carry[t] = c;
+    const u64 S = outfresh((u64)c + s.lead) - outfresh(c) + s.rest;
+    prefix[t] = S;
+    mysum += S;
+    st = rs_combine(st, rs_make(s.allsame, s.fc, s.lc, s.trail % 255, (u32)(tl % 255)));
+  }
+  // 4. exclusive add scan of the thread sums
+  sa[tid] = mysum;
+  __syncthreads();
+  src = sa; dst = sb;
+  for (u32 o = 1; o < RS_THREADS; o <<= 1) {
+    u64 x = src[tid];
+    if (tid >= o) x += src[tid - o];
+    dst[tid] = x;
+    __syncthreads();
+    u64* tmp = src; src = dst; dst = tmp;
+  }
+  u64 run = tid ? src[tid - 1] : 0;
+  const u64 grand = src[RS_THREADS - 1];
+  for (u64 t = t0; t < t1; t++) {
+    const u64 S = prefix[t];
+    prefix[t] = run;
+    run += S;
+  }
+  if (tid == 0) prefix[ntiles] = grand;
+}
+
+// ---- C ---------------------------------------------------------------------------------
+struct BlocksShared {
+  TileScratch sc;
+  u64 r64;
+  u32 r32;
+};
+
+// W(x): RLE1 output of raw[0,x) under maximal phases.  Whole CTA.
+__device__ u64 eval_W(const u8* in, u64 N, const u32* carry, const u64* prefix, u64 x, BlocksShared& sh) {
+  const u64 t = x / RLE_TILE;
+  const u32 off = (u32)(x % RLE_TILE);
+  if (off == 0) return prefix[t];
+  TileView v;
+  tile_view(in, N, t * RLE_TILE, carry[t], sh.sc, v);
+  const u32 tid = threadIdx.x;
+  if (off / RT_PER == tid) {
+    u32 a = v.excl;
+    for (u32 j = 0; j < off % RT_PER; j++) a += v.w[j];
+    sh.r64 = prefix[t] + a;
+  }
+  __syncthreads();
+  u64 r = sh.r64;
+  __syncthreads();
+  return r;
+}
+
+// first position >= s whose byte differs from in[s], capped at cap.  Whole CTA.
+__device__ u64 find_run_end(const u8* in, u64 s, u64 cap, BlocksShared& sh) {
+  const u8 ch = in[s];
+  for (u64 base = s; base < cap; base += RLE_TILE) {
+    const u64 p0 = base + (u64)threadIdx.x * RT_PER;
+    u32 found = 0xffffffffu;
+    for (u32 j = 0; j < RT_PER; j++) {
+      const u64 p = p0 + j;
+      if (p < cap && in[p] != ch) { found = (u32)(p - base); break; }
+    }
+    const u32 f = block_min256(found, sh.sc.red);
+    if (f != 0xffffffffu) return base + f;
+  }
+  return cap;
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ carry, const u64* __restrict__ prefix, u64 ntiles,
+             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks) {
+  __shared__ BlocksShared sh;
+  const u32 tid = threadIdx.x;
+  const u64 Wtotal = prefix[ntiles];
+  u64 s = 0, Ws = 0;
+  bool Ws_valid = true;  // W(0) = 0
+  u32 k = 0;
+  while (s < N && k < maxblocks) {
+    BlkInfo bi;
+    bi.s = s;
+    const bool midrun = s > 0 && in[s - 1] == in[s];
+    u64 b = s;
+    if (midrun) {
+      const u64 cap = min(N, s + cneed(BS));
+      b = find_run_end(in, s, cap, sh);
+    }
+    const u64 ofs = outfresh(b - s);
+    u64 e;
+    if (ofs >= BS) {
+      // the block fills up inside its first (re-phased) run
+      e = s + cneed(BS);
+      bi.e = e; bi.b = e; bi.Wb = 0; bi.ofs = 0; bi.n = BS;
+      Ws_valid = false;
+    } else {
+      u64 Wb;
+      if (midrun) Wb = eval_W(in, N, carry, prefix, b, sh);
+      else Wb = Ws_valid ? Ws : eval_W(in, N, carry, prefix, s, sh);
+      const u64 V = Wb + (BS - ofs);
+      if (V > Wtotal) {
+        e = N;
+        bi.e = e; bi.b = b; bi.Wb = Wb; bi.ofs = (u32)ofs; bi.n = (u32)(ofs + (Wtotal - Wb));
+        Ws_valid = false;
+      } else {
+        // largest tile t >= tile(b) with prefix[t] < V
+        u64 lo = b / RLE_TILE, hi = ntiles;  // pred(lo) true, pred(hi) false
+        {
+          // narrow with a guess window first (typical data: about BS raw bytes per block)
+          const u64 a = ((BS - ofs) * 4 / 5) / RLE_TILE;
+          const u64 g0 = lo + (a > 1 ? a - 1 : 0);
+          if (g0 < ntiles && prefix[g0] < V) {
+            lo = g0;
+            const u64 g1 = g0 + 4 * RT_THREADS;
+            if (g1 < ntiles && !(prefix[g1] < V)) hi = g1;
+          }
+        }
+        while (hi - lo > 1) {
+          const u64 span = hi - lo;
+          // probe points lo < p_i < hi, increasing in i
+          const u64 pi = lo + 1 + (span - 1) * (u64)tid / RT_THREADS;
+          const bool valid = pi < hi && (tid == 0 || pi != lo + 1 + (span - 1) * (u64)(tid - 1) / RT_THREADS);
+          const bool pr = valid && prefix[pi] < V;
+          // largest true probe -> new lo ; smallest false probe -> new hi
+          const u32 tr = block_max256(pr ? tid + 1 : 0, sh.sc.red);
+          const u32 fl = block_min256((valid && !pr) ? tid : 0xffffffffu, sh.sc.red);
+          u64 nlo = lo, nhi = hi;
+          if (tr) nlo = lo + 1 + (span - 1) * (u64)(tr - 1) / RT_THREADS;
+          if (fl != 0xffffffffu) nhi = lo + 1 + (span - 1) * (u64)fl / RT_THREADS;
+          lo = nlo; hi = nhi;
+        }
+        const u64 t = lo;
+        TileView v;
+        tile_view(in, N, t * RLE_TILE, carry[t], sh.sc, v);
+        // smallest position whose inclusive W reaches V
+        u32 found = 0xffffffffu;
+        {
+          u64 acc = prefix[t] + v.excl;
+          for (u32 j = 0; j < v.cnt; j++) {
+            acc += v.w[j];
+            if (acc >= V) { found = tid * RT_PER + j; break; }
+          }
+        }
+        const u32 f = block_min256(found, sh.sc.red);
+        // f always exists: prefix[t+1] >= V
+        if (f / RT_PER == tid) {
+          u64 acc = prefix[t] + v.excl;
+          for (u32 j = 0; j <= f % RT_PER; j++) acc += v.w[j];
+          sh.r64 = acc;
+        }
+        __syncthreads();
+        const u64 We = sh.r64;
+        __syncthreads();
+        e = t * RLE_TILE + f + 1;
+        const u64 produced = ofs + (We - Wb);
+        bi.e = e; bi.b = b; bi.Wb = Wb; bi.ofs = (u32)ofs; bi.n = (u32)min(produced, (u64)BS);
+        Ws = We; Ws_valid = true;
+      }
+    }
+    if (tid == 0) blocks[k] = bi;
+    k++;
+    s = e;
+  }
+  if (tid == 0) *nblocks_out = k;
+}
+
+// ---- D ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_THREADS)
+k_rle_emit(const u8* __restrict__ in, u64 N, const u32* __restrict__ carry, const u64* __restrict__ prefix,
+           const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u64* __restrict__ tile_base, u8* __restrict__ T) {
+  __shared__ TileScratch sc;
+  __shared__ u32 s_k;
+  // which block does this CTA work for?  tile_base[k] = first CTA of block (first+k)
+  if (threadIdx.x == 0) {
+    u32 lo = 0, hi = count;
+    while (hi - lo > 1) {
+      u32 mid = (lo + hi) >> 1;
+      if (tile_base[mid] <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    s_k = lo;
+  }
+  __syncthreads();
+  const u32 kk = s_k;
+  const BlkInfo bi = blocks[first + kk];
+  const u64 t = bi.s / RLE_TILE + (blockIdx.x - tile_base[kk]);
+  const u64 tstart = t * RLE_TILE;
+  TileView v;
+  tile_view(in, N, tstart, carry[t], sc, v);
+  u8* Tb = T + ((size_t)kk << SEG_SHIFT);
+  const u64 Pt = prefix[t];
+  u32 run = v.excl;
+  for (u32 j = 0; j < v.cnt; j++) {
+    const u64 x = tstart + threadIdx.x * RT_PER + j;
+    const u32 wmax = v.w[j];
+    const u32 exw = run;
+    run += wmax;
+    if (x < bi.s || x >= bi.e) continue;
+    u32 r;
+    u64 opos;
+    if (x < bi.b) {
+      const u64 d = x - bi.s;
+      r = (u32)(d % 255) + 1;
+      opos = outfresh(d);
+    } else {
+      r = wmax == 0 ? 5u : (wmax == 2 ? 4u : 1u);  // only "literal / 4th byte / counted" matters
+      opos = bi.ofs + (Pt + exw - bi.Wb);
+    }
+    if (r > 4 || opos >= bi.n) continue;
+    const u8 ch = v.by[j];
+    Tb[opos] = ch;
+    if (r == 4 && opos + 1 < bi.n) {
+      // count byte: how many more equal bytes does this 255-chunk take inside the block?
+      u64 lim = x + 1 + 251;
+      if (lim > bi.e) lim = bi.e;
+      if (x < bi.b && lim > bi.b) lim = bi.b;
+      u32 c = 0;
+      while (x + 1 + c < lim && in[x + 1 + c] == ch) c++;
+      Tb[opos + 1] = (u8)c;
+    }
+  }
+}
+
+// ---- CRC ---------------------------------------------------------------------------------
+#define CRC_POLY 0x04c11db7u
+__host__ __device__ __forceinline__ u32 gf_mulmod(u32 a, u32 b) {
+  u32 r = 0;
+  for (int i = 31; i >= 0; i--) {
+    r = (r << 1) ^ ((r & 0x80000000u) ? CRC_POLY : 0u);
+    if ((b >> i) & 1) r ^= a;
+  }
+  return r;
+}
+struct CrcConsts {
+  u32 table[256];
+  u32 pow[48];  // pow[i] = x^(8 * 2^i) mod P
+};
+static CrcConsts make_crc_consts() {
+  CrcConsts c;
+  for (u32 i = 0; i < 256; i++) {
+    u32 v = i << 24;
+    for (int k = 0; k < 8; k++) v = (v & 0x80000000u) ? (v << 1) ^ CRC_POLY : (v << 1);
+    c.table[i] = v;
+  }
+  c.pow[0] = 0x100;  // x^8
+  for (int i = 1; i < 48; i++) c.pow[i] = gf_mulmod(c.pow[i - 1], c.pow[i - 1]);
+  return c;
+}
+__constant__ CrcConsts c_crc;
+static bool g_crc_ready = false;
+static void crc_setup() {
+  if (g_crc_ready) return;
+  CrcConsts h = make_crc_consts();
+  CUDA_CHECK(cudaMemcpyToSymbol(c_crc, &h, sizeof h));
+  g_crc_ready = true;
+}
+// x^(8*bytes) mod P
+__device__ __forceinline__ u32 crc_xpow(u64 bytes) {
+  u32 r = 1u;  // bit i of a register value is the coefficient of x^i, so the polynomial 1 is 0x1
+  for (int i = 0; bytes; i++, bytes >>= 1)
+    if (bytes & 1) r = gf_mulmod(r, c_crc.pow[i]);
+  return r;
+}
+
+#define CRC_PIECE 256
+// pieces are aligned from the END of each block's raw range; piece j covers
+// [e - (j+1)*256, e - j*256) clipped at s.  acc[k] ^= R(piece) * x^(8*256*j).
+__global__ void __launch_bounds__(256)
+k_crc_pieces(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u64* __restrict__ piece_base,
+             u64 total_pieces, u32* __restrict__ acc) {
+  __shared__ u32 tab[256];
+  tab[threadIdx.x] = c_crc.table[threadIdx.x];
+  __syncthreads();
+  const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total_pieces) return;
+  u32 lo = 0, hi = count;
+  while (hi - lo > 1) {
+    u32 mid = (lo + hi) >> 1;
+    if (piece_base[mid] <= gid) lo = mid; else hi = mid;
+  }
+  const BlkInfo bi = blocks[first + lo];
+  const u64 j = gid - piece_base[lo];
+  const u64 pend = bi.e - j * CRC_PIECE;
+  const u64 pbeg = (pend - bi.s > CRC_PIECE) ? pend - CRC_PIECE : bi.s;
+  u32 crc = 0;
+  const u8* p = in + pbeg;
+  const u32 len = (u32)(pend - pbeg);
+  u32 i = 0;
+  if (len == CRC_PIECE && (((size_t)p) & 15) == 0) {
+    for (; i < CRC_PIECE; i += 16) {
+      uint4 q = *reinterpret_cast<const uint4*>(p + i);
+      u32 a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int w = 0; w < 4; w++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) crc = (crc << 8) ^ tab[((crc >> 24) ^ (a[w] >> (8 * b))) & 0xff];
+    }
+  } else {
+    for (; i < len; i++) crc = (crc << 8) ^ tab[((crc >> 24) ^ p[i]) & 0xff];
+  }
+  if (j) crc = gf_mulmod(crc, crc_xpow(j * CRC_PIECE));
+  atomicXor(&acc[lo], crc);
+}
+__global__ void k_crc_final(const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u32* __restrict__ acc, u32* __restrict__ crc_out) {
+  u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const BlkInfo bi = blocks[first + k];
+  const u64 len = bi.e - bi.s;
+  crc_out[k] = ~(acc[k] ^ gf_mulmod(0xffffffffu, crc_xpow(len)));
+}
+
+// single-buffer CRC (b2_crc32_bzip2)
+u32 crc32_device(Ctx& c, const u8* d_p, size_t n) {
+  crc_setup();
+  BlkInfo bi;
+  memset(&bi, 0, sizeof bi);
+  bi.s = 0; bi.e = n; bi.b = 0; bi.n = 0;
+  DBuf<BlkInfo> db(c, 1);
+  DBuf<u64> pb(c, 1);
+  DBuf<u32> acc(c, 1), out(c, 1);
+  u64 zero = 0;
+  CUDA_CHECK(cudaMemcpyAsync(db, &bi, sizeof bi, cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemcpyAsync(pb, &zero, 8, cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, 4, c.stream));
+  const u64 pieces = (n + CRC_PIECE - 1) / CRC_PIECE;
+  if (pieces) {
+    k_crc_pieces<<<(unsigned)((pieces + 255) / 256), 256, 0, c.stream>>>(d_p, db, 0, 1, pb, pieces, acc);
+    KLAUNCH(c); KCHECK();
+  }
+  k_crc_final<<<1, 32, 0, c.stream>>>(db, 0, 1, acc, out);
+  KLAUNCH(c); KCHECK();
+  u32 h = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h, out, 4, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  return h;
+}
+
+// ---- host drivers ---------------------------------------------------------------------------
+void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) {
+  crc_setup();
+  plan.nblocks = 0;
+  plan.h_blocks.clear();
+  if (n == 0) return;
+  const u32 BS = (u32)level * 100000 - 19;  // lib/Bzip2.js:892-900
+  const u64 ntiles = (n + RLE_TILE - 1) / RLE_TILE;
+  plan.ntiles = ntiles;
+  DBuf<TileSum> sums(c, ntiles);
+  plan.tile_carry.alloc(c, ntiles);
+  plan.tile_prefix.alloc(c, ntiles + 1);
+  k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums);
+  KLAUNCH(c); KCHECK();
+  k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix);
+  KLAUNCH(c); KCHECK();
+  const u32 maxblocks = (u32)(n / ((u64)BS * 4 / 5) + 2);
+  plan.blocks.alloc(c, maxblocks);
+  DBuf<u32> dnb(c, 1);
+  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks);
+  KLAUNCH(c); KCHECK();
+  u32 nb = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&nb, dnb, 4, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  plan.nblocks = nb;
+  plan.h_blocks.resize(nb);
+  if (nb) CUDA_CHECK(cudaMemcpyAsync(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc) {
+  if (count == 0) return;
+  std::vector<u64> tbase(count + 1), pbase(count + 1);
+  std::vector<u32> hn(count);
+  u64 tt = 0, pp = 0;
+  for (size_t k = 0; k < count; k++) {
+    const BlkInfo& bi = plan.h_blocks[first + k];
+    tbase[k] = tt; pbase[k] = pp;
+    tt += (bi.e - 1) / RLE_TILE - bi.s / RLE_TILE + 1;
+    pp += (bi.e - bi.s + CRC_PIECE - 1) / CRC_PIECE;
+    hn[k] = bi.n;
+  }
+  tbase[count] = tt; pbase[count] = pp;
+  DBuf<u64> dtb(c, count + 1), dpb(c, count + 1);
+  DBuf<u32> acc(c, count);
+  CUDA_CHECK(cudaMemcpyAsync(dtb, tbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemcpyAsync(dpb, pbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_n, hn.data(), 4 * count, cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * count, c.stream));
+  k_rle_emit<<<(unsigned)tt, RT_THREADS, 0, c.stream>>>(d_in, n, plan.tile_carry, plan.tile_prefix, plan.blocks, (u32)first, (u32)count, dtb, d_T);
+  KLAUNCH(c); KCHECK();
+  k_crc_pieces<<<(unsigned)((pp + 255) / 256), 256, 0, c.stream>>>(d_in, plan.blocks, (u32)first, (u32)count, dpb, pp, acc);
+  KLAUNCH(c); KCHECK();
+  k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(plan.blocks, (u32)first, (u32)count, acc, d_crc);
+  KLAUNCH(c); KCHECK();
+  // tbase/pbase/hn are pageable host vectors: make sure the async copies are done before they die
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}

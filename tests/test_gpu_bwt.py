@@ -1,0 +1,50 @@
+"""GPU parity: forward cyclic BWT (lib/BWT.js:372-417 bwtransform2) -- CUDA vs oracle, bit exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import util as T
+
+pytestmark = pytest.mark.gpu
+
+KATS = [  # test/bwtest.js:39-79
+    ("bcababa", "cbbaaab", 5),
+    ("ABCDEFGHIJKLMNOPQRSTUVWXYZ", "ZABCDEFGHIJKLMNOPQRSTUVWXY", 0),
+    ("ZYXWVUTSRQPONMLKJIHGFEDCBA", "BCDEFGHIJKLMNOPQRSTUVWXYZA", 25),
+    ("SIX.MIXED.PIXIES.SIFT.SIXTY.PIXIE.DUST.BOXES", "TEXYDST.E.IXIXIXXSSMPPS.B..E.S.EUSFXDIIOIIIT", 29),
+]
+
+
+def test_bwt_kats():
+    for i, o, p in KATS:
+        assert T.native_bwt(i.encode()) == (o.encode(), p)
+    mary = ("Mary had a little lamb, its fleece was white as snow" * 8 + "Nary had a little lamb, its fleece was white as snow").encode()
+    u, p = T.native_bwt(mary)
+    assert p == 99 and (u, p) == O.bwt_cyclic(mary)
+
+
+@pytest.mark.parametrize("data", [b"ab", b"aa", b"aaaa", b"abababab", b"abcabcabc", b"a" * 1000, b"ab" * 777, b"\x00" * 300 + b"\xff" * 300,
+                                  bytes(range(256)) * 3, b"abc" * 341 + b"abd"])
+def test_bwt_degenerate(data):
+    assert T.native_bwt(data) == O.bwt_cyclic(data)
+
+
+@pytest.mark.parametrize("n,kind", [(1000, "ascii"), (4096, "ascii"), (4097, "text"), (70000, "text"), (100000, "runs"), (300000, "ascii")])
+def test_bwt_random(n, kind):
+    data = {"ascii": T.ascii_random, "text": T.texty, "runs": T.runs}[kind](n, seed=n)
+    assert T.native_bwt(data) == O.bwt_cyclic(data)
+
+
+def test_bwt_full_block_and_batch():
+    blocks = [T.ascii_random(899981, 5), T.texty(899981, 6), T.runs(50000, 7), b"x" * 70000, T.texty(12345, 8), b"q",
+              (T.texty(3000, 9) * 40)[:100000]]
+    got = T.native_bwt_batch(blocks)
+    for b, g in zip(blocks, got):
+        assert g == O.bwt_cyclic(b)
+    st = T.native().stats()
+    assert st["radix_launches"] > 0 and st["kernel_launches"] > 0
+
+
+def test_bwt_fixture_sample3():
+    data = T.fixture("sample3.ref")  # highly repetitive: many doubling rounds
+    assert T.native_bwt(data) == O.bwt_cyclic(data)
