@@ -43,7 +43,8 @@ struct HuffBlk {
 };
 // Table optimisation (lib/Bzip2.js:671-733, 826-843 + HuffmanAllocator.js): selectors u8 (slot layout >> 0, stride SEL_STRIDE)
 #define SEL_STRIDE 18432
-void huffman_batch(Ctx& c, const u16* d_sym, const u32* d_m, const u32* d_freq, const u32* d_used, u32 nblk, u8* d_sel, HuffBlk* d_hb);
+void huffman_batch(Ctx& c, const u16* d_sym, const u32* d_m, const u32* d_freq, const u32* d_used, u32 nblk, u8* d_sel, u8* d_selmtf,
+                   HuffBlk* d_hb);
 // bit packing of blocks at their final bit offsets (lib/Bzip2.js:740-741,749-758,847-874)
-void pack_batch(Ctx& c, const u16* d_sym, const u8* d_sel, const HuffBlk* d_hb, const u32* d_used, const u32* d_pidx, const u32* d_crc,
-                const u64* d_bitoff, u32 nblk, u32* d_out_words);
+void pack_batch(Ctx& c, const u16* d_sym, const u8* d_sel, const u8* d_selmtf, const HuffBlk* d_hb, const u32* d_used, const u32* d_pidx,
+                const u32* d_crc, const u64* d_bitoff, const u32* d_flag, u32 nblk, u32 max_m, u32* d_out_words);

@@ -1,0 +1,400 @@
+// encode.cu -- bit packing of the .bz2 stream and the compressFile driver.
+//
+// Reference: lib/Bzip2.js:879-929 (compressFile: "BZh"+level, per block magic/CRC/body,
+// trailer magic + stream CRC, zero pad), :735-876 (compressBlock body layout, SURVEY.md
+// Appendix B) and lib/BitStream.js:52-105 (MSB-first bit order).
+//
+// The reference pushes one bit at a time through a BitStream.  Here every block's total bit
+// length is known after the Huffman stage, so an exclusive scan gives each block its final bit
+// offset in the file and all blocks are packed in place concurrently:
+//   k_offsets     : running bit cursor + stream CRC fold (rotl1 ^ crc, lib/Bzip2.js:917)
+//   k_pack_header : per block: magic, CRC, pidx, symbol map, selectors (unary of the MTF'd table
+//                   ids, offsets by prefix sum), code-length tables (delta coded)
+//   k_pack_codes  : per 256 groups: per-group bit counts -> chained scan -> each thread encodes
+//                   its 50 symbols into a shared-memory staging tile that is aligned to the
+//                   global 32-bit word grid, then the tile is written out coalesced
+//                   (only the two boundary words need atomics)
+#include <algorithm>
+#include <vector>
+#include "enc.h"
+
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx);
+
+// ---- bit writers (stream is MSB first; words are stored big-endian) ----------------------
+__device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
+
+// OR `nbits` (<= 32) of `val` into a zero-initialised global stream at absolute bit `pos`
+__device__ __forceinline__ void gput(u32* out, u64 pos, u32 nbits, u32 val) {
+  if (nbits == 0) return;
+  const u64 w = pos >> 5;
+  const u32 o = (u32)(pos & 31);
+  const u64 v = ((u64)val << (64 - nbits)) >> o;  // left aligned in 64 bits, then shifted to the offset
+  const u32 hi = (u32)(v >> 32), lo = (u32)v;
+  if (hi) atomicOr(&out[w], bswap32(hi));
+  if (lo) atomicOr(&out[w + 1], bswap32(lo));
+}
+
+// Sequential writer for one thread that owns a contiguous bit range: words strictly inside the
+// range are stored, the first and last (shared) words are OR-ed.
+struct BitAcc {
+  u32* out; u64 word; unsigned long long acc; u32 nb; bool first;
+  __device__ __forceinline__ void init(u32* o, u64 pos) { out = o; word = pos >> 5; nb = (u32)(pos & 31); acc = 0; first = true; }
+  __device__ __forceinline__ void put(u32 nbits, u32 val) {
+    acc = (acc << nbits) | val;
+    nb += nbits;
+    if (nb >= 32) {
+      const u32 wv = (u32)(acc >> (nb - 32));
+      if (first) { atomicOr(&out[word], bswap32(wv)); first = false; }
+      else out[word] = bswap32(wv);
+      word++;
+      nb -= 32;
+      acc &= (1ull << nb) - 1;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (nb) {
+      const u32 wv = (u32)(acc << (32 - nb));
+      if (wv) atomicOr(&out[word], bswap32(wv));
+    }
+  }
+};
+
+// ---- offsets ---------------------------------------------------------------------------------
+// state[0] = bit cursor, state[1] = stream crc, state[2] = overflow flag
+__global__ void k_offsets(const HuffBlk* __restrict__ hb, const u32* __restrict__ crc, u32 nblk, u64* state, u64* __restrict__ bitoff,
+                          u64 cap_bits, u32* flag) {
+  if (threadIdx.x || blockIdx.x) return;
+  u64 cur = state[0];
+  u32 scrc = (u32)state[1];
+  for (u32 k = 0; k < nblk; k++) {
+    bitoff[k] = cur;
+    cur += hb[k].body_bits;
+    scrc = ((scrc << 1) | (scrc >> 31)) ^ crc[k];
+  }
+  state[0] = cur;
+  state[1] = scrc;
+  if (cur + 96 + 64 > cap_bits) *flag = 1;
+}
+
+// ---- header --------------------------------------------------------------------------------
+#define PH_THREADS 256
+__global__ void __launch_bounds__(PH_THREADS)
+k_pack_header(const u8* __restrict__ selmtf, const HuffBlk* __restrict__ hb_arr, const u32* __restrict__ used, const u32* __restrict__ pidx,
+              const u32* __restrict__ crc, const u64* __restrict__ bitoff, const u32* __restrict__ flag, u32* __restrict__ out,
+              u32* __restrict__ code_start, u32* __restrict__ codes) {
+  __shared__ u32 ws[PH_THREADS / 32 + 1];
+  __shared__ u32 tab_off[HUFF_MAXGROUPS + 1];
+  if (*flag) return;
+  const u32 blk = blockIdx.x, tid = threadIdx.x;
+  const HuffBlk* hb = hb_arr + blk;
+  const u32 ng = hb->ngroups, nsel = hb->nsel, A = hb->alpha + 2;
+  if (ng == 0) return;
+  const u64 P0 = bitoff[blk];
+  // canonical codes (lib/Bzip2.js:581-600): ascending (length, symbol); the code of a symbol is the
+  // number of code points of its length taken by everything that sorts before it
+  for (u32 i = tid; i < ng * A; i += PH_THREADS) {
+    const u32 t = i / A, sy = i % A;
+    const u32 l = hb->len[t][sy];
+    u32 codev = 0;
+    for (u32 j = 0; j < A; j++) {
+      const u32 lj = hb->len[t][j];
+      if (lj < l || (lj == l && j < sy)) codev += 1u << (l - lj);
+    }
+    codes[((size_t)blk * HUFF_MAXGROUPS + t) * (HUFF_MAXSYM + 2) + sy] = (l << 24) | codev;
+  }
+  // fixed part
+  u32 mapbits = 0;
+  for (u32 r = 0; r < 16; r++) {
+    const u32 w = used[blk * 8 + (r >> 1)];
+    if ((w >> ((r & 1) * 16)) & 0xffffu) mapbits += 16;
+  }
+  const u64 Psel = P0 + 48 + 32 + 1 + 24 + 16 + mapbits + 3 + 15;
+  if (tid == 0) {
+    u64 p = P0;
+    gput(out, p, 24, 0x314159u); p += 24;      // WHOLEPI lib/Bzip2.js:49
+    gput(out, p, 24, 0x265359u); p += 24;
+    gput(out, p, 32, crc[blk]); p += 32;
+    gput(out, p, 1, 0); p += 1;                // not randomised
+    gput(out, p, 24, pidx[blk]); p += 24;
+    u32 compact = 0;
+    for (u32 r = 0; r < 16; r++) {
+      const u32 w = used[blk * 8 + (r >> 1)];
+      if ((w >> ((r & 1) * 16)) & 0xffffu) compact |= 1u << (15 - r);
+    }
+    gput(out, p, 16, compact); p += 16;
+    for (u32 r = 0; r < 16; r++) {
+      const u32 w = (used[blk * 8 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
+      if (w) {
+        // bit j of the range (byte r*16+j) is written MSB first: reverse the 16 bits
+        const u32 rev = __brev(w) >> 16;
+        gput(out, p, 16, rev); p += 16;
+      }
+    }
+    gput(out, p, 3, ng); p += 3;
+    gput(out, p, 15, nsel); p += 15;
+  }
+  // selectors: j ones then a zero each
+  const u8* sm = selmtf + (size_t)blk * SEL_STRIDE;
+  const u32 per = (nsel + PH_THREADS - 1) / PH_THREADS;
+  const u32 ga = min(nsel, tid * per), gb = min(nsel, ga + per);
+  u32 mybits = 0;
+  for (u32 g = ga; g < gb; g++) mybits += (u32)sm[g] + 1;
+  u32 total;
+  const u32 ex = block_excl_add<PH_THREADS, u32>(mybits, ws, &total);
+  if (gb > ga) {
+    BitAcc ba;
+    ba.init(out, Psel + ex);
+    for (u32 g = ga; g < gb; g++) {
+      const u32 j = sm[g];
+      ba.put(j + 1, ((1u << j) - 1) << 1);
+    }
+    ba.flush();
+  }
+  // tables
+  const u64 Ptab = Psel + total;
+  if (tid == 0) {
+    u32 o = 0;
+    for (u32 t = 0; t < ng; t++) {
+      tab_off[t] = o;
+      u32 bits = 5, cur = hb->len[t][0];
+      for (u32 i = 0; i < A; i++) {
+        const u32 l = hb->len[t][i];
+        bits += 2 * (l > cur ? l - cur : cur - l) + 1;
+        cur = l;
+      }
+      o += bits;
+    }
+    tab_off[ng] = o;
+    code_start[blk] = (u32)(Ptab + o - P0);
+  }
+  __syncthreads();
+  if (tid < ng) {
+    BitAcc ba;
+    ba.init(out, Ptab + tab_off[tid]);
+    u32 cur = hb->len[tid][0];
+    ba.put(5, cur);
+    for (u32 i = 0; i < A; i++) {
+      const u32 l = hb->len[tid][i];
+      const u32 v = cur < l ? 2u : 3u;
+      u32 d = cur < l ? l - cur : cur - l;
+      while (d--) ba.put(2, v);
+      ba.put(1, 0);
+      cur = l;
+    }
+    ba.flush();
+  }
+}
+
+// ---- codes ---------------------------------------------------------------------------------
+#define PC_THREADS 256
+#define PC_GROUPS 256
+#define PC_STAGE_WORDS (PC_GROUPS * 1000 / 32 + 4)
+
+struct PackSmem {
+  u32 tile[PC_GROUPS * 25];
+  u32 stage[PC_STAGE_WORDS];
+  u32 code[HUFF_MAXGROUPS][HUFF_MAXSYM + 2];  // len << 24 | code
+  u32 ws[PC_THREADS / 32 + 1];
+  u32 s_tile, s_carry;
+};
+
+__global__ void __launch_bounds__(PC_THREADS)
+k_pack_codes(const u16* __restrict__ sym, const u8* __restrict__ sel, const HuffBlk* __restrict__ hb_arr, const u64* __restrict__ bitoff,
+             const u32* __restrict__ code_start, const u32* __restrict__ codes, const u32* __restrict__ flag, u32 tps, u32* ticket,
+             u64* status, u32* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PackSmem& s = *reinterpret_cast<PackSmem*>(smem_raw);
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s.s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s.s_tile;
+  const u32 blk = tile / tps, lt = tile % tps;
+  const HuffBlk* hb = hb_arr + blk;
+  const u32 nsel = hb->nsel, m = hb->m, ng = hb->ngroups, A = hb->alpha + 2;
+  const u32 g0 = lt * PC_GROUPS;
+  if (*flag || g0 >= nsel) return;
+  for (u32 i = tid; i < ng * A; i += PC_THREADS) {
+    const u32 t = i / A, sy = i % A;
+    s.code[t][sy] = codes[((size_t)blk * HUFF_MAXGROUPS + t) * (HUFF_MAXSYM + 2) + sy];
+  }
+  const u32* symw = reinterpret_cast<const u32*>(sym + ((size_t)blk << SEG_SHIFT));
+  const u32 nwords = (m + 1) >> 1;
+  const u32 w0 = g0 * 25;
+  for (u32 i = tid; i < PC_GROUPS * 25; i += PC_THREADS) s.tile[i] = (w0 + i < nwords) ? symw[w0 + i] : 0u;
+  for (u32 i = tid; i < PC_STAGE_WORDS; i += PC_THREADS) s.stage[i] = 0;
+  __syncthreads();
+  const u32 g = g0 + tid;
+  u32 bits = 0, cnt = 0, tsel = 0;
+  if (g < nsel) {
+    cnt = min(50u, m - 50u * g);
+    tsel = sel[(size_t)blk * SEL_STRIDE + g];
+    for (u32 k = 0; k < 25; k++) {
+      const u32 w = s.tile[tid * 25 + k];
+      if (2 * k < cnt) bits += s.code[tsel][w & 0xffffu] >> 24;
+      if (2 * k + 1 < cnt) bits += s.code[tsel][w >> 16] >> 24;
+    }
+  }
+  u32 total;
+  const u32 ex = block_excl_add<PC_THREADS, u32>(bits, s.ws, &total);
+  if (tid < 32) {
+    u32 cr = lookback_warp(status + (size_t)blk * tps, lt, total, OpAdd());
+    if (tid == 0) s.s_carry = cr;
+  }
+  __syncthreads();
+  const u64 P = bitoff[blk] + code_start[blk] + s.s_carry;  // absolute bit of this tile's first code
+  const u32 phase = (u32)(P & 31);
+  if (g < nsel) {
+    BitAcc ba;
+    ba.init(s.stage, (u64)phase + ex);
+    for (u32 k = 0; k < 25; k++) {
+      const u32 w = s.tile[tid * 25 + k];
+      if (2 * k < cnt) { const u32 cv = s.code[tsel][w & 0xffffu]; ba.put(cv >> 24, cv & 0xffffffu); }
+      if (2 * k + 1 < cnt) { const u32 cv = s.code[tsel][w >> 16]; ba.put(cv >> 24, cv & 0xffffffu); }
+    }
+    ba.flush();
+  }
+  __syncthreads();
+  // stage words are already byte-swapped by BitAcc; copy out
+  const u32 nw = (phase + total + 31) >> 5;
+  u32* dst = out + (P >> 5);
+  for (u32 i = tid; i < nw; i += PC_THREADS) {
+    const u32 v = s.stage[i];
+    if (i == 0 || i == nw - 1) { if (v) atomicOr(&dst[i], v); }
+    else dst[i] = v;
+  }
+}
+
+void pack_batch(Ctx& c, const u16* d_sym, const u8* d_sel, const u8* d_selmtf, const HuffBlk* d_hb, const u32* d_used, const u32* d_pidx,
+                const u32* d_crc, const u64* d_bitoff, const u32* d_flag, u32 nblk, u32 max_m, u32* d_out_words) {
+  static bool attr = false;
+  if (!attr) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_pack_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
+    attr = true;
+  }
+  DBuf<u32> code_start(c, nblk), ticket(c, 1), codes(c, (size_t)nblk * HUFF_MAXGROUPS * (HUFF_MAXSYM + 2));
+  k_pack_header<<<nblk, PH_THREADS, 0, c.stream>>>(d_selmtf, d_hb, d_used, d_pidx, d_crc, d_bitoff, d_flag, d_out_words, code_start, codes);
+  KLAUNCH(c); KCHECK();
+  const u32 max_sel = (max_m + HUFF_GROUP - 1) / HUFF_GROUP;
+  const u32 tps = (max_sel + PC_GROUPS - 1) / PC_GROUPS;
+  DBuf<u64> status(c, (size_t)nblk * tps);
+  CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)nblk * tps * 8, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+  k_pack_codes<<<nblk * tps, PC_THREADS, sizeof(PackSmem), c.stream>>>(d_sym, d_sel, d_hb, d_bitoff, code_start, codes, d_flag, tps, ticket, status,
+                                                                      d_out_words);
+  KLAUNCH(c); KCHECK();
+}
+
+// ---- file header / trailer ---------------------------------------------------------------
+__global__ void k_file_ends(u32* out, int level, const u64* state, int write_header) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (write_header) {
+    gput(out, 0, 8, 'B'); gput(out, 8, 8, 'Z'); gput(out, 16, 8, 'h'); gput(out, 24, 8, (u32)('0' + level));  // lib/Bzip2.js:903-906
+  }
+  u64 p = state[0];
+  gput(out, p, 24, 0x177245u); p += 24;  // SQRTPI lib/Bzip2.js:50
+  gput(out, p, 24, 0x385090u); p += 24;
+  gput(out, p, 32, (u32)state[1]);
+}
+
+// compressFile on device buffers.  whole_file: header + all blocks + trailer.  Otherwise encodes
+// blocks [first_block, first_block+block_count) starting at bit `bit_phase` of d_out.
+void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n, size_t first_block,
+                           size_t block_count, int bit_phase, bool whole_file, u64* out_bits, std::vector<u32>* crcs_out,
+                           size_t* total_blocks) {
+  Rle1Plan plan;
+  {
+    StageScope s(c, ST_RLE1);
+    rle1_plan(c, d_in, n, level, plan);
+  }
+  const size_t nb_all = plan.nblocks;
+  if (total_blocks) *total_blocks = nb_all;
+  c.trace.clear();
+  if (!whole_file && block_count == 0) { *out_n = 0; return; }
+  if (((size_t)d_out) & 3) throw B2Error{B2_ERR_BAD_ARG, "output buffer must be 4-byte aligned"};
+  size_t first = whole_file ? 0 : std::min(first_block, nb_all);
+  size_t count = whole_file ? nb_all : std::min(block_count, nb_all - first);
+  const size_t cap_words = out_cap / 4;
+  if (cap_words < 8) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
+  CUDA_CHECK(cudaMemsetAsync(d_out, 0, cap_words * 4, c.stream));
+  DBuf<u64> state(c, 4);
+  DBuf<u32> flag(c, 1);
+  u64 h_state[4] = {whole_file ? 32ull : (u64)bit_phase, 0, 0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(state, h_state, sizeof h_state, cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(flag, 0, 4, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  std::vector<u32> all_crc(count);
+  std::vector<b2_block_trace> tr(count);
+  const u32 B = c.bwt_batch;
+  if (count) {
+    const u32 nbmax = (u32)std::min<size_t>(B, count);
+    DBuf<u8> T(c, (size_t)nbmax << SEG_SHIFT), U(c, (size_t)nbmax << SEG_SHIFT);
+    DBuf<u16> sym(c, (size_t)nbmax << SEG_SHIFT);
+    DBuf<u32> dn(c, nbmax), dcrc(c, nbmax), dpidx(c, nbmax), dm(c, nbmax), dfreq(c, (size_t)nbmax * HUFF_MAXSYM), dused(c, (size_t)nbmax * 8);
+    DBuf<u8> dsel(c, (size_t)nbmax * SEL_STRIDE), dselmtf(c, (size_t)nbmax * SEL_STRIDE);
+    DBuf<HuffBlk> dhb(c, nbmax);
+    DBuf<u64> dbitoff(c, nbmax);
+    std::vector<u32> hn(nbmax), hm(nbmax), hp(nbmax);
+    std::vector<HuffBlk> hhb(nbmax);
+    std::vector<u64> hoff(nbmax);
+    for (size_t k0 = 0; k0 < count; k0 += B) {
+      const u32 nb = (u32)std::min<size_t>(B, count - k0);
+      u32 nmax = 0;
+      for (u32 b = 0; b < nb; b++) { hn[b] = plan.h_blocks[first + k0 + b].n; nmax = std::max(nmax, hn[b]); }
+      {
+        StageScope s(c, ST_RLE1);
+        rle1_materialize(c, d_in, n, plan, first + k0, nb, T, dn, dcrc);
+      }
+      {
+        StageScope s(c, ST_BWT);
+        CUDA_CHECK(cudaMemsetAsync(dpidx, 0, nb * 4, c.stream));
+        bwt_forward_batch(c, T, U, dn, hn.data(), nb, dpidx);
+      }
+      {
+        StageScope s(c, ST_MTF);
+        mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused);
+      }
+      {
+        StageScope s(c, ST_HUFF);
+        huffman_batch(c, sym, dm, dfreq, dused, nb, dsel, dselmtf, dhb);
+      }
+      {
+        StageScope s(c, ST_PACK);
+        k_offsets<<<1, 32, 0, c.stream>>>(dhb, dcrc, nb, state, dbitoff, (u64)cap_words * 32, flag);
+        KLAUNCH(c); KCHECK();
+        pack_batch(c, sym, dsel, dselmtf, dhb, dused, dpidx, dcrc, dbitoff, flag, nb, nmax + 1, reinterpret_cast<u32*>(d_out));
+      }
+      // per-block bookkeeping for the host (trace + CRCs)
+      CUDA_CHECK(cudaMemcpyAsync(hm.data(), dm, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hp.data(), dpidx, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hhb.data(), dhb, nb * sizeof(HuffBlk), cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hoff.data(), dbitoff, nb * 8, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(all_crc.data() + k0, dcrc, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      for (u32 b = 0; b < nb; b++) {
+        b2_block_trace& t = tr[k0 + b];
+        const BlkInfo& bi = plan.h_blocks[first + k0 + b];
+        t.n = (int32_t)bi.n; t.pidx = (int32_t)hp[b]; t.m = (int32_t)hm[b]; t.alpha = (int32_t)hhb[b].alpha;
+        t.ngroups = (int32_t)hhb[b].ngroups; t.nsel = (int32_t)hhb[b].nsel; t.crc = all_crc[k0 + b]; t.pad = 0;
+        t.raw_start = bi.s; t.raw_len = bi.e - bi.s; t.bit_start = hoff[b]; t.bit_len = hhb[b].body_bits;
+      }
+      c.stats.blocks += nb;
+    }
+  }
+  u32 h_flag = 0;
+  if (whole_file) {
+    k_file_ends<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), level, state, 1);
+    KLAUNCH(c); KCHECK();
+  }
+  CUDA_CHECK(cudaMemcpyAsync(h_state, state, sizeof h_state, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  if (h_flag) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
+  if (whole_file) {
+    *out_n = (size_t)((h_state[0] + 80 + 7) / 8);  // trailer 48 + 32 bits, zero padded (lib/BitStream.js:68-73)
+  } else {
+    *out_n = (size_t)((h_state[0] + 7) / 8);
+    if (out_bits) *out_bits = h_state[0] - (u64)bit_phase;
+  }
+  if (crcs_out) *crcs_out = all_crc;
+  c.trace = tr;
+}

@@ -127,7 +127,7 @@ __device__ void recount(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 ns
 
 __global__ void __launch_bounds__(HF_THREADS)
 k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32* __restrict__ freq0, const u32* __restrict__ used,
-          u8* __restrict__ sel_out, HuffBlk* __restrict__ hb_out) {
+          u8* __restrict__ sel_out, u8* __restrict__ selmtf_out, HuffBlk* __restrict__ hb_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HuffSmem& s = *reinterpret_cast<HuffSmem*>(smem_raw);
   const u32 tid = threadIdx.x;
@@ -233,6 +233,7 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
     }
     // selectors: MTF over the table ids, unary (lib/Bzip2.js:850-862)
     u8 M[HUFF_MAXGROUPS];
+    u8* sm = selmtf_out + (size_t)blk * SEL_STRIDE;
     for (u32 t = 0; t < ng; t++) M[t] = (u8)t;
     for (u32 g = 0; g < nsel; g++) {
       const u8 v = s.sel[g];
@@ -240,6 +241,7 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
       while (M[j] != v) j++;
       for (u32 k = j; k > 0; k--) M[k] = M[k - 1];
       M[0] = v;
+      sm[g] = (u8)j;
       hbits += j + 1;
     }
     // tables: 5 bits + per symbol 2*|delta| + 1 (lib/Bzip2.js:610-629)
@@ -257,12 +259,13 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
   }
 }
 
-void huffman_batch(Ctx& c, const u16* d_sym, const u32* d_m, const u32* d_freq, const u32* d_used, u32 nblk, u8* d_sel, HuffBlk* d_hb) {
+void huffman_batch(Ctx& c, const u16* d_sym, const u32* d_m, const u32* d_freq, const u32* d_used, u32 nblk, u8* d_sel, u8* d_selmtf,
+                   HuffBlk* d_hb) {
   static bool attr = false;
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
     attr = true;
   }
-  k_huffman<<<nblk, HF_THREADS, sizeof(HuffSmem), c.stream>>>(d_sym, d_m, d_freq, d_used, d_sel, d_hb);
+  k_huffman<<<nblk, HF_THREADS, sizeof(HuffSmem), c.stream>>>(d_sym, d_m, d_freq, d_used, d_sel, d_selmtf, d_hb);
   KLAUNCH(c); KCHECK();
 }

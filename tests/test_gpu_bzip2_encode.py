@@ -1,0 +1,89 @@
+"""GPU parity: Bzip2.compressFile (lib/Bzip2.js:879-929) -- CUDA stream bytes == oracle, bit exact,
+and every stream decodes with libbz2 and with the oracle's decoder."""
+import bz2
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import util as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(data, level, libbz2=True):
+    from compressjs_b200 import Bzip2, _native
+    got = Bzip2.compressFile(data, None, level)
+    exp, tr = O.bzip2_compress(data, level, trace=True)
+    if got != exp:
+        gt = _native.last_trace()
+        msg = ["stream mismatch: got %d bytes, expected %d; blocks got %d expected %d" % (len(got), len(exp), len(gt), len(tr))]
+        for k, (a, b) in enumerate(zip(gt, tr)):
+            fa = dict((f, getattr(a, f)) for f, _ in a._fields_)
+            fb = dict((f, getattr(b, f)) for f, _ in b._fields_)
+            diff = {f: (fa[f], fb[f]) for f in fa if fa[f] != fb[f] and f != "pad"}
+            if diff:
+                msg.append("block %d differs: %r" % (k, diff))
+                break
+        first = next((i for i in range(min(len(got), len(exp))) if got[i] != exp[i]), None)
+        msg.append("first differing byte: %r" % first)
+        raise AssertionError("\n".join(msg))
+    if libbz2:
+        assert bz2.decompress(got) == bytes(data)
+    return got
+
+
+def test_sample0_config1():
+    # BASELINE config 1: "This is a test\n", level 1 -> the 57-byte stream of SURVEY.md Appendix C
+    got = _check(b"This is a test\n", 1)
+    assert got.hex() == ("425a6831314159265359ea29357d000002538000104000040022600c00200021aa8f6f4a9ef5"
+                         "0806059702fb58a70bb9229c284875149abe80")
+
+
+def test_empty_and_tiny():
+    from compressjs_b200 import Bzip2
+    assert Bzip2.compressFile(b"", None, 9) == O.bzip2_compress(b"", 9)
+    assert len(Bzip2.compressFile(b"", None, 9)) == 14
+    for d in (b"a", b"ab", b"aaaa", b"aaaaa", b"\x00" * 300, bytes(range(256))):
+        _check(d, 9)
+
+
+@pytest.mark.parametrize("level", [1, 5, 9])
+@pytest.mark.parametrize("kind,n", [("ascii", 250000), ("text", 1200000), ("runs", 400000)])
+def test_synthetic(kind, n, level):
+    data = {"ascii": T.ascii_random, "text": T.texty, "runs": T.runs}[kind](n, seed=n + level)
+    _check(data, level)
+
+
+def test_rle1_block_boundary_quirks():
+    # block fills on the 4th byte of a run: no count byte is written (libbz2 rejects this stream,
+    # the reference's own decoder accepts it -- SURVEY.md section 7)
+    base = T.ascii_random(99977, 3).replace(b"aaaa", b"abab")
+    data = base + b"a" * 20 + T.ascii_random(1000, 4)
+    _check(data, 1, libbz2=False)
+    # block ends right after a zero count byte
+    data = T.ascii_random(99976, 5) + b"b" * 300 + T.ascii_random(500, 6)
+    _check(data, 1, libbz2=False)
+    # long runs straddling block boundaries, runs of 255/256/600
+    data = (b"x" * 70000 + b"y" * 255 + b"z" * 256 + T.ascii_random(29000, 7) + b"w" * 200000 + b"v" * 4 + b"u" * 5) * 2
+    _check(data, 1, libbz2=False)
+    _check(b"q" * 5000000, 1, libbz2=False)
+
+
+@pytest.mark.parametrize("name", ["sample0", "sample1", "sample2", "sample3", "sample4", "sample5"])
+@pytest.mark.parametrize("level", [1, 9])
+def test_reference_samples(name, level):
+    data = T.fixture(name + ".ref")
+    got = _check(data, level)
+    gold = T.golden().get("bzip2_%s_-%d" % (name, level))
+    if gold:
+        assert (len(got), hashlib.sha256(got).hexdigest()) == (gold["size"], gold["sha256"])
+
+
+def test_multi_batch_and_trace():
+    from compressjs_b200 import Bzip2, _native
+    data = T.texty(3 * 99981 + 5000, 11) + T.ascii_random(2 * 99981, 12)
+    _check(data, 1)
+    st = _native.stats()
+    assert st["blocks"] >= 5 and st["kernel_launches"] > 20

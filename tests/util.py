@@ -84,3 +84,10 @@ def native_bwt_batch(blocks):
     for o, l, p in zip(offs, lens, pidx):
         res.append((u[int(o):int(o) + int(l)].tobytes(), int(p)))
     return res
+
+
+def golden():
+    import json
+    p = os.path.join(ROOT, "tests", "golden", "golden.json")
+    with open(p) as f:
+        return json.load(f)
