@@ -1,0 +1,292 @@
+"""bench.py -- headline benchmark of the bzip2 block pipeline (BASELINE.json).
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA, libb2bz.so)
+  python bench.py --impl reference --gpus 1 ...            the reference's CPU path (oracle port)
+  torchrun ... bench.py --gpus N ...                       one rank per GPU, weak scaling
+
+A step = one bzip2 -9 encode of the workload (BASELINE configs[1]: 1 GiB synthetic ASCII per GPU,
+numpy PCG64 seed 20260923, 94 printable bytes + newline).  `value` = whole-job MB/s (10^6 raw bytes
+per second) with the input resident in HBM; `e2e` = the same through the host-buffer C ABI call
+(b2_bzip2_compress: H2D + all kernels + D2H inside the timed region).  The roofline entry is for the
+dominant kernel (k_radix_pass, the onesweep pass of the BWT suffix sort): algorithmic bytes per launch
+over its CUDA-event time, against the measured HBM copy bandwidth.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 20260923
+LEVEL = 9
+METRIC = "bzip2_-9_encode_MBps"
+
+
+def gen_ascii(nbytes, seed):
+    g = np.random.Generator(np.random.PCG64(seed))
+    out = np.empty(nbytes, dtype=np.uint8)
+    step = 1 << 26
+    for o in range(0, nbytes, step):
+        k = min(step, nbytes - o)
+        a = g.integers(32, 127, size=k, dtype=np.uint8)
+        a[a == 126] = 10
+        out[o:o + k] = a
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles():
+    p = os.path.join(ROOT, "profiles", "radix_pass_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def cpu_sample_blocks(data, nblocks):
+    bs = LEVEL * 100000 - 19
+    return data[: min(len(data), nblocks * bs)]
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path (its JavaScript cannot run here: no node in the
+    image; this is the C restatement in oracle/, all host threads), on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    per_step_blocks = max(2, cores)  # one 900k block per core and step keeps the run in minutes
+    mb = int(os.environ.get("B2_BENCH_MB", "1024"))
+    data = gen_ascii(min(mb << 20, per_step_blocks * 900000 + 1000), SEED)
+    sample = np.ascontiguousarray(cpu_sample_blocks(data, per_step_blocks))
+    for _ in range(args.warmup):
+        O.bzip2_compress(sample[: 2 * 900000], LEVEL, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.bzip2_compress(sample, LEVEL, threads=cores)
+    dt = time.perf_counter() - t0
+    val = sample.size * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": "1 GiB synthetic ASCII (PCG64 seed %d), bzip2 -9 (900k blocks) encode" % SEED, "level": LEVEL,
+                   "sample": "first %d blocks (%d bytes) per step" % (per_step_blocks, sample.size)},
+        "cpu_baseline": {"value": val, "unit": "MB/s", "cores": cores, "kind": "port",
+                         "sample": "%d x 900k blocks per step, %d threads (oracle/bz2_oracle.c, one block per thread)" % (per_step_blocks, cores)},
+        "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference JS cannot execute in this image (no node); C restatement of its algorithm timed instead",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mb", type=int, default=int(os.environ.get("B2_BENCH_MB", "1024")), help="MiB of input per GPU and step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from compressjs_b200 import _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _native.lib()
+    rc = L.b2_init(local)
+    if rc:
+        raise SystemExit("b2_init: " + _native.last_error())
+
+    nbytes = args.mb << 20
+    host = gen_ascii(nbytes, SEED + rank)  # every rank owns an independent shard of blocks (weak scaling)
+    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = host
+    d_in = pinned.cuda(non_blocking=False)
+    cap = L.b2_bzip2_bound(nbytes)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    out_n = C.c_size_t()
+
+    def step_resident():
+        rc = L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n))
+        if rc:
+            raise SystemExit("compress_dev failed: " + _native.last_error())
+        return _native.stats()
+
+    def step_e2e():
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = L.b2_bzip2_compress(pinned.data_ptr(), nbytes, LEVEL, C.byref(out), C.byref(n))
+        if rc:
+            raise SystemExit("compress failed: " + _native.last_error())
+        st = _native.stats()
+        L.b2_free(out)
+        return st, n.value
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident (HBM) arm ----
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    agg = {}
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        st = step_resident()
+        dev_ms += st["ms_total"]
+        for k, v in st.items():
+            agg[k] = agg.get(k, 0) + v
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    comp_bytes = out_n.value
+
+    # device time: max over ranks (events on the library's launching stream)
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = t.tolist()
+
+    # ---- e2e arm: host buffers through the C ABI ----
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_comp = 0
+    for _ in range(e2e_steps):
+        _, e2e_comp = step_e2e()
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_wall = t.item()
+
+    if rank == 0:
+        total_raw = nbytes * world
+        value = total_raw * args.steps / (dev_ms_max / 1e3) / 1e6
+        peak, peak_src = peaks()
+        radix_gbs = (agg["radix_bytes"] / 1e9) / (agg["ms_radix"] / 1e3) if agg.get("ms_radix") else 0.0
+        bwt_gbs = (agg["bwt_bytes"] / 1e9) / (agg["ms_bwt"] / 1e3) if agg.get("ms_bwt") else 0.0
+        tr = traffic_from_profiles()
+        line = {
+            "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "%d MiB synthetic ASCII per GPU (PCG64 seed %d+rank), bzip2 -9 (900k blocks) encode" % (args.mb, SEED),
+                       "level": LEVEL, "bytes_per_gpu": nbytes, "blocks_per_gpu": int(agg["blocks"] // max(args.steps, 1)),
+                       "l2": "inputs (%d MiB) larger than L2 (126 MB); no flush needed" % args.mb, "bwt_batch_blocks": int(os.environ.get("B2_BWT_BATCH", "64")),
+                       "compressed_bytes_per_gpu": comp_bytes, "wall_ms_per_step": wall_ms_max / args.steps},
+            "e2e": {"value": total_raw * e2e_steps / e2e_wall / 1e6, "unit": "MB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": e2e_comp,
+                    "steps": e2e_steps, "api": "b2_bzip2_compress (host pinned in, library-pinned out)"},
+            "gpu_launches": int(agg["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_radix_pass (BWT onesweep pass)", "achieved": radix_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": radix_gbs / peak if peak else None, "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                         "peak_source": peak_src, "launches": int(agg["radix_launches"]),
+                         "algorithmic_bytes_per_launch": agg["radix_bytes"] / max(agg["radix_launches"], 1),
+                         "avg_launch_ms": agg["ms_radix"] / max(agg["radix_launches"], 1),
+                         "bwt_stage": {"achieved": bwt_gbs, "frac": bwt_gbs / peak if peak else None, "rounds": int(agg["bwt_rounds"] // max(args.steps, 1)),
+                                       "ms_per_step": agg["ms_bwt"] / args.steps}},
+            "stages_ms_per_step": {k: agg[k] / args.steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack", "ms_radix")},
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            from oracle import oracle as O
+            O.build()
+            sample = np.ascontiguousarray(cpu_sample_blocks(host, 8))
+            tc = time.perf_counter()
+            zc = O.bzip2_compress(sample, LEVEL)
+            dtc = time.perf_counter() - tc
+            line["cpu_baseline"] = {"value": sample.size / dtc / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
+                                    "sample": "first 8 x 900k blocks (%d bytes) of the same workload, oracle/bz2_oracle.c, 1 thread" % sample.size,
+                                    "compressed_bytes": len(zc)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
