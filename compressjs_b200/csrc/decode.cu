@@ -1,5 +1,929 @@
-#include "ctx.h"
+// decode.cu -- many-block parallel bzip2 decode on the GPU.
+//
+// Reference: lib/Bzip2.js:90-548 (Bunzip: _start_bunzip, _get_next_block, _read_bunzip, decode,
+// decodeBlock, table).  The reference decodes strictly serially, one bit at a time.  Here:
+//
+//   k_scan_magic   : every bit offset is tested for the 48-bit block / end-of-stream magics
+//                    (blocks start at arbitrary bit positions and a .bz2 has no index)
+//   k_hdec         : one warp per candidate block: header parse (symbol map, selectors, code length
+//                    tables -- lib/Bzip2.js:137-275), canonical decode tables exactly as the
+//                    reference builds them (limit/base/permute) plus a 10-bit LUT derived from them,
+//                    then the Huffman symbol stream (lib/Bzip2.js:288-307)
+//   k_unmtf_a/scan/b: RUNA/RUNB expansion and inverse move-to-front (lib/Bzip2.js:312-361), chunk
+//                    parallel: per chunk the composite MTF permutation, a per-block scan over the
+//                    chunks, then every chunk replays from its true start list
+//   inverse BWT    : T-vector by one onesweep radix pass on the L column (lib/Bzip2.js:370-381),
+//                    then the n-step pointer chase (lib/Bzip2.js:418-423) is broken into ~440
+//                    independent walks per block between sampled rows (walk, chain, walk+emit)
+//   k_unrle_*      : RLE1 decode (lib/Bzip2.js:424-436): count bytes are identified from local
+//                    synchronisation points, output offsets by chained scan, CRC32 per block
+//   host           : walks the block chain (a block must start exactly where the previous one
+//                    ended), folds/validates CRCs and raises the reference's errors in stream order.
+#include <algorithm>
 #include <vector>
-int bzip2_decompress_device(Ctx& c, const u8* d_in, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n,
-                            bool single_block, u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len,
-                            u8** d_out_alloc) { throw B2Error{-200,"decode not built yet"}; }
+#include "enc.h"
+#include "radix.cuh"
+#include "radix_host.cuh"
+
+#define WHOLEPI 0x314159265359ull
+#define SQRTPI 0x177245385090ull
+#define SEL_CAP 32768
+#define DEC_OK 0
+#define DEC_NOT_BZIP (-2)
+#define DEC_DATA_ERROR (-5)
+#define DEC_OBSOLETE (-7)
+
+struct Cand {
+  u64 pos;     // bit position of the magic
+  u32 type;    // 1 = block, 2 = end of stream
+  u32 next32;  // the 32 bits that follow the magic (block CRC / stream CRC)
+};
+
+struct CandRes {
+  int status;      // 0 or a (negative) reference error code
+  u32 detail;      // 1 = "initial position out of bounds"
+  u32 m;           // decoded symbols incl. EOB
+  u32 orig;        // origPointer
+  u32 sym_total;   // distinct bytes
+  u32 n;           // block length after un-MTF (filled later)
+  u32 rawlen;      // bytes after RLE1 decode (filled later)
+  u32 pad;
+  u64 endbit;      // bit position just behind the EOB code
+  u8 sym_to_byte[256];
+};
+
+// ---- magic scan ---------------------------------------------------------------------------
+__global__ void k_scan_magic(const u8* __restrict__ in, u64 n, Cand* __restrict__ cands, u32* count, u32 cap) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 hi = 0;  // bytes i .. i+7
+  u32 lo = 0;  // bytes i+8 .. i+11
+  for (int k = 0; k < 8; k++) hi = (hi << 8) | (i + k < n ? in[i + k] : 0);
+  for (int k = 8; k < 12; k++) lo = (lo << 8) | (i + k < n ? in[i + k] : 0);
+  for (int s = 0; s < 8; s++) {
+    const u64 w = s ? ((hi << s) | (lo >> (32 - s))) : hi;
+    const u64 v = w >> 16;
+    if (v == WHOLEPI || v == SQRTPI) {
+      const u32 idx = atomicAdd(count, 1u);
+      if (idx < cap) {
+        Cand c;
+        c.pos = i * 8 + s;
+        c.type = v == WHOLEPI ? 1u : 2u;
+        // 32 bits behind the 48-bit magic: bits 48..79 of the window starting at (i, s)
+        const u64 w2 = ((w << 48) | ((u64)((s ? (lo << s) : lo)) << 16));
+        c.next32 = (u32)(w2 >> 32);
+        cands[idx] = c;
+      }
+    }
+  }
+}
+
+// ---- bit reader (one thread) ----------------------------------------------------------------
+struct BitReader {
+  const u32* words; u64 nwords; u64 widx; u64 buf; u32 avail;
+  __device__ __forceinline__ u32 fetch() {
+    u32 w = widx < nwords ? words[widx] : 0u;  // bits past EOF read as zeros (lib/BitStream.js:88-89)
+    widx++;
+    return __byte_perm(w, 0, 0x0123);
+  }
+  __device__ __forceinline__ void init(const u8* base, u64 nbytes, u64 bitpos) {
+    words = reinterpret_cast<const u32*>(base);
+    nwords = (nbytes + 3) / 4;  // the input buffer is zero padded to a multiple of 4 (+16)
+    widx = bitpos >> 5;
+    const u32 skip = (u32)(bitpos & 31);
+    buf = (u64)fetch() << 32;
+    buf <<= skip;
+    avail = 32 - skip;
+  }
+  __device__ __forceinline__ void ensure() {
+    if (avail <= 32) { buf |= (u64)fetch() << (32 - avail); avail += 32; }
+  }
+  __device__ __forceinline__ u32 peek(u32 k) { return k ? (u32)(buf >> (64 - k)) : 0u; }
+  __device__ __forceinline__ void skip(u32 k) { buf <<= k; avail -= k; }
+  __device__ __forceinline__ u32 get(u32 k) { ensure(); u32 v = peek(k); skip(k); return v; }
+  __device__ __forceinline__ u64 tell() const { return widx * 32 - avail; }
+};
+
+// ---- header + Huffman decode: one warp per candidate ----------------------------------------
+#define HD_WARPS 4
+struct HdecWarp {
+  int limit[HUFF_MAXGROUPS][22];
+  int base[HUFF_MAXGROUPS][22];
+  u16 permute[HUFF_MAXGROUPS][HUFF_MAXSYM + 2];
+  u16 lut[HUFF_MAXGROUPS][1024];
+  u8 len[HUFF_MAXGROUPS][HUFF_MAXSYM + 2];
+  int minlen[HUFF_MAXGROUPS], maxlen[HUFF_MAXGROUPS];
+  int status; u32 ngroups, nsel, symcount;
+};
+
+__global__ void __launch_bounds__(HD_WARPS * 32)
+k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u32 first, u32 count, u32 dbuf_size, u8* __restrict__ sel_buf,
+       u16* __restrict__ sym_out, CandRes* __restrict__ res) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HdecWarp* all = reinterpret_cast<HdecWarp*>(smem_raw);
+  const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 ci = blockIdx.x * HD_WARPS + w;
+  if (ci >= count) return;
+  HdecWarp& s = all[w];
+  const Cand cd = cands[first + ci];
+  CandRes* r = res + ci;
+  u8* sel = sel_buf + (size_t)ci * SEL_CAP;
+  u16* so = sym_out + ((size_t)ci << SEG_SHIFT);
+  BitReader br;
+  u32 symTotal = 0;
+  if (lane == 0) {
+    s.status = 0;
+    r->detail = 0; r->m = 0; r->n = 0; r->rawlen = 0; r->endbit = 0;
+    br.init(in, nbytes, cd.pos + 48 + 32);
+    do {
+      if (br.get(1)) { s.status = DEC_OBSOLETE; break; }           // lib/Bzip2.js:143
+      const u32 orig = br.get(24);
+      r->orig = orig;
+      if (orig > dbuf_size) { s.status = DEC_DATA_ERROR; r->detail = 1; break; }  // :146
+      const u32 t16 = br.get(16);
+      for (int i = 0; i < 16; i++) {
+        if (t16 & (1u << (15 - i))) {
+          const u32 k = br.get(16);
+          for (int j = 0; j < 16; j++)
+            if (k & (1u << (15 - j))) r->sym_to_byte[symTotal++] = (u8)(i * 16 + j);
+        }
+      }
+      const u32 gc = br.get(3);
+      if (gc < 2 || gc > 6) { s.status = DEC_DATA_ERROR; break; }    // :167
+      const u32 ns = br.get(15);
+      if (ns == 0) { s.status = DEC_DATA_ERROR; break; }             // :174
+      u8 mtf[HUFF_MAXGROUPS + 2];  // the reference's list is a zero-filled 256-entry buffer: slot gc reads as 0
+      for (u32 i = 0; i < HUFF_MAXGROUPS + 2; i++) mtf[i] = (u8)(i < gc ? i : 0);
+      bool bad = false;
+      for (u32 i = 0; i < ns && !bad; i++) {
+        u32 j = 0;
+        while (br.get(1)) { if (j >= gc) { bad = true; break; } j++; }   // :184-185
+        if (bad) break;
+        const u8 v = mtf[j];
+        for (u32 k = j; k > 0; k--) mtf[k] = mtf[k - 1];
+        mtf[0] = v;
+        sel[i] = v;
+      }
+      if (bad) { s.status = DEC_DATA_ERROR; break; }
+      const u32 symCount = symTotal + 2;
+      for (u32 g = 0; g < gc && !bad; g++) {
+        int t = (int)br.get(5);
+        for (u32 i = 0; i < symCount; i++) {
+          for (;;) {
+            if (t < 1 || t > 20) { bad = true; break; }               // :203
+            if (!br.get(1)) break;
+            if (!br.get(1)) t++; else t--;
+          }
+          if (bad) break;
+          s.len[g][i] = (u8)t;
+        }
+      }
+      if (bad) { s.status = DEC_DATA_ERROR; break; }
+      s.ngroups = gc; s.nsel = ns; s.symcount = symCount;
+    } while (0);
+    r->sym_total = symTotal;
+  }
+  __syncwarp();
+  if (s.status != 0) {
+    if (lane == 0) r->status = s.status;
+    return;
+  }
+  const u32 gc = s.ngroups, symCount = s.symcount;
+  // ---- limit / base / permute exactly as lib/Bzip2.js:216-274, one lane per table ----
+  if (lane < gc) {
+    const u32 g = lane;
+    int minLen = s.len[g][0], maxLen = s.len[g][0];
+    for (u32 i = 1; i < symCount; i++) {
+      const int l = s.len[g][i];
+      if (l > maxLen) maxLen = l; else if (l < minLen) minLen = l;
+    }
+    s.minlen[g] = minLen; s.maxlen[g] = maxLen;
+    int temp[22];
+    for (int i = 0; i < 22; i++) { temp[i] = 0; s.limit[g][i] = 0; s.base[g][i] = 0; }
+    for (u32 i = 0; i < HUFF_MAXSYM; i++) s.permute[g][i] = 0;
+    int pp = 0;
+    for (int i = minLen; i <= maxLen; i++)
+      for (u32 t = 0; t < symCount; t++)
+        if (s.len[g][t] == i) s.permute[g][pp++] = (u16)t;
+    for (u32 i = 0; i < symCount; i++) temp[s.len[g][i]]++;
+    pp = 0;
+    int t = 0;
+    for (int i = minLen; i < maxLen; i++) {
+      pp += temp[i];
+      s.limit[g][i] = pp - 1;
+      pp <<= 1;
+      t += temp[i];
+      s.base[g][i + 1] = pp - t;
+    }
+    s.limit[g][maxLen] = pp + temp[maxLen] - 1;
+    s.base[g][minLen] = 0;
+  }
+  __syncwarp();
+  // ---- 10-bit LUT derived from the reference's decode loop (lib/Bzip2.js:296-307) ----
+  for (u32 e = lane; e < gc * 1024; e += 32) {
+    const u32 g = e >> 10, p = e & 1023;
+    const int minLen = s.minlen[g], maxLen = s.maxlen[g];
+    u16 ent = 0;  // 0 = needs more than 10 bits (or fails): take the slow path
+    int i = minLen;
+    if (i <= 10) {
+      int j = (int)(p >> (10 - i));
+      for (;;) {
+        if (i > maxLen) break;
+        if (j <= s.limit[g][i]) {
+          const int jj = j - s.base[g][i];
+          if (jj >= 0 && jj < HUFF_MAXSYM) ent = (u16)((i << 9) | s.permute[g][jj]);
+          break;
+        }
+        i++;
+        if (i > 10) break;
+        j = (j << 1) | (int)((p >> (10 - i)) & 1);
+      }
+    }
+    s.lut[g][p] = ent;
+  }
+  __syncwarp();
+  // ---- symbol stream ----
+  if (lane == 0) {
+    int status = 0;
+    u32 m = 0, selector = 0, left = 0, g = 0, runs = 0;
+    const u32 ns = s.nsel;
+    for (;;) {
+      if (left == 0) {
+        left = HUFF_GROUP;
+        if (selector >= ns) { status = DEC_DATA_ERROR; break; }       // :291
+        g = sel[selector++];
+      }
+      left--;
+      br.ensure();
+      u32 sym;
+      const u16 ent = s.lut[g][br.peek(10)];
+      if (ent) {
+        sym = ent & 511u;
+        br.skip(ent >> 9);
+      } else {
+        int i = s.minlen[g];
+        int j = (int)br.peek((u32)i);
+        const u32 window = br.peek(21);
+        for (;;) {
+          if (i > s.maxlen[g]) { status = DEC_DATA_ERROR; break; }    // :299
+          if (j <= s.limit[g][i]) break;
+          i++;
+          j = (int)(window >> (21 - i));
+        }
+        if (status) break;
+        br.skip((u32)i);
+        const int jj = j - s.base[g][i];
+        if (jj < 0 || jj >= HUFF_MAXSYM) { status = DEC_DATA_ERROR; break; }  // :306
+        sym = s.permute[g][jj];
+      }
+      if (m >= SEG_SIZE - 1) { status = DEC_DATA_ERROR; break; }
+      so[m++] = (u16)sym;
+      if (sym <= 1) {
+        if (++runs > 40) { status = DEC_DATA_ERROR; break; }  // a run this long overflows any block; the reference would spin
+      } else {
+        runs = 0;
+        if (sym > symTotal) break;  // end of block (:345)
+      }
+    }
+    r->status = status;
+    r->m = m;
+    r->endbit = br.tell();
+  }
+}
+
+// ---- inverse MTF + run expansion --------------------------------------------------------------
+#define UM_CHUNK 4096
+#define UM_WARPS 8
+struct ChunkSum {
+  u64 leadval;   // sum (d_j+1) << j over the leading run digits
+  u32 nlead;     // number of leading run digits
+  u32 rest;      // bytes produced by everything behind the leading digits
+  u32 trail;     // run digits at the end of the chunk
+  u32 allrun;    // chunk consists of run digits only
+  u32 nsyms;
+  u32 bad;
+};
+
+// move list[idx] to the front; returns the moved value.  List = 8 bytes per lane (lo, hi).
+__device__ __forceinline__ u32 mtf_take(u32& lo, u32& hi, u32 idx, u32 lane) {
+  const u32 fl = idx >> 3, pos = idx & 7;
+  const u64 v0 = ((u64)hi << 32) | lo;
+  const u32 mine = (u32)(v0 >> (8 * pos)) & 255u;
+  const u32 c = __shfl_sync(FULL_MASK, mine, fl);
+  if (idx != 0) {
+    u32 carry = __shfl_up_sync(FULL_MASK, hi >> 24, 1);
+    if (lane == 0) carry = c;
+    u64 v = v0;
+    if (lane < fl) v = (v << 8) | carry;
+    else if (lane == fl) {
+      const u64 lowmask = (1ull << (8 * pos)) - 1;
+      const u64 highmask = pos == 7 ? 0ull : ~((1ull << (8 * (pos + 1))) - 1);
+      v = (v & highmask) | (((v & lowmask) << 8) | carry);
+    }
+    lo = (u32)v; hi = (u32)(v >> 32);
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(UM_WARPS * 32)
+k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, ChunkSum* __restrict__ sums, u8* __restrict__ perms) {
+  const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 gchunk = blockIdx.x * UM_WARPS + w;
+  const u32 ci = gchunk / cps, ch = gchunk % cps;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 m = r->m;
+  const u32 start = ch * UM_CHUNK;
+  if (start >= m) return;
+  const u32 count = min((u32)UM_CHUNK, m - start);
+  const u16* s = sym + ((size_t)ci << SEG_SHIFT) + start;
+  const u32 symTotal = r->sym_total;
+  u32 lo = 0x03020100u + lane * 0x08080808u, hi = 0x07060504u + lane * 0x08080808u;  // identity list
+  u64 leadval = 0; u32 nlead = 0, rest = 0, krun = 0, bad = 0;
+  bool seen_lit = false;
+  for (u32 base = 0; base < count; base += 32) {
+    const u32 mine = (base + lane < count) ? s[base + lane] : 0xffffu;
+    const u32 lim = min(32u, count - base);
+    for (u32 t = 0; t < lim; t++) {
+      const u32 sy = __shfl_sync(FULL_MASK, mine, t);
+      if (sy <= 1) {
+        if (!seen_lit) {
+          if (nlead < 40) leadval += (u64)(sy + 1) << nlead; else bad = 1;
+          nlead++;
+        } else {
+          if (krun < 31) rest += (sy + 1) << krun; else bad = 1;
+          krun++;
+        }
+      } else {
+        seen_lit = true; krun = 0;
+        if (sy <= symTotal) {
+          mtf_take(lo, hi, sy - 1, lane);
+          rest++;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    ChunkSum cs;
+    cs.leadval = leadval; cs.nlead = nlead; cs.rest = rest; cs.trail = seen_lit ? krun : nlead; cs.allrun = seen_lit ? 0u : 1u;
+    cs.nsyms = count; cs.bad = bad;
+    sums[gchunk] = cs;
+  }
+  u32* p = reinterpret_cast<u32*>(perms + (size_t)gchunk * 256);
+  p[lane * 2] = lo; p[lane * 2 + 1] = hi;
+}
+
+struct ChunkStart {
+  u32 k;    // run digits immediately before the chunk
+  u32 off;  // output offset of the chunk
+};
+
+__global__ void __launch_bounds__(32)
+k_unmtf_scan(CandRes* __restrict__ res, u32 ncand, u32 cps, u32 dbuf_size, const ChunkSum* __restrict__ sums, const u8* __restrict__ perms,
+             u8* __restrict__ lists, ChunkStart* __restrict__ starts) {
+  __shared__ u8 L[256], P[256];
+  const u32 ci = blockIdx.x, lane = threadIdx.x;
+  CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 m = r->m;
+  const u32 nch = (m + UM_CHUNK - 1) / UM_CHUNK;
+  for (u32 i = lane; i < 256; i += 32) L[i] = (u8)i;
+  __syncwarp();
+  u64 off = 0; u32 k = 0; int status = 0;
+  for (u32 ch = 0; ch < nch; ch++) {
+    const size_t gc = (size_t)ci * cps + ch;
+    const ChunkSum cs = sums[gc];
+    for (u32 i = lane; i < 256; i += 32) { lists[gc * 256 + i] = L[i]; P[i] = perms[gc * 256 + i]; }
+    if (lane == 0) { ChunkStart st; st.k = k; st.off = (u32)off; starts[gc] = st; }
+    if (cs.bad || (cs.nlead && k + cs.nlead > 32)) { status = DEC_DATA_ERROR; break; }
+    off += (cs.leadval << k) + cs.rest;
+    if (off > dbuf_size) { status = DEC_DATA_ERROR; break; }        // lib/Bzip2.js:338,354
+    k = cs.allrun ? k + cs.nsyms : cs.trail;
+    __syncwarp();
+    u8 nl[8];
+    for (int j = 0; j < 8; j++) nl[j] = L[P[lane * 8 + j]];
+    __syncwarp();
+    for (int j = 0; j < 8; j++) L[lane * 8 + j] = nl[j];
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (!status && r->orig >= (u32)off) status = DEC_DATA_ERROR;      // lib/Bzip2.js:368
+    r->status = status;
+    r->n = (u32)off;
+  }
+}
+
+__global__ void __launch_bounds__(UM_WARPS * 32)
+k_unmtf_b(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, const u8* __restrict__ lists,
+          const ChunkStart* __restrict__ starts, u8* __restrict__ tt) {
+  const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 gchunk = blockIdx.x * UM_WARPS + w;
+  const u32 ci = gchunk / cps, ch = gchunk % cps;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 m = r->m;
+  const u32 start = ch * UM_CHUNK;
+  if (start >= m) return;
+  const u32 count = min((u32)UM_CHUNK, m - start);
+  const u16* s = sym + ((size_t)ci << SEG_SHIFT) + start;
+  const u32 symTotal = r->sym_total;
+  const u32* lp = reinterpret_cast<const u32*>(lists + (size_t)gchunk * 256);
+  u32 lo = lp[lane * 2], hi = lp[lane * 2 + 1];
+  const ChunkStart st = starts[gchunk];
+  u32 k = st.k, o = st.off;
+  u8* out = tt + ((size_t)ci << SEG_SHIFT);
+  const u8* s2b = r->sym_to_byte;
+  for (u32 base = 0; base < count; base += 32) {
+    const u32 mine = (base + lane < count) ? s[base + lane] : 0xffffu;
+    const u32 lim = min(32u, count - base);
+    for (u32 t = 0; t < lim; t++) {
+      const u32 sy = __shfl_sync(FULL_MASK, mine, t);
+      if (sy <= 1) {
+        const u32 wgt = (sy + 1) << k;
+        k++;
+        const u8 b = s2b[__shfl_sync(FULL_MASK, lo & 255u, 0)];
+        for (u32 x = lane; x < wgt; x += 32) out[o + x] = b;
+        o += wgt;
+      } else {
+        k = 0;
+        if (sy <= symTotal) {
+          const u32 c = mtf_take(lo, hi, sy - 1, lane);
+          if (lane == 0) out[o] = s2b[c];
+          o++;
+        }
+      }
+    }
+  }
+}
+
+// ---- inverse BWT ------------------------------------------------------------------------------
+__global__ void k_ibwt_keys(const u8* __restrict__ tt, const u32* __restrict__ seg_n, u32 nslots, u32* __restrict__ key) {
+  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nslots) return;
+  if ((g & SEG_MASK) < seg_n[g >> SEG_SHIFT]) key[g] = tt[g];
+}
+// P[j] = T[j] << 8 | L[j]   (lib/Bzip2.js:370-381: dbuf[j] low byte = L column, high bits = next row)
+__global__ void k_ibwt_pack(const u8* __restrict__ tt, const u32* __restrict__ tvec, const u32* __restrict__ seg_n, u32 nslots, u32* __restrict__ P) {
+  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nslots) return;
+  if ((g & SEG_MASK) < seg_n[g >> SEG_SHIFT]) P[g] = ((tvec[g] & SEG_MASK) << 8) | tt[g];
+}
+
+#define IB_SHIFT 11
+#define IB_STEP (1u << IB_SHIFT)
+#define IB_SEGS (SEG_SIZE / IB_STEP + 1)  // sampled rows per block + the start row
+#define IB_VCAP 2048
+
+struct Seg { u32 len, next; };
+struct Visit { u32 row, off, len; };
+
+// walk from every sampled row (multiples of 2^11 and the start row) to the next sampled row
+__global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, Seg* __restrict__ segs) {
+  const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 ci = gid / IB_SEGS, sid = gid % IB_SEGS;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 n = r->n;
+  const u32* p = P + ((size_t)ci << SEG_SHIFT);
+  const u32 r0 = p[r->orig] >> 8;  // first row whose byte is output (lib/Bzip2.js:386-391)
+  u32 a;
+  if (sid == IB_SEGS - 1) { if ((r0 & (IB_STEP - 1)) == 0) return; a = r0; }
+  else { a = sid << IB_SHIFT; if (a >= n) return; }
+  u32 row = a, steps = 0;
+  do {
+    row = p[row] >> 8;
+    steps++;
+  } while ((row & (IB_STEP - 1)) != 0 && row != r0 && steps < n);
+  Seg sg;
+  sg.len = steps;
+  sg.next = ((row & (IB_STEP - 1)) == 0) ? (row >> IB_SHIFT) : (IB_SEGS - 1);
+  segs[(size_t)ci * IB_SEGS + sid] = sg;
+}
+
+// order the segments along the chain that starts at the start row
+__global__ void k_ibwt_chain(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Seg* __restrict__ segs,
+                             Visit* __restrict__ visits, u32* __restrict__ nvisits) {
+  const u32 ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0) { nvisits[ci] = 0; return; }
+  const u32 n = r->n;
+  const u32* p = P + ((size_t)ci << SEG_SHIFT);
+  const u32 r0 = p[r->orig] >> 8;
+  u32 cur = ((r0 & (IB_STEP - 1)) == 0) ? (r0 >> IB_SHIFT) : (IB_SEGS - 1);
+  u32 off = 0, nv = 0;
+  Visit* v = visits + (size_t)ci * IB_VCAP;
+  while (off < n) {
+    const Seg sg = segs[(size_t)ci * IB_SEGS + cur];
+    const u32 len = min(sg.len, n - off);
+    if (nv >= IB_VCAP) { nv = 0xffffffffu; break; }  // degenerate (periodic) block: fall back to one serial walk
+    Visit vv;
+    vv.row = (cur == IB_SEGS - 1) ? r0 : (cur << IB_SHIFT);
+    vv.off = off; vv.len = len;
+    v[nv++] = vv;
+    off += len;
+    cur = sg.next;
+  }
+  nvisits[ci] = nv;
+}
+
+__global__ void k_ibwt_walk2(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Visit* __restrict__ visits,
+                             const u32* __restrict__ nvisits, u8* __restrict__ out) {
+  const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 ci = gid / IB_VCAP, vi = gid % IB_VCAP;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 nv = nvisits[ci];
+  const u32* p = P + ((size_t)ci << SEG_SHIFT);
+  u8* o = out + ((size_t)ci << SEG_SHIFT);
+  u32 row, off, len;
+  if (nv == 0xffffffffu) {
+    if (vi != 0) return;
+    row = p[r->orig] >> 8; off = 0; len = r->n;
+  } else {
+    if (vi >= nv) return;
+    const Visit v = visits[(size_t)ci * IB_VCAP + vi];
+    row = v.row; off = v.off; len = v.len;
+  }
+  for (u32 t = 0; t < len; t++) {
+    const u32 e = p[row];
+    o[off + t] = (u8)e;
+    row = e >> 8;
+  }
+}
+
+// ---- RLE1 decode ------------------------------------------------------------------------------
+#define UR_THREADS 256
+#define UR_ITEMS 8
+#define UR_TILE (UR_THREADS * UR_ITEMS)
+
+__device__ __forceinline__ bool unrle_sync(const u8* b, u32 i) {
+  if (i == 0) return true;
+  if (b[i] == b[i - 1]) return false;
+  if (i >= 4 && b[i - 1] == b[i - 2] && b[i - 2] == b[i - 3] && b[i - 3] == b[i - 4]) return false;
+  return true;
+}
+// cls[i] = 1 when byte i is a repeat count (lib/Bzip2.js:424-436)
+__global__ void __launch_bounds__(256) k_unrle_classify(const u8* __restrict__ rle, const CandRes* __restrict__ res, u32 ncand, u8* __restrict__ cls) {
+  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 ci = g >> SEG_SHIFT, i = g & SEG_MASK;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0 || i >= r->n) return;
+  const u32 n = r->n;
+  const u8* b = rle + ((size_t)ci << SEG_SHIFT);
+  u8* c = cls + ((size_t)ci << SEG_SHIFT);
+  if (!unrle_sync(b, i)) return;
+  u32 j = i, run = 0;
+  int prev = -1;
+  for (;;) {
+    const int v = b[j];
+    c[j] = 0;
+    run = (v == prev) ? run + 1 : 1;
+    prev = v;
+    j++;
+    if (j >= n) break;
+    if (run == 4) {
+      c[j] = 1;
+      j++;
+      run = 0; prev = -1;
+      if (j >= n) break;
+    }
+    if (unrle_sync(b, j)) break;
+  }
+}
+
+__global__ void __launch_bounds__(UR_THREADS)
+k_unrle_scan(const u8* __restrict__ rle, const u8* __restrict__ cls, CandRes* __restrict__ res, u32 tps, u32* ticket, u64* status, u32* __restrict__ tileoff) {
+  __shared__ u32 ws[UR_THREADS / 32 + 1];
+  __shared__ u32 s_tile, s_carry;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 ci = tile / tps, lt = tile % tps;
+  CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 n = r->n;
+  const u32 start = lt * UR_TILE;
+  if (start >= n) return;
+  const u8* b = rle + ((size_t)ci << SEG_SHIFT);
+  const u8* c = cls + ((size_t)ci << SEG_SHIFT);
+  u32 sum = 0;
+  const u32 p0 = start + tid * UR_ITEMS;
+#pragma unroll
+  for (int j = 0; j < UR_ITEMS; j++) {
+    const u32 p = p0 + j;
+    if (p < n) sum += c[p] ? (u32)b[p] : 1u;
+  }
+  u32 total;
+  block_excl_add<UR_THREADS, u32>(sum, ws, &total);
+  if (tid < 32) {
+    u32 cr = lookback_warp(status + (size_t)ci * tps, lt, total, OpAdd());
+    if (tid == 0) s_carry = cr;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tileoff[(size_t)ci * tps + lt] = s_carry;
+    if (start + UR_TILE >= n) r->rawlen = s_carry + total;
+  }
+}
+
+__global__ void __launch_bounds__(UR_THREADS)
+k_unrle_emit(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandRes* __restrict__ res, u32 tps, const u32* __restrict__ tileoff,
+             const u64* __restrict__ outbase, u8* __restrict__ out) {
+  __shared__ u32 ws[UR_THREADS / 32 + 1];
+  const u32 tid = threadIdx.x;
+  const u32 ci = blockIdx.x / tps, lt = blockIdx.x % tps;
+  const u64 ob = outbase[ci];
+  if (ob == ~0ull) return;  // candidate is not part of the stream
+  const CandRes* r = res + ci;
+  const u32 n = r->n;
+  const u32 start = lt * UR_TILE;
+  if (start >= n) return;
+  const u8* b = rle + ((size_t)ci << SEG_SHIFT);
+  const u8* c = cls + ((size_t)ci << SEG_SHIFT);
+  u32 len[UR_ITEMS];
+  u32 sum = 0;
+  const u32 p0 = start + tid * UR_ITEMS;
+#pragma unroll
+  for (int j = 0; j < UR_ITEMS; j++) {
+    const u32 p = p0 + j;
+    len[j] = (p < n) ? (c[p] ? (u32)b[p] : 1u) : 0u;
+    sum += len[j];
+  }
+  u32 total;
+  const u32 ex = block_excl_add<UR_THREADS, u32>(sum, ws, &total);
+  u8* o = out + ob + tileoff[(size_t)ci * tps + lt] + ex;
+#pragma unroll
+  for (int j = 0; j < UR_ITEMS; j++) {
+    const u32 p = p0 + j;
+    if (p < n) {
+      if (c[p]) {
+        const u8 v = b[p - 1];
+        for (u32 x = 0; x < len[j]; x++) o[x] = v;
+      } else {
+        o[0] = b[p];
+      }
+      o += len[j];
+    }
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+static std::string hexs(u32 v) {
+  char b[16];
+  snprintf(b, sizeof b, "%x", v);
+  return b;
+}
+
+struct Event { int kind; size_t cand; u32 a, b; int code; std::string msg; };  // kind: 0 block, 1 eos, 2 error
+
+int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n, bool single_block,
+                            u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len, u8** d_out_alloc) {
+  *out_n = 0;
+  if (d_out_alloc) *d_out_alloc = nullptr;
+  // padded private copy of the input (aligned word reads past the end must be safe)
+  DBuf<u8> din(c, n + 32);
+  CUDA_CHECK(cudaMemsetAsync(din.p + (n & ~(size_t)3), 0, (n + 32) - (n & ~(size_t)3), c.stream));
+  if (n) CUDA_CHECK(cudaMemcpyAsync(din, d_in_user, n, cudaMemcpyDeviceToDevice, c.stream));
+  u8 hdr[4] = {0, 0, 0, 0};
+  if (n >= 4) CUDA_CHECK(cudaMemcpyAsync(hdr, din, 4, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  // lib/Bzip2.js:105-124 _start_bunzip
+  if (n < 4 || hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h') throw B2Error{DEC_NOT_BZIP, "Not bzip data: bad magic"};
+  int level = hdr[3] - 0x30;
+  if (level < 1 || level > 9) throw B2Error{DEC_NOT_BZIP, "Not bzip data: level out of range"};
+  u32 dbuf_size = 100000u * (u32)level;
+
+  // ---- 1. candidates ----
+  std::vector<Cand> cands;
+  {
+    StageScope ss(c, ST_SCAN);
+    const u32 cap = (u32)(n / 8000 + 1024);
+    DBuf<Cand> dc(c, cap);
+    DBuf<u32> dcount(c, 1);
+    CUDA_CHECK(cudaMemsetAsync(dcount, 0, 4, c.stream));
+    k_scan_magic<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(din, n, dc, dcount, cap);
+    KLAUNCH(c); KCHECK();
+    u32 cnt = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&cnt, dcount, 4, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (cnt > cap) throw B2Error{B2_ERR_CUDA, "too many magic candidates"};
+    cands.resize(cnt);
+    if (cnt) CUDA_CHECK(cudaMemcpyAsync(cands.data(), dc, sizeof(Cand) * cnt, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.pos < b.pos; });
+  }
+  // block candidates that are decoded
+  std::vector<size_t> blk_idx;  // index into cands
+  if (single_block) {
+    // lib/Bzip2.js:482-503: seekBit(pos) then one _get_next_block
+    const Cand* hit = nullptr;
+    for (auto& cd : cands) if (cd.pos == bitpos) hit = &cd;
+    if (!hit) throw B2Error{DEC_NOT_BZIP, "Not bzip data"};
+    if (hit->type == 2) { *out_n = 0; return 0; }
+    blk_idx.push_back((size_t)(hit - cands.data()));
+  } else {
+    for (size_t i = 0; i < cands.size(); i++) if (cands[i].type == 1) blk_idx.push_back(i);
+  }
+  const size_t nb = blk_idx.size();
+  std::vector<Cand> bc(nb);
+  for (size_t i = 0; i < nb; i++) bc[i] = cands[blk_idx[i]];
+  std::vector<CandRes> hres(nb);
+  // persistent per-candidate arrays
+  DBuf<Cand> dcand(c, nb ? nb : 1);
+  DBuf<CandRes> dres(c, nb ? nb : 1);
+  DBuf<u8> rle(c, (nb ? nb : 1) << SEG_SHIFT), cls(c, (nb ? nb : 1) << SEG_SHIFT);
+  const u32 ur_tps = SEG_SIZE / UR_TILE;
+  DBuf<u32> tileoff(c, (nb ? nb : 1) * (size_t)ur_tps);
+  if (nb) CUDA_CHECK(cudaMemcpyAsync(dcand, bc.data(), sizeof(Cand) * nb, cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+
+  // ---- 2. decode every candidate block, in batches ----
+  const u32 DB = std::max(1u, std::min(c.bwt_batch, 128u));
+  static bool attr = false;
+  if (!attr) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HdecWarp) * HD_WARPS)));
+    attr = true;
+  }
+  if (nb) {
+    const u32 nbm = (u32)std::min<size_t>(DB, nb);
+    DBuf<u16> sym(c, (size_t)nbm << SEG_SHIFT);
+    DBuf<u8> selbuf(c, (size_t)nbm * SEL_CAP), tt(c, (size_t)nbm << SEG_SHIFT);
+    const u32 cps = SEG_SIZE / UM_CHUNK;
+    DBuf<ChunkSum> sums(c, (size_t)nbm * cps);
+    DBuf<u8> perms(c, (size_t)nbm * cps * 256), lists(c, (size_t)nbm * cps * 256);
+    DBuf<ChunkStart> starts(c, (size_t)nbm * cps);
+    DBuf<u32> keyA(c, (size_t)nbm << SEG_SHIFT), keyB(c, (size_t)nbm << SEG_SHIFT), valA(c, (size_t)nbm << SEG_SHIFT), valB(c, (size_t)nbm << SEG_SHIFT);
+    DBuf<u32> dn(c, nbm), nvis(c, nbm), ticket(c, 1);
+    DBuf<Seg> segs(c, (size_t)nbm * IB_SEGS);
+    DBuf<Visit> visits(c, (size_t)nbm * IB_VCAP);
+    DBuf<u64> lbst(c, (size_t)nbm * ur_tps);
+    std::vector<u32> hn(nbm);
+    for (size_t k0 = 0; k0 < nb; k0 += DB) {
+      const u32 cnt = (u32)std::min<size_t>(DB, nb - k0);
+      CandRes* rb = dres.p + k0;
+      {
+        StageScope ss(c, ST_HDEC);
+        k_hdec<<<(cnt + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, sizeof(HdecWarp) * HD_WARPS, c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size,
+                                                                                                       selbuf, sym, rb);
+        KLAUNCH(c); KCHECK();
+      }
+      {
+        StageScope ss(c, ST_UNMTF);
+        const u32 chunks = cnt * cps;
+        k_unmtf_a<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, sums, perms);
+        KLAUNCH(c); KCHECK();
+        k_unmtf_scan<<<cnt, 32, 0, c.stream>>>(rb, cnt, cps, dbuf_size, sums, perms, lists, starts);
+        KLAUNCH(c); KCHECK();
+        k_unmtf_b<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, lists, starts, tt);
+        KLAUNCH(c); KCHECK();
+      }
+      CUDA_CHECK(cudaMemcpyAsync(hres.data() + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      u32 nmax = 0; u64 ntot = 0;
+      for (u32 i = 0; i < cnt; i++) { hn[i] = hres[k0 + i].status == 0 ? hres[k0 + i].n : 0; nmax = std::max(nmax, hn[i]); ntot += hn[i]; }
+      if (nmax) {
+        StageScope ss(c, ST_IBWT);
+        CUDA_CHECK(cudaMemcpyAsync(dn, hn.data(), cnt * 4, cudaMemcpyHostToDevice, c.stream));
+        const u32 nslots = cnt << SEG_SHIFT;
+        u32 *kin = keyA, *kout = keyB, *vin = valA, *vout = valB;
+        k_ibwt_keys<<<(nslots + 255) / 256, 256, 0, c.stream>>>(tt, dn, nslots, kin);
+        KLAUNCH(c); KCHECK();
+        radix_sort<u32>(c, kin, vin, kout, vout, dn, cnt, SEG_SHIFT, nmax, 0, 1, true, ntot);
+        u32* Pp = kout;  // the other key buffer is free now
+        k_ibwt_pack<<<(nslots + 255) / 256, 256, 0, c.stream>>>(tt, vin, dn, nslots, Pp);
+        KLAUNCH(c); KCHECK();
+        k_ibwt_walk1<<<(cnt * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Pp, rb, cnt, segs);
+        KLAUNCH(c); KCHECK();
+        k_ibwt_chain<<<(cnt + 31) / 32, 32, 0, c.stream>>>(Pp, rb, cnt, segs, visits, nvis);
+        KLAUNCH(c); KCHECK();
+        k_ibwt_walk2<<<(cnt * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Pp, rb, cnt, visits, nvis, rle.p + (k0 << SEG_SHIFT));
+        KLAUNCH(c); KCHECK();
+      }
+      if (nmax) {
+        StageScope ss(c, ST_UNRLE);
+        const u32 nslots = cnt << SEG_SHIFT;
+        k_unrle_classify<<<(nslots + 255) / 256, 256, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), rb, cnt, cls.p + (k0 << SEG_SHIFT));
+        KLAUNCH(c); KCHECK();
+        CUDA_CHECK(cudaMemsetAsync(lbst, 0, (size_t)cnt * ur_tps * 8, c.stream));
+        CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+        k_unrle_scan<<<cnt * ur_tps, UR_THREADS, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), cls.p + (k0 << SEG_SHIFT), rb, ur_tps, ticket, lbst,
+                                                               tileoff.p + k0 * ur_tps);
+        KLAUNCH(c); KCHECK();
+        CUDA_CHECK(cudaMemcpyAsync(hres.data() + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      c.stats.blocks += cnt;
+    }
+  }
+
+  // ---- 3. walk the chain in stream order (lib/Bzip2.js:454-481 / 508-548) ----
+  std::vector<Event> events;
+  std::vector<u64> outbase(nb ? nb : 1, ~0ull);
+  u64 total_out = 0;
+  auto find_cand = [&](u64 pos) -> long {
+    size_t lo = 0, hi = cands.size();
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (cands[mid].pos < pos) lo = mid + 1; else hi = mid; }
+    return (lo < cands.size() && cands[lo].pos == pos) ? (long)lo : -1;
+  };
+  std::vector<long> cand_to_blk(cands.size(), -1);
+  for (size_t i = 0; i < nb; i++) cand_to_blk[blk_idx[i]] = (long)i;
+  auto block_event = [&](size_t bi) -> bool {  // returns false when the walk must stop (error recorded)
+    const CandRes& r = hres[bi];
+    if (r.status != 0) {
+      std::string msg = r.status == DEC_OBSOLETE ? "Obsolete (pre 0.9.5) bzip format not supported." : "Data error";
+      if (r.detail == 1) msg += ": initial position out of bounds";
+      events.push_back({2, bi, 0, 0, r.status, msg});
+      return false;
+    }
+    outbase[bi] = total_out;
+    total_out += r.rawlen;
+    events.push_back({0, bi, 0, 0, 0, ""});
+    return true;
+  };
+  if (single_block) {
+    block_event(0);
+  } else {
+    u64 pos = 32;
+    u32 stream_crc = 0;
+    for (;;) {
+      if ((pos + 7) / 8 >= n) break;  // 'eof' in inputStream && inputStream.eof() (lib/Bzip2.js:462)
+      const long ci = find_cand(pos);
+      if (ci < 0) { events.push_back({2, 0, 0, 0, DEC_NOT_BZIP, "Not bzip data"}); break; }
+      if (cands[ci].type == 1) {
+        const size_t bi = (size_t)cand_to_blk[ci];
+        stream_crc = cands[ci].next32 ^ ((stream_crc << 1) | (stream_crc >> 31));  // lib/Bzip2.js:138-139
+        if (!block_event(bi)) break;
+        pos = hres[bi].endbit;
+      } else {
+        events.push_back({1, 0, stream_crc, cands[ci].next32, 0, ""});
+        pos += 80;
+        const u64 bytepos = (pos + 7) / 8;
+        if (multistream && bytepos < n) {
+          // _start_bunzip on the byte stream (resyncs to the next byte)
+          u8 h2[4] = {0, 0, 0, 0};
+          const size_t avail = (size_t)std::min<u64>(4, n - bytepos);
+          CUDA_CHECK(cudaMemcpyAsync(h2, din.p + bytepos, avail, cudaMemcpyDeviceToHost, c.stream));
+          CUDA_CHECK(cudaStreamSynchronize(c.stream));
+          if (avail != 4 || h2[0] != 'B' || h2[1] != 'Z' || h2[2] != 'h') { events.push_back({2, 0, 0, 0, DEC_NOT_BZIP, "Not bzip data: bad magic"}); break; }
+          const int lv = h2[3] - 0x30;
+          if (lv < 1 || lv > 9) { events.push_back({2, 0, 0, 0, DEC_NOT_BZIP, "Not bzip data: level out of range"}); break; }
+          if ((u32)lv * 100000u != dbuf_size) { events.push_back({2, 0, 0, 0, B2_ERR_BAD_ARG, "multistream members with different block sizes are not supported"}); break; }
+          stream_crc = 0;
+          pos = (bytepos + 4) * 8;
+        } else break;
+      }
+    }
+  }
+
+  // ---- 4. expand the chain blocks, CRC them ----
+  u8* dout = d_out;
+  DBuf<u8> own;
+  if (!d_out) {
+    own.alloc(c, total_out ? total_out : 1);
+    dout = own.p;
+  } else if (total_out > out_cap) {
+    *out_n = (size_t)total_out;
+    throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
+  }
+  std::vector<u32> got_crc(nb ? nb : 1, 0);
+  if (nb) {
+    StageScope ss(c, ST_UNRLE);
+    DBuf<u64> dob(c, nb);
+    CUDA_CHECK(cudaMemcpyAsync(dob, outbase.data(), 8 * nb, cudaMemcpyHostToDevice, c.stream));
+    k_unrle_emit<<<(unsigned)(nb * ur_tps), UR_THREADS, 0, c.stream>>>(rle, cls, dres, ur_tps, tileoff, dob, dout);
+    KLAUNCH(c); KCHECK();
+    std::vector<BlkInfo> ranges(nb);
+    for (size_t i = 0; i < nb; i++) {
+      memset(&ranges[i], 0, sizeof(BlkInfo));
+      if (outbase[i] != ~0ull) { ranges[i].s = outbase[i]; ranges[i].e = outbase[i] + hres[i].rawlen; }
+    }
+    DBuf<BlkInfo> dr(c, nb);
+    DBuf<u32> dcrc(c, nb);
+    CUDA_CHECK(cudaMemcpyAsync(dr, ranges.data(), sizeof(BlkInfo) * nb, cudaMemcpyHostToDevice, c.stream));
+    crc_ranges(c, dout, dr, ranges, dcrc);
+    CUDA_CHECK(cudaMemcpyAsync(got_crc.data(), dcrc, 4 * nb, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  }
+  // ---- 5. replay the events: first failure in stream order wins ----
+  for (auto& ev : events) {
+    if (ev.kind == 0) {
+      const u32 want = bc[ev.cand].next32, got = got_crc[ev.cand];
+      if (want != got) throw B2Error{DEC_DATA_ERROR, "Data error: Bad block CRC (got " + hexs(got) + " expected " + hexs(want) + ")"};
+      if (tab_pos) { tab_pos->push_back(bc[ev.cand].pos); tab_len->push_back(hres[ev.cand].rawlen); }
+    } else if (ev.kind == 1) {
+      if (!tab_pos && ev.a != ev.b) throw B2Error{DEC_DATA_ERROR, "Data error: Bad stream CRC (got " + hexs(ev.a) + " expected " + hexs(ev.b) + ")"};
+    } else {
+      throw B2Error{ev.code, ev.msg};
+    }
+  }
+  *out_n = (size_t)total_out;
+  if (!d_out && d_out_alloc) { *d_out_alloc = own.p; own.p = nullptr; }
+  return 0;
+}

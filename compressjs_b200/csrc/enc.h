@@ -48,3 +48,6 @@ void huffman_batch(Ctx& c, const u16* d_sym, const u32* d_m, const u32* d_freq, 
 // bit packing of blocks at their final bit offsets (lib/Bzip2.js:740-741,749-758,847-874)
 void pack_batch(Ctx& c, const u16* d_sym, const u8* d_sel, const u8* d_selmtf, const HuffBlk* d_hb, const u32* d_used, const u32* d_pidx,
                 const u32* d_crc, const u64* d_bitoff, const u32* d_flag, u32 nblk, u32 max_m, u32* d_out_words);
+
+#include <vector>
+void crc_ranges(Ctx& c, const u8* d_data, const BlkInfo* d_ranges, const std::vector<BlkInfo>& h_ranges, u32* d_crc_out);

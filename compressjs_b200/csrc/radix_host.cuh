@@ -1,0 +1,42 @@
+// radix_host.cuh -- host driver of the segmented onesweep radix sort (radix.cuh).
+#pragma once
+#include "ctx.h"
+#include "radix.cuh"
+
+template <typename KeyT>
+static void radix_sort(Ctx& c, KeyT*& kin, u32*& vin, KeyT*& kout, u32*& vout, const u32* d_seg_n, u32 nseg, u32 seg_shift,
+                       u32 max_seg_n, u32 begin_bit, u32 npass, bool iota_first, u64 total_elems) {
+  if (npass == 0 || total_elems == 0) return;
+  static bool attr_set = false;  // per translation unit (kernels are instantiated per TU)
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<u32>)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<u64>)));
+    attr_set = true;
+  }
+  const u32 tps = (max_seg_n + RP_TILE - 1) / RP_TILE;
+  const u32 htps = (max_seg_n + RH_TILE - 1) / RH_TILE;
+  const size_t ntiles = (size_t)tps * nseg;
+  DBuf<u32> hist(c, (size_t)nseg * npass * RADIX), status(c, ntiles * RADIX), ticket(c, 1);
+  CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)nseg * npass * RADIX * 4, c.stream));
+  k_radix_hist<KeyT><<<htps * nseg, RH_THREADS, 0, c.stream>>>(kin, d_seg_n, htps, seg_shift, hist, npass, begin_bit);
+  KLAUNCH(c); KCHECK();
+  c.stats.bwt_bytes += total_elems * sizeof(KeyT);
+  for (u32 p = 0; p < npass; p++) {
+    CUDA_CHECK(cudaMemsetAsync(status, 0, ntiles * RADIX * 4, c.stream));
+    CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+    const int iota = (iota_first && p == 0) ? 1 : 0;
+    size_t ev = c.begin(ST_RADIX);
+    k_radix_pass<KeyT><<<(unsigned)ntiles, RP_THREADS, sizeof(RadixSmem<KeyT>), c.stream>>>(
+        kin, vin, kout, vout, d_seg_n, tps, seg_shift, hist, npass, p, begin_bit + p * RADIX_BITS, ticket, status, iota);
+    c.end(ev);
+    KLAUNCH(c); KCHECK();
+    const u64 bytes = total_elems * (2 * sizeof(KeyT) + (iota ? 4 : 8));
+    c.stats.radix_launches++;
+    c.stats.radix_bytes += bytes;
+    c.stats.bwt_bytes += bytes;
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  // result is in (kin, vin) after the swaps
+}
+

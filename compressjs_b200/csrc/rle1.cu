@@ -625,3 +625,29 @@ void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, si
   // tbase/pbase/hn are pageable host vectors: make sure the async copies are done before they die
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
+
+// CRC32 of arbitrary byte ranges [s,e) of one device buffer (decoder: per-block CRC of the output).
+// h_ranges/d_ranges: only .s and .e are used.
+void crc_ranges(Ctx& c, const u8* d_data, const BlkInfo* d_ranges, const std::vector<BlkInfo>& h_ranges, u32* d_crc_out) {
+  crc_setup();
+  const size_t count = h_ranges.size();
+  if (count == 0) return;
+  std::vector<u64> pbase(count + 1);
+  u64 pp = 0;
+  for (size_t k = 0; k < count; k++) {
+    pbase[k] = pp;
+    pp += (h_ranges[k].e - h_ranges[k].s + CRC_PIECE - 1) / CRC_PIECE;
+  }
+  pbase[count] = pp;
+  DBuf<u64> dpb(c, count + 1);
+  DBuf<u32> acc(c, count);
+  CUDA_CHECK(cudaMemcpyAsync(dpb, pbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * count, c.stream));
+  if (pp) {
+    k_crc_pieces<<<(unsigned)((pp + 255) / 256), 256, 0, c.stream>>>(d_data, d_ranges, 0, (u32)count, dpb, pp, acc);
+    KLAUNCH(c); KCHECK();
+  }
+  k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d_ranges, 0, (u32)count, acc, d_crc_out);
+  KLAUNCH(c); KCHECK();
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
