@@ -174,29 +174,50 @@ def main():
     if rc:
         raise SystemExit("b2_init: " + _native.last_error())
 
-    nbytes = args.mb << 20
-    host = gen_ascii(nbytes, SEED + rank)  # every rank owns an independent shard of blocks (weak scaling)
+    shard = args.mb << 20
+    nbytes = shard * world
+    # weak scaling: the job is ONE stream of world x shard bytes; every rank holds the input (the block
+    # cutting scan needs it), encodes a contiguous range of blocks, and the fragments are gathered over NCCL.
+    host = np.concatenate([gen_ascii(shard, SEED + r) for r in range(world)]) if world > 1 else gen_ascii(shard, SEED)
     pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     pinned.numpy()[:] = host
     d_in = pinned.cuda(non_blocking=False)
     cap = L.b2_bzip2_bound(nbytes)
-    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda") if world == 1 else None
     out_n = C.c_size_t()
+    from compressjs_b200 import sharded as SH
+    state = {"comp": 0}
 
     def step_resident():
-        rc = L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n))
-        if rc:
-            raise SystemExit("compress_dev failed: " + _native.last_error())
-        return _native.stats()
+        if world == 1:
+            rc = L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n))
+            if rc:
+                raise SystemExit("compress_dev failed: " + _native.last_error())
+            state["comp"] = out_n.value
+            return _native.stats()
+        out = SH.compress_file_sharded(d_in, LEVEL)
+        st = _native.stats()
+        if out is not None:
+            state["comp"] = out.numel()
+        return st
 
     def step_e2e():
-        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
-        rc = L.b2_bzip2_compress(pinned.data_ptr(), nbytes, LEVEL, C.byref(out), C.byref(n))
-        if rc:
-            raise SystemExit("compress failed: " + _native.last_error())
-        st = _native.stats()
-        L.b2_free(out)
-        return st, n.value
+        if world == 1:
+            out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+            rc = L.b2_bzip2_compress(pinned.data_ptr(), nbytes, LEVEL, C.byref(out), C.byref(n))
+            if rc:
+                raise SystemExit("compress failed: " + _native.last_error())
+            st = _native.stats()
+            L.b2_free(out)
+            return st, n.value
+        d = pinned.cuda(non_blocking=True)          # H2D of the step's input
+        torch.cuda.current_stream().synchronize()   # the library works on its own stream
+        out = SH.compress_file_sharded(d, LEVEL)
+        nn = 0
+        if out is not None:
+            hostout = out.cpu()                      # D2H of the step's result
+            nn = hostout.numel()
+        return _native.stats(), nn
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,15 +235,20 @@ def main():
     t0 = time.perf_counter()
     agg = {}
     dev_ms = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     for _ in range(args.steps):
         st = step_resident()
         dev_ms += st["ms_total"]
         for k, v in st.items():
             agg[k] = agg.get(k, 0) + v
+    ev1.record()
     barrier()
     wall = time.perf_counter() - t0
+    if world > 1:
+        dev_ms = ev0.elapsed_time(ev1)  # includes the NCCL gather and the assembly on rank 0
     clocks = sampler.stop() if rank == 0 else None
-    comp_bytes = out_n.value
+    comp_bytes = state["comp"]
 
     # device time: max over ranks (events on the library's launching stream)
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
@@ -246,7 +272,7 @@ def main():
     e2e_wall = t.item()
 
     if rank == 0:
-        total_raw = nbytes * world
+        total_raw = nbytes
         value = total_raw * args.steps / (dev_ms_max / 1e3) / 1e6
         peak, peak_src = peaks()
         radix_gbs = (agg["radix_bytes"] / 1e9) / (agg["ms_radix"] / 1e3) if agg.get("ms_radix") else 0.0
@@ -257,11 +283,12 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": "%d MiB synthetic ASCII per GPU (PCG64 seed %d+rank), bzip2 -9 (900k blocks) encode" % (args.mb, SEED),
-                       "level": LEVEL, "bytes_per_gpu": nbytes, "blocks_per_gpu": int(agg["blocks"] // max(args.steps, 1)),
+                       "level": LEVEL, "bytes_per_gpu": shard, "total_bytes": nbytes, "blocks_per_gpu": int(agg["blocks"] // max(args.steps, 1)),
                        "l2": "inputs (%d MiB) larger than L2 (126 MB); no flush needed" % args.mb, "bwt_batch_blocks": int(os.environ.get("B2_BWT_BATCH", "64")),
-                       "compressed_bytes_per_gpu": comp_bytes, "wall_ms_per_step": wall_ms_max / args.steps},
-            "e2e": {"value": total_raw * e2e_steps / e2e_wall / 1e6, "unit": "MB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": e2e_comp,
-                    "steps": e2e_steps, "api": "b2_bzip2_compress (host pinned in, library-pinned out)"},
+                       "compressed_bytes": comp_bytes, "wall_ms_per_step": wall_ms_max / args.steps},
+            "e2e": {"value": total_raw * e2e_steps / e2e_wall / 1e6, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": e2e_comp,
+                    "steps": e2e_steps, "api": "b2_bzip2_compress (host pinned in, library-pinned out)" if world == 1 else
+                    "sharded.compress_file_sharded (pinned host in on every rank, stream gathered to rank 0 over NCCL, D2H on rank 0)"},
             "gpu_launches": int(agg["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_radix_pass (BWT onesweep pass)", "achieved": radix_gbs, "peak": peak, "unit": "GB/s",
                          "frac": radix_gbs / peak if peak else None, "traffic": (tr or {}).get("dram_bytes_per_launch"),
@@ -273,6 +300,24 @@ def main():
             "stages_ms_per_step": {k: agg[k] / args.steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack", "ms_radix")},
             "clocks": clocks,
         }
+        if world == 1:
+            # decode leg: the stream just produced, HBM resident (b2_bzip2_decompress_dev) -- the second half of the metric
+            d_dec = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            dn = C.c_size_t()
+            comp = comp_bytes
+            L.b2_bzip2_decompress_dev(d_out.data_ptr(), comp, 0, d_dec.data_ptr(), nbytes, C.byref(dn))
+            dms, dst = 0.0, None
+            dsteps = max(1, min(args.steps, 3))
+            for _ in range(dsteps):
+                rc = L.b2_bzip2_decompress_dev(d_out.data_ptr(), comp, 0, d_dec.data_ptr(), nbytes, C.byref(dn))
+                if rc:
+                    raise SystemExit("decompress_dev failed: " + _native.last_error())
+                dst = _native.stats()
+                dms += dst["ms_total"]
+            ok = bool(torch.equal(d_dec[: dn.value], d_in)) and dn.value == nbytes
+            line["decode"] = {"metric": "bzip2_-9_decode_MBps", "value": nbytes * dsteps / (dms / 1e3) / 1e6, "unit": "MB/s", "steps": dsteps,
+                              "roundtrip_ok": ok, "ms_per_step": dms / dsteps,
+                              "stages_ms": {k: dst[k] for k in ("ms_scan", "ms_hdec", "ms_unmtf", "ms_ibwt", "ms_unrle")}}
         if not args.no_cpu and world == 1:
             from oracle import oracle as O
             O.build()

@@ -1,0 +1,112 @@
+// addon.cc -- Node N-API veneer over include/b2bz.h (cannot be built in the graft image: no node
+// headers).  It only marshals Buffers; every byte of work happens behind the C ABI.
+// Build (where node-gyp exists): node-gyp configure build  with libraries: ["-lb2bz"].
+#include <node_api.h>
+#include <stdint.h>
+#include "../../include/b2bz.h"
+
+static void fin(napi_env, void* data, void*) { b2_free(data); }
+
+static napi_value fail(napi_env env, int rc) {
+  napi_value msg, err, code;
+  napi_create_string_utf8(env, b2_last_error(), NAPI_AUTO_LENGTH, &msg);
+  if (rc == B2_ERR_BAD_LEVEL) napi_create_error(env, nullptr, msg, &err);        // `new Error(...)` lib/Bzip2.js:888-890
+  else napi_create_type_error(env, nullptr, msg, &err);                            // `new TypeError(...)` lib/Bzip2.js:82-88
+  napi_create_int32(env, rc, &code);
+  napi_set_named_property(env, err, "errorCode", code);
+  napi_throw(env, err);
+  return nullptr;
+}
+
+static bool buf_arg(napi_env env, napi_value v, const uint8_t** p, size_t* n) {
+  void* d = nullptr;
+  if (napi_get_buffer_info(env, v, &d, n) != napi_ok) return false;
+  *p = (const uint8_t*)d;
+  return true;
+}
+
+// compressFile(buffer, level) -> Buffer            (Bzip2.compressFile, lib/Bzip2.js:879)
+static napi_value CompressFile(napi_env env, napi_callback_info info) {
+  size_t argc = 2; napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* in; size_t n; int32_t level = 9;
+  if (!buf_arg(env, argv[0], &in, &n)) return fail(env, B2_ERR_BAD_ARG);
+  napi_get_value_int32(env, argv[1], &level);
+  uint8_t* out; size_t out_n;
+  int rc = b2_bzip2_compress(in, n, level, &out, &out_n);
+  if (rc) return fail(env, rc);
+  napi_value buf; napi_create_external_buffer(env, out_n, out, fin, nullptr, &buf);
+  return buf;
+}
+// decompressFile(buffer, multistream) -> Buffer    (Bunzip.decode, lib/Bzip2.js:454)
+static napi_value DecompressFile(napi_env env, napi_callback_info info) {
+  size_t argc = 2; napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* in; size_t n; bool ms = false;
+  if (!buf_arg(env, argv[0], &in, &n)) return fail(env, B2_ERR_BAD_ARG);
+  if (argc > 1) napi_get_value_bool(env, argv[1], &ms);
+  uint8_t* out; size_t out_n;
+  int rc = b2_bzip2_decompress(in, n, ms ? 1 : 0, &out, &out_n);
+  if (rc) return fail(env, rc);
+  napi_value buf; napi_create_external_buffer(env, out_n, out, fin, nullptr, &buf);
+  return buf;
+}
+// decompressBlock(buffer, bitpos) -> Buffer        (Bunzip.decodeBlock, lib/Bzip2.js:482)
+static napi_value DecompressBlock(napi_env env, napi_callback_info info) {
+  size_t argc = 2; napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* in; size_t n; double pos = 0;
+  if (!buf_arg(env, argv[0], &in, &n)) return fail(env, B2_ERR_BAD_ARG);
+  napi_get_value_double(env, argv[1], &pos);
+  uint8_t* out; size_t out_n;
+  int rc = b2_bzip2_decompress_block(in, n, (uint64_t)pos, &out, &out_n);
+  if (rc) return fail(env, rc);
+  napi_value buf; napi_create_external_buffer(env, out_n, out, fin, nullptr, &buf);
+  return buf;
+}
+// table(buffer, multistream) -> [[bitpos, size], ...]   (Bunzip.table, lib/Bzip2.js:508)
+static napi_value Table(napi_env env, napi_callback_info info) {
+  size_t argc = 2; napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* in; size_t n; bool ms = false;
+  if (!buf_arg(env, argv[0], &in, &n)) return fail(env, B2_ERR_BAD_ARG);
+  if (argc > 1) napi_get_value_bool(env, argv[1], &ms);
+  uint64_t* bp; uint32_t* sz; size_t cnt;
+  int rc = b2_bzip2_table(in, n, ms ? 1 : 0, &bp, &sz, &cnt);
+  if (rc) return fail(env, rc);
+  napi_value arr; napi_create_array_with_length(env, cnt, &arr);
+  for (size_t i = 0; i < cnt; i++) {
+    napi_value row, a, b;
+    napi_create_array_with_length(env, 2, &row);
+    napi_create_double(env, (double)bp[i], &a); napi_create_uint32(env, sz[i], &b);
+    napi_set_element(env, row, 0, a); napi_set_element(env, row, 1, b);
+    napi_set_element(env, arr, (uint32_t)i, row);
+  }
+  b2_free(bp); b2_free(sz);
+  return arr;
+}
+// bwtransform2(T, U, n) -> pidx                     (BWT.bwtransform2, lib/BWT.js:372)
+static napi_value Bwtransform2(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value argv[3];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t *T, *U; size_t tn, un; int32_t n = 0;
+  if (!buf_arg(env, argv[0], &T, &tn) || !buf_arg(env, argv[1], &U, &un)) return fail(env, B2_ERR_BAD_ARG);
+  napi_get_value_int32(env, argv[2], &n);
+  int32_t p = b2_bwt_cyclic(T, (uint8_t*)U, n);
+  if (p < 0) return fail(env, p);
+  napi_value r; napi_create_int32(env, p, &r);
+  return r;
+}
+
+static napi_value Init(napi_env env, napi_value exports) {
+  napi_property_descriptor d[] = {
+      {"compressFile", nullptr, CompressFile, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"decompressFile", nullptr, DecompressFile, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"decompressBlock", nullptr, DecompressBlock, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"table", nullptr, Table, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"bwtransform2", nullptr, Bwtransform2, nullptr, nullptr, nullptr, napi_default, nullptr},
+  };
+  napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
+  return exports;
+}
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

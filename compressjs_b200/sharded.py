@@ -1,0 +1,161 @@
+"""Block-parallel bzip2 encode over the GPUs of one box.
+
+bzip2 blocks are independent once the RLE1 stage has cut them, so every rank encodes a contiguous
+range of blocks on its own GPU with no data-path collective.  The only exchange is the final
+bitstream gather (north_star: "NCCL over NVLink only for the final bitstream gather"):
+
+  1. every rank cuts the blocks (b2_bzip2_plan -- a cheap scan) and encodes blocks
+     [first, first+count) into a fragment that starts at bit 0 of a private buffer
+     (b2_bzip2_encode_range_dev)
+  2. all_gather of (fragment bits, block count)   -> every rank knows its global bit offset
+  3. the fragment is shifted to (global offset mod 8) so that only whole bytes move
+  4. gather of the byte fragments to rank 0 (NCCL), neighbouring fragments share at most one
+     byte, which is OR-ed; rank 0 adds "BZh"+level and the trailer (stream CRC folded over the
+     per-block CRCs in order, lib/Bzip2.js:917,925-927)
+
+The resulting stream is byte-identical to Bzip2.compressFile on one GPU (and to the oracle).
+The shifting / merging below is plain torch tensor code so that the same logic runs on CPU tensors
+with the gloo backend in the unit tests (tests/test_sharded_host.py), where the per-range encoder
+is injected.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+SQRTPI = 0x177245385090
+
+
+def block_range(nblocks, rank, world):
+    first = rank * nblocks // world
+    last = (rank + 1) * nblocks // world
+    return first, last - first
+
+
+def shift_right_bits(frag, nbits, phase):
+    """Returns a uint8 tensor holding `frag`'s first nbits starting at bit `phase` (MSB first)."""
+    nbytes = (phase + nbits + 7) // 8
+    src = frag[: (nbits + 7) // 8]
+    out = torch.zeros(nbytes, dtype=torch.uint8, device=frag.device)
+    if nbits == 0:
+        return out
+    if phase == 0:
+        out[: src.numel()] = src
+    else:
+        s16 = src.to(torch.int16)
+        out[: src.numel()] |= (s16 >> phase).to(torch.uint8)
+        spill = ((s16 << (8 - phase)) & 0xFF).to(torch.uint8)
+        k = min(nbytes - 1, src.numel())
+        out[1: 1 + k] |= spill[:k]
+    # clear the bits behind the fragment
+    tail = (phase + nbits) % 8
+    if tail:
+        out[-1] &= (0xFF << (8 - tail)) & 0xFF
+    return out
+
+
+def fold_stream_crc(crcs):
+    s = 0
+    for c in crcs:
+        s = (((s << 1) | (s >> 31)) ^ int(c)) & 0xFFFFFFFF  # lib/Bzip2.js:917
+    return s
+
+
+def trailer_bytes(bitpos, stream_crc):
+    """The 80 trailer bits placed at absolute bit `bitpos`: (first byte index, bytes)."""
+    val = (SQRTPI << 32) | stream_crc
+    phase = bitpos % 8
+    total = phase + 80
+    nbytes = (total + 7) // 8
+    val <<= nbytes * 8 - total
+    return bitpos // 8, val.to_bytes(nbytes, "big")
+
+
+def assemble(level, frags, bits, crcs_per_rank, device):
+    """Rank-0 side: frags[r] = byte tensor already shifted to its phase; bits[r] = fragment bits."""
+    offs, o = [], 32
+    for b in bits:
+        offs.append(o)
+        o += int(b)
+    total_bits = o + 80
+    out = torch.zeros((total_bits + 7) // 8, dtype=torch.uint8, device=device)
+    out[:4] = torch.tensor(list(b"BZh" + bytes([0x30 + level])), dtype=torch.uint8, device=device)
+    for r, f in enumerate(frags):
+        if bits[r] == 0:
+            continue
+        b0 = offs[r] // 8
+        nb = (offs[r] % 8 + int(bits[r]) + 7) // 8
+        out[b0: b0 + nb] |= f[:nb].to(device)
+    crcs = [c for rc in crcs_per_rank for c in rc]
+    b0, tb = trailer_bytes(o, fold_stream_crc(crcs))
+    out[b0: b0 + len(tb)] |= torch.tensor(list(tb), dtype=torch.uint8, device=device)
+    return out
+
+
+def compress_sharded(encode_range, nblocks, level, device, group=None):
+    """encode_range(first, count) -> (uint8 tensor fragment starting at bit 0, nbits, [block crcs]).
+    Returns the complete .bz2 stream as a uint8 tensor on rank 0 (None elsewhere)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    first, count = block_range(nblocks, rank, world)
+    frag, nbits, crcs = encode_range(first, count)
+    if world == 1:
+        return assemble(level, [frag], [nbits], [crcs], device)
+    # 2. everybody learns every fragment's size
+    mine = torch.tensor([nbits, count], dtype=torch.int64, device=device)
+    allv = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    bits = [int(v[0]) for v in allv]
+    counts = [int(v[1]) for v in allv]
+    off = 32 + sum(bits[:rank])
+    phase = off % 8
+    shifted = shift_right_bits(frag, nbits, phase)
+    # 3. gather the (padded) byte fragments and the block CRCs on rank 0
+    maxlen = max((32 + sum(bits[:r])) % 8 + bits[r] + 7 for r in range(world)) // 8 + 1
+    maxcnt = max(counts + [1])
+    pad = torch.zeros(maxlen, dtype=torch.uint8, device=device)
+    pad[: shifted.numel()] = shifted
+    crct = torch.zeros(maxcnt, dtype=torch.int64, device=device)
+    if count:
+        crct[:count] = torch.tensor([int(c) for c in crcs], dtype=torch.int64, device=device)
+    if rank == 0:
+        glist = [torch.zeros(maxlen, dtype=torch.uint8, device=device) for _ in range(world)]
+        clist = [torch.zeros(maxcnt, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.gather(pad, glist, dst=0, group=group)
+        dist.gather(crct, clist, dst=0, group=group)
+        crcs_per_rank = [clist[r][: counts[r]].tolist() for r in range(world)]
+        return assemble(level, glist, bits, crcs_per_rank, device)
+    dist.gather(pad, None, dst=0, group=group)
+    dist.gather(crct, None, dst=0, group=group)
+    return None
+
+
+def gpu_encode_range_fn(d_in, level):
+    """encode_range callable backed by libb2bz.so for a uint8 CUDA tensor holding the whole input."""
+    from . import _native
+    L = _native.lib()
+    n = d_in.numel()
+    total = C.c_size_t()
+    rc = L.b2_bzip2_plan(d_in.data_ptr(), n, level, C.byref(total))
+    if rc:
+        raise RuntimeError("b2_bzip2_plan: " + _native.last_error())
+
+    def encode_range(first, count):
+        if count == 0:
+            return torch.zeros(8, dtype=torch.uint8, device=d_in.device), 0, []
+        cap = count * 1400000 + 4096
+        out = torch.empty(cap, dtype=torch.uint8, device=d_in.device)
+        bits = C.c_uint64()
+        crcs = (C.c_uint32 * count)()
+        rc = L.b2_bzip2_encode_range_dev(d_in.data_ptr(), n, level, first, count, 0, out.data_ptr(), cap, C.byref(bits), crcs)
+        if rc:
+            raise RuntimeError("b2_bzip2_encode_range_dev: " + _native.last_error())
+        return out, int(bits.value), list(crcs)
+
+    return encode_range, int(total.value)
+
+
+def compress_file_sharded(d_in, level=9, group=None):
+    """Whole-file bzip2 encode of a CUDA uint8 tensor present on every rank; stream on rank 0."""
+    enc, nblocks = gpu_encode_range_fn(d_in, level)
+    return compress_sharded(enc, nblocks, level, d_in.device, group)
