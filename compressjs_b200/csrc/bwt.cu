@@ -22,16 +22,36 @@
 #include "radix_host.cuh"
 
 // ---------------------------------------------------------------------------------------
-__global__ void k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 nslots, u32* __restrict__ key32) {
-  u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nslots) return;
-  u32 b = g >> SEG_SHIFT, i = g & SEG_MASK, n = seg_n[b];
-  if (i >= n) return;
+// key32 = first four bytes of every rotation; hist[b][256] = byte histogram of block b (which is the
+// digit histogram of EVERY pass of the 4-byte-prefix sort, because each text byte is the k-th byte of
+// exactly one rotation).
+#define BK_THREADS 256
+#define BK_ITEMS 16
+__global__ void __launch_bounds__(BK_THREADS)
+k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ key32, u32* __restrict__ hist) {
+  __shared__ u32 h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 b = blockIdx.x / tps, lt = blockIdx.x % tps;
+  const u32 n = seg_n[b];
+  const u32 start = lt * (BK_THREADS * BK_ITEMS);
+  if (start >= n) return;
   const u8* t = T + ((size_t)b << SEG_SHIFT);
-  u32 i1 = i + 1; if (i1 >= n) i1 -= n;
-  u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
-  u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
-  key32[g] = ((u32)t[i] << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3];
+  u32* ko = key32 + ((size_t)b << SEG_SHIFT);
+#pragma unroll 4
+  for (int k = 0; k < BK_ITEMS; k++) {
+    const u32 i = start + k * BK_THREADS + threadIdx.x;
+    if (i < n) {
+      u32 i1 = i + 1; if (i1 >= n) i1 -= n;
+      u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
+      u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
+      const u32 c0 = t[i];
+      ko[i] = (c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3];
+      atomicAdd(&h[c0], 1u);
+    }
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -154,6 +174,76 @@ k_rerank(const u32* __restrict__ key32, const u64* __restrict__ key64, const u32
   }
 }
 
+// Specialised "after the initial sort" variant: tiles never straddle blocks, invalid slots are skipped,
+// 32-bit keys staged in padded shared memory (conflict-free blocked reads).  Group head chain per
+// block, compaction offsets as one flat chain over all tiles.
+#define RI_PAD(j) ((j) + ((j) >> 5))
+__global__ void __launch_bounds__(RR_THREADS)
+k_rerank_init(const u32* __restrict__ key32, const u32* __restrict__ vals, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ rank,
+              u32* __restrict__ next_head, u32* __restrict__ next_idx, u32* next_count, u32* ticket, u64* st_new, u64* st_cnt, u32 ntiles) {
+  __shared__ u32 sk[RR_TILE + RR_TILE / 32 + 2];
+  __shared__ u32 ws[RR_THREADS / 32 + 1];
+  __shared__ u32 s_tile, s_cn, s_cc, s_prev, s_next;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 b = tile / tps, lt = tile - b * tps;
+  const u32 n = seg_n[b];
+  const u32 start = lt * RR_TILE;
+  const u32 cnt = start < n ? min((u32)RR_TILE, n - start) : 0u;
+  const size_t base = ((size_t)b << SEG_SHIFT) + start;
+  for (u32 j = tid; j < cnt; j += RR_THREADS) sk[RI_PAD(j)] = key32[base + j];
+  if (tid == 0 && cnt) {
+    s_prev = start ? key32[base - 1] : 0u;
+    s_next = (start + cnt < n) ? key32[base + cnt] : 0u;
+  }
+  __syncthreads();
+  u32 vn[RR_ITEMS], nc[RR_ITEMS];
+  u32 mn = 0, cs = 0;
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; j++) {
+    const u32 p = tid * RR_ITEMS + j;
+    vn[j] = 0; nc[j] = 0;
+    if (p < cnt) {
+      const u32 k = sk[RI_PAD(p)];
+      const bool hasprev = p > 0 || start > 0;
+      const u32 kp = p > 0 ? sk[RI_PAD(p - 1)] : s_prev;
+      const bool nh = !hasprev || kp != k;
+      const bool hasnext = (p + 1 < cnt) || (start + cnt < n);
+      const u32 kn = (p + 1 < cnt) ? sk[RI_PAD(p + 1)] : s_next;
+      const bool single = nh && (!hasnext || kn != k);
+      vn[j] = nh ? start + p + 1 : 0u;
+      nc[j] = single ? 0u : 1u;
+      mn = max(mn, vn[j]); cs += nc[j];
+    }
+  }
+  u32 tot_n, tot_c;
+  const u32 ex_n = block_excl_max_u32(mn, ws, &tot_n);
+  const u32 ex_c = block_excl_add<RR_THREADS, u32>(cs, ws, &tot_c);
+  {
+    const u32 w = tid >> 5;
+    if (w == 0 && cnt) { u32 r = lookback_warp(st_new + (size_t)b * tps, lt, tot_n, OpMax()); if (lane_id() == 0) s_cn = r; }
+    else if (w == 1) { u32 r = lookback_warp(st_cnt, tile, tot_c, OpAdd()); if (lane_id() == 0) s_cc = r; }
+  }
+  __syncthreads();
+  if (tile == ntiles - 1 && tid == 0) *next_count = s_cc + tot_c;
+  if (cnt == 0) return;
+  u32 run_n = max(s_cn, ex_n), run_c = s_cc + ex_c;
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; j++) {
+    const u32 p = tid * RR_ITEMS + j;
+    if (p < cnt) {
+      run_n = max(run_n, vn[j]);
+      const u32 lastnew = run_n - 1;  // position (inside the block) of this suffix's group head
+      const u32 g = vals[base + p];
+      rank[g] = lastnew;
+      if (nc[j]) { next_head[run_c] = (b << SEG_SHIFT) | lastnew; next_idx[run_c] = g; }
+      run_c += nc[j];
+    }
+  }
+}
+
 // key64 = head << 20 | rank of the rotation h further on (or n-1-i for the final tie-break).
 __global__ void k_gather(const u32* __restrict__ head, const u32* __restrict__ idx, u32 M, const u32* __restrict__ rank,
                          const u32* __restrict__ seg_n, u32 h, int tiebreak, u64* __restrict__ key_out, u32* __restrict__ val_out) {
@@ -200,18 +290,25 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   DBuf<u64> st(c, (size_t)3 * rr_tiles_init);
   u32 *kin = keyA, *kout = keyB, *vin = valA, *vout = valB;
 
-  k_build_keys<<<(nslots + 255) / 256, 256, 0, c.stream>>>(d_T, d_n, nslots, kin);
+  DBuf<u32> bytehist(c, (size_t)nblk * 256);
+  CUDA_CHECK(cudaMemsetAsync(bytehist, 0, (size_t)nblk * 256 * 4, c.stream));
+  const u32 bk_tps = (n_max + BK_THREADS * BK_ITEMS - 1) / (BK_THREADS * BK_ITEMS);
+  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist);
   KLAUNCH(c); KCHECK();
   c.stats.bwt_bytes += n_total * 5;
-  radix_sort<u32>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 0, 4, true, n_total);
+  radix_sort<u32>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 0, 4, true, n_total, bytehist.p);
   // kin/vin now hold the sorted keys / suffix ids; vin doubles as the suffix array
   u32* SA = vin;
   CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
   CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
   CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4, c.stream));
-  k_rerank<true><<<rr_tiles_init, RR_THREADS, 0, c.stream>>>(kin, nullptr, vin, d_n, nslots, SA, rank, headA, idxA, cnt, ticket,
-                                                            st.p, st.p + rr_tiles_init, st.p + 2 * (size_t)rr_tiles_init, rr_tiles_init);
-  KLAUNCH(c); KCHECK();
+  {
+    const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;
+    const u32 ri_tiles = ri_tps * nblk;  // <= rr_tiles_init
+    k_rerank_init<<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, vin, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init,
+                                                         ri_tiles);
+    KLAUNCH(c); KCHECK();
+  }
   c.stats.bwt_bytes += n_total * (8 + 4);
   u32 M = 0;
   CUDA_CHECK(cudaMemcpyAsync(&M, cnt, 4, cudaMemcpyDeviceToHost, c.stream));

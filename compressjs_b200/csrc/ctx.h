@@ -18,7 +18,7 @@ struct Ctx {
   size_t ev_used = 0;
   std::vector<std::pair<int, size_t>> ev_tags;  // (stage id, pool index) recorded in the current call
   std::vector<b2_block_trace> trace;
-  u32 bwt_batch = 64;  // bzip2 blocks sorted together in one segmented batch
+  u32 bwt_batch = 296;  // bzip2 blocks processed together in one batch (2 CTAs x 148 SMs for the per-block kernels)
   bool timing = true;
 
   void* dalloc(size_t bytes) {

@@ -106,6 +106,7 @@ struct BitReader {
 
 // ---- header + Huffman decode: one warp per candidate ----------------------------------------
 #define HD_WARPS 4
+#define HD_WIN 512
 struct HdecWarp {
   int limit[HUFF_MAXGROUPS][22];
   int base[HUFF_MAXGROUPS][22];
@@ -114,6 +115,12 @@ struct HdecWarp {
   u8 len[HUFF_MAXGROUPS][HUFF_MAXSYM + 2];
   int minlen[HUFF_MAXGROUPS], maxlen[HUFF_MAXGROUPS];
   int status; u32 ngroups, nsel, symcount;
+  // speculative window decode of the symbol stream
+  u32 win[20];          // 544 bits of the stream, big-endian words
+  u16 wsym[HD_WIN];     // symbol that would start at every bit offset of the window
+  u8 wlen[HD_WIN];      // its code length (0 = no valid code there)
+  u16 spos[HUFF_GROUP + 2];
+  u32 c_cnt, c_pos, c_flag;
 };
 
 __global__ void __launch_bounds__(HD_WARPS * 32)
@@ -242,52 +249,94 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     s.lut[g][p] = ent;
   }
   __syncwarp();
-  // ---- symbol stream ----
-  if (lane == 0) {
+  // ---- symbol stream (lib/Bzip2.js:288-307).  Per 50-symbol group the table is fixed, so all 32
+  // lanes decode the (symbol, length) that WOULD start at every bit offset of a 512-bit window, and
+  // lane 0 only follows the chain pos += len[pos] through shared memory; the symbols on the chain are
+  // then written out by the whole warp. ----
+  {
+    const u32 ns = s.nsel, eob = s.symcount - 1;  // symTotal + 1
+    u64 P = 0;
+    if (lane == 0) P = br.tell();
+    P = __shfl_sync(FULL_MASK, P, 0);
+    const u32* words = reinterpret_cast<const u32*>(in);
+    const u64 nwords = (nbytes + 3) / 4;
+    u32 m = 0, selector = 0;
     int status = 0;
-    u32 m = 0, selector = 0, left = 0, g = 0, runs = 0;
-    const u32 ns = s.nsel;
-    for (;;) {
-      if (left == 0) {
-        left = HUFF_GROUP;
-        if (selector >= ns) { status = DEC_DATA_ERROR; break; }       // :291
-        g = sel[selector++];
-      }
-      left--;
-      br.ensure();
-      u32 sym;
-      const u16 ent = s.lut[g][br.peek(10)];
-      if (ent) {
-        sym = ent & 511u;
-        br.skip(ent >> 9);
-      } else {
-        int i = s.minlen[g];
-        int j = (int)br.peek((u32)i);
-        const u32 window = br.peek(21);
-        for (;;) {
-          if (i > s.maxlen[g]) { status = DEC_DATA_ERROR; break; }    // :299
-          if (j <= s.limit[g][i]) break;
-          i++;
-          j = (int)(window >> (21 - i));
+    bool done = false;
+    while (!done) {
+      if (selector >= ns) { status = DEC_DATA_ERROR; break; }          // :291
+      const u32 g = sel[selector++];
+      const u16* lut = s.lut[g];
+      const int minLen = s.minlen[g], maxLen = s.maxlen[g];
+      u32 remaining = HUFF_GROUP;
+      while (remaining && !done) {
+        // stage 17 words (544 bits) starting at the word that holds bit P
+        const u64 w0 = P >> 5;
+        const u32 shiftbase = (u32)(P & 31);
+        if (lane < 18) {
+          const u64 wi = w0 + lane;
+          const u32 wv = wi < nwords ? words[wi] : 0u;
+          s.win[lane] = __byte_perm(wv, 0, 0x0123);
         }
-        if (status) break;
-        br.skip((u32)i);
-        const int jj = j - s.base[g][i];
-        if (jj < 0 || jj >= HUFF_MAXSYM) { status = DEC_DATA_ERROR; break; }  // :306
-        sym = s.permute[g][jj];
-      }
-      if (m >= SEG_SIZE - 1) { status = DEC_DATA_ERROR; break; }
-      so[m++] = (u16)sym;
-      if (sym <= 1) {
-        if (++runs > 40) { status = DEC_DATA_ERROR; break; }  // a run this long overflows any block; the reference would spin
-      } else {
-        runs = 0;
-        if (sym > symTotal) break;  // end of block (:345)
+        __syncwarp();
+#pragma unroll 4
+        for (u32 o = lane; o < HD_WIN; o += 32) {
+          const u32 bp = shiftbase + o;
+          const u32 wi = bp >> 5, sh = bp & 31;
+          const u64 v64 = ((u64)s.win[wi] << 32) | s.win[wi + 1];
+          const u32 bits20 = (u32)((v64 << sh) >> 44);
+          u32 sym = 0, len = 0;
+          const u32 ent = lut[bits20 >> 10];
+          if (ent) {
+            sym = ent & 511u; len = ent >> 9;
+          } else {
+            int i = minLen;
+            int j = (int)(bits20 >> (20 - i));
+            for (;;) {
+              if (i > maxLen) { i = 0; break; }                        // :299 -> marks "no code here"
+              if (j <= s.limit[g][i]) break;
+              i++;
+              if (i > 20) { i = 0; break; }
+              j = (int)(bits20 >> (20 - i));
+            }
+            if (i) {
+              const int jj = j - s.base[g][i];
+              if (jj >= 0 && jj < HUFF_MAXSYM) { sym = s.permute[g][jj]; len = (u32)i; }  // :306
+            }
+          }
+          s.wsym[o] = (u16)sym;
+          s.wlen[o] = (u8)len;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          u32 pos = 0, cnt = 0, flag = 0;
+          while (cnt < remaining && pos < HD_WIN) {
+            const u32 l = s.wlen[pos];
+            if (l == 0) { flag = 2; break; }
+            const u32 sy = s.wsym[pos];
+            s.spos[cnt++] = (u16)pos;
+            pos += l;
+            if (sy >= eob && sy > 1) { flag = 1; break; }                // end of block (:345)
+          }
+          s.c_cnt = cnt; s.c_pos = pos; s.c_flag = flag;
+        }
+        __syncwarp();
+        const u32 cnt = s.c_cnt, flag = s.c_flag;
+        if (m + cnt >= SEG_SIZE) { status = DEC_DATA_ERROR; done = true; break; }
+        for (u32 i = lane; i < cnt; i += 32) so[m + i] = s.wsym[s.spos[i]];
+        m += cnt;
+        remaining -= cnt;
+        P += s.c_pos;
+        if (flag == 2) { status = DEC_DATA_ERROR; done = true; }
+        else if (flag == 1) done = true;
+        __syncwarp();
       }
     }
-    r->status = status;
-    r->m = m;
-    r->endbit = br.tell();
+    if (lane == 0) {
+      r->status = status;
+      r->m = m;
+      r->endbit = P;
+    }
   }
 }
 
@@ -471,10 +520,11 @@ __global__ void k_ibwt_pack(const u8* __restrict__ tt, const u32* __restrict__ t
   if ((g & SEG_MASK) < seg_n[g >> SEG_SHIFT]) P[g] = ((tvec[g] & SEG_MASK) << 8) | tt[g];
 }
 
-#define IB_SHIFT 11
+#define IB_SHIFT 8
 #define IB_STEP (1u << IB_SHIFT)
 #define IB_SEGS (SEG_SIZE / IB_STEP + 1)  // sampled rows per block + the start row
-#define IB_VCAP 2048
+#define IB_VCAP 8192
+#define IB_SUB 28  // blocks walked together: their packed T-vectors (3.6 MB each) stay L2 resident
 
 struct Seg { u32 len, next; };
 struct Visit { u32 row, off, len; };
@@ -745,7 +795,7 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
 
   // ---- 2. decode every candidate block, in batches ----
-  const u32 DB = std::max(1u, std::min(c.bwt_batch, 128u));
+  const u32 DB = std::max(1u, c.bwt_batch);
   static bool attr = false;
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HdecWarp) * HD_WARPS)));
@@ -799,12 +849,17 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
         u32* Pp = kout;  // the other key buffer is free now
         k_ibwt_pack<<<(nslots + 255) / 256, 256, 0, c.stream>>>(tt, vin, dn, nslots, Pp);
         KLAUNCH(c); KCHECK();
-        k_ibwt_walk1<<<(cnt * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Pp, rb, cnt, segs);
-        KLAUNCH(c); KCHECK();
-        k_ibwt_chain<<<(cnt + 31) / 32, 32, 0, c.stream>>>(Pp, rb, cnt, segs, visits, nvis);
-        KLAUNCH(c); KCHECK();
-        k_ibwt_walk2<<<(cnt * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Pp, rb, cnt, visits, nvis, rle.p + (k0 << SEG_SHIFT));
-        KLAUNCH(c); KCHECK();
+        for (u32 s0 = 0; s0 < cnt; s0 += IB_SUB) {
+          const u32 sc = std::min<u32>(IB_SUB, cnt - s0);
+          const u32* Ps = Pp + ((size_t)s0 << SEG_SHIFT);
+          k_ibwt_walk1<<<(sc * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS);
+          KLAUNCH(c); KCHECK();
+          k_ibwt_chain<<<(sc + 31) / 32, 32, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0);
+          KLAUNCH(c); KCHECK();
+          k_ibwt_walk2<<<(sc * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0,
+                                                                       rle.p + ((k0 + s0) << SEG_SHIFT));
+          KLAUNCH(c); KCHECK();
+        }
       }
       if (nmax) {
         StageScope ss(c, ST_UNRLE);

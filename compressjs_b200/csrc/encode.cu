@@ -324,7 +324,9 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
   std::vector<u32> all_crc(count);
   std::vector<b2_block_trace> tr(count);
-  const u32 B = c.bwt_batch;
+  // balanced batches: ceil(count / batches) blocks each, so that no tiny tail batch starves the per-block kernels
+  const u32 nbatches = (u32)((count + c.bwt_batch - 1) / c.bwt_batch);
+  const u32 B = nbatches ? (u32)((count + nbatches - 1) / nbatches) : 1;
   if (count) {
     const u32 nbmax = (u32)std::min<size_t>(B, count);
     DBuf<u8> T(c, (size_t)nbmax << SEG_SHIFT), U(c, (size_t)nbmax << SEG_SHIFT);

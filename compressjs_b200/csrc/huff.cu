@@ -72,22 +72,46 @@ __device__ void build_tables(HuffSmem& s, u32 ntab, u32 A) {
 
 // lib/Bzip2.js:671-684: every group goes to the table that codes it in the fewest bits
 // (ties -> lowest table index).  Fills s.sel / s.cost.
+// Tiles of 256 groups (6400 words) are staged through shared memory; the next tile's global loads are
+// issued into registers before the current tile is consumed, so the L2/HBM latency overlaps the math.
+struct TileRegs { u32 r[HF_TILE_WORDS / HF_THREADS]; };
+__device__ __forceinline__ void tile_fetch(TileRegs& t, const u32* __restrict__ symw, u32 w0, u32 nwords) {
+#pragma unroll
+  for (int k = 0; k < HF_TILE_WORDS / HF_THREADS; k++) {
+    const u32 i = w0 + k * HF_THREADS + threadIdx.x;
+    t.r[k] = i < nwords ? symw[i] : 0u;
+  }
+}
+__device__ __forceinline__ void tile_store(const TileRegs& t, u32* tile) {
+#pragma unroll
+  for (int k = 0; k < HF_TILE_WORDS / HF_THREADS; k++) tile[k * HF_THREADS + threadIdx.x] = t.r[k];
+}
+
 __device__ void assign_selectors(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 nsel, u32 ntab) {
   const u32 tid = threadIdx.x;
   const u32 nwords = (m + 1) >> 1;
+  TileRegs tr;
+  tile_fetch(tr, symw, 0, nwords);
   for (u32 g0 = 0; g0 < nsel; g0 += HF_TILE_GROUPS) {
-    const u32 w0 = g0 * 25;
-    for (u32 i = tid; i < HF_TILE_WORDS; i += HF_THREADS) s.tile[i] = (w0 + i < nwords) ? symw[w0 + i] : 0u;
+    tile_store(tr, s.tile);
     __syncthreads();
+    if (g0 + HF_TILE_GROUPS < nsel) tile_fetch(tr, symw, (g0 + HF_TILE_GROUPS) * 25, nwords);
     const u32 g = g0 + tid;
     if (g < nsel) {
       const u32 cnt = min(50u, m - 50u * g);
       unsigned long long acc = 0;
+      if (cnt == 50) {
 #pragma unroll 5
-      for (u32 k = 0; k < 25; k++) {
-        const u32 w = s.tile[tid * 25 + k];
-        if (2 * k < cnt) acc += s.pk[w & 0xffffu];
-        if (2 * k + 1 < cnt) acc += s.pk[w >> 16];
+        for (u32 k = 0; k < 25; k++) {
+          const u32 w = s.tile[tid * 25 + k];
+          acc += s.pk[w & 0xffffu] + s.pk[w >> 16];
+        }
+      } else {
+        for (u32 k = 0; k < 25; k++) {
+          const u32 w = s.tile[tid * 25 + k];
+          if (2 * k < cnt) acc += s.pk[w & 0xffffu];
+          if (2 * k + 1 < cnt) acc += s.pk[w >> 16];
+        }
       }
       u32 best = 0, bc = (u32)(acc & 1023u);
       for (u32 t = 1; t < ntab; t++) {
@@ -105,11 +129,13 @@ __device__ void recount(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 ns
   const u32 tid = threadIdx.x;
   const u32 nwords = (m + 1) >> 1;
   for (u32 i = tid; i < ntab * (HUFF_MAXSYM + 2); i += HF_THREADS) (&s.freq[0][0])[i] = 0;
+  TileRegs tr;
+  tile_fetch(tr, symw, 0, nwords);
   __syncthreads();
   for (u32 g0 = 0; g0 < nsel; g0 += HF_TILE_GROUPS) {
-    const u32 w0 = g0 * 25;
-    for (u32 i = tid; i < HF_TILE_WORDS; i += HF_THREADS) s.tile[i] = (w0 + i < nwords) ? symw[w0 + i] : 0u;
+    tile_store(tr, s.tile);
     __syncthreads();
+    if (g0 + HF_TILE_GROUPS < nsel) tile_fetch(tr, symw, (g0 + HF_TILE_GROUPS) * 25, nwords);
     const u32 g = g0 + tid;
     if (g < nsel) {
       const u32 cnt = min(50u, m - 50u * g);
@@ -123,6 +149,61 @@ __device__ void recount(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 ns
     __syncthreads();
   }
   (void)A;
+}
+
+// ---- move-to-front over <= 6 table ids, list packed as six nibbles -------------------------------
+__device__ __forceinline__ u32 mtf6_find(u32 list, u32 v) {
+  u32 j = 0;
+#pragma unroll
+  for (u32 k = 1; k < HUFF_MAXGROUPS; k++) j = (((list >> (4 * k)) & 15u) == v) ? k : j;
+  return j;
+}
+__device__ __forceinline__ u32 mtf6_front(u32 list, u32 j) {  // move the entry at position j to the front
+  const u32 v = (list >> (4 * j)) & 15u;
+  const u32 low = list & ((1u << (4 * j)) - 1u);
+  const u32 high = list & ~((1u << (4 * (j + 1))) - 1u);
+  return high | (low << 4) | v;
+}
+// The selector MTF is value based ("find table id v"), so a run of selectors is summarised by its
+// RECENCY list: the distinct ids it used, most recent first (count in bits 28..31, unused nibbles 0).
+// list after the run from any start list Y = R ++ (Y minus R).
+__device__ __forceinline__ u32 rec_apply(u32 R, u32 v) {
+  u32 cnt = R >> 28, lst = R & 0x00ffffffu, j = cnt;
+#pragma unroll
+  for (u32 k = 0; k < HUFF_MAXGROUPS; k++) j = (k < cnt && ((lst >> (4 * k)) & 15u) == v) ? k : j;
+  if (j == cnt) {
+    lst = ((lst << 4) | v) & 0x00ffffffu;
+    cnt++;
+  } else {
+    const u32 low = lst & ((1u << (4 * j)) - 1u);
+    const u32 high = lst & ~((1u << (4 * (j + 1))) - 1u);
+    lst = high | (low << 4) | v;
+  }
+  return (cnt << 28) | lst;
+}
+__device__ __forceinline__ bool rec_has(u32 R, u32 v) {
+  const u32 cnt = R >> 28;
+  bool f = false;
+#pragma unroll
+  for (u32 k = 0; k < HUFF_MAXGROUPS; k++) f = f || (k < cnt && ((R >> (4 * k)) & 15u) == v);
+  return f;
+}
+__device__ __forceinline__ u32 rec_op(u32 A, u32 B) {  // A = earlier run, B = later run
+  u32 cnt = B >> 28, lst = B & 0x00ffffffu;
+  const u32 ca = A >> 28;
+#pragma unroll
+  for (u32 k = 0; k < HUFF_MAXGROUPS; k++) {
+    const u32 v = (A >> (4 * k)) & 15u;
+    if (k < ca && !rec_has(B, v)) { lst |= v << (4 * cnt); cnt++; }
+  }
+  return (cnt << 28) | lst;
+}
+__device__ __forceinline__ u32 rec_full(u32 R) {  // R ++ (identity minus R): the full 6-entry list
+  u32 cnt = R >> 28, lst = R & 0x00ffffffu;
+#pragma unroll
+  for (u32 v = 0; v < HUFF_MAXGROUPS; v++)
+    if (!rec_has(R, v)) { lst |= v << (4 * cnt); cnt++; }
+  return lst;
 }
 
 __global__ void __launch_bounds__(HF_THREADS)
@@ -157,9 +238,17 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
     for (u32 i = tid; i < 1024; i += HF_THREADS) s.chist[i] = 0;
     __syncthreads();
     {
-      u32 loc[HUFF_MAXGROUPS] = {0, 0, 0, 0, 0, 0};
-      for (u32 g = tid; g < nsel; g += HF_THREADS) loc[s.sel[g]]++;
-      for (u32 t = 0; t < ng; t++) if (loc[t]) atomicAdd(&s.gcount[t], loc[t]);
+      u32 l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0, l5 = 0;
+      for (u32 g = tid; g < nsel; g += HF_THREADS) {
+        const u32 v = s.sel[g];
+        l0 += v == 0; l1 += v == 1; l2 += v == 2; l3 += v == 3; l4 += v == 4; l5 += v == 5;
+      }
+      if (l0) atomicAdd(&s.gcount[0], l0);
+      if (l1) atomicAdd(&s.gcount[1], l1);
+      if (l2) atomicAdd(&s.gcount[2], l2);
+      if (l3) atomicAdd(&s.gcount[3], l3);
+      if (l4) atomicAdd(&s.gcount[4], l4);
+      if (l5) atomicAdd(&s.gcount[5], l5);
     }
     __syncthreads();
     u32 which = 0;
@@ -223,26 +312,53 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
   u8* so = sel_out + (size_t)blk * SEL_STRIDE;
   for (u32 g = tid; g < nsel; g += HF_THREADS) so[g] = s.sel[g];
   for (u32 i = tid; i < ng * A; i += HF_THREADS) hb->len[i / A][i % A] = s.len[i / A][i % A];
-  __syncthreads();
+  // selectors: MTF over the table ids, unary (lib/Bzip2.js:850-862).  Parallel over threads: every
+  // thread composes the permutation of its run of selectors, an exclusive scan of the compositions
+  // gives its start list, then it replays its run.
+  u32 selbits = 0;
+  {
+    const u32 per = (nsel + HF_THREADS - 1) / HF_THREADS;
+    const u32 ga = min(nsel, tid * per), gb = min(nsel, ga + per);
+    u32 P = 0;  // empty recency list
+    for (u32 g = ga; g < gb; g++) P = rec_apply(P, s.sel[g]);
+    u32* sa = s.chist;          // reuse: 2 x 256 words
+    u32* sb = s.chist + HF_THREADS;
+    sa[tid] = P;
+    __syncthreads();
+    u32 *src = sa, *dst = sb;
+    for (u32 o = 1; o < HF_THREADS; o <<= 1) {
+      u32 x = src[tid];
+      if (tid >= o) x = rec_op(src[tid - o], x);
+      dst[tid] = x;
+      __syncthreads();
+      u32* tmp = src; src = dst; dst = tmp;
+    }
+    u32 L = rec_full(tid ? src[tid - 1] : 0u);
+    u8* sm = selmtf_out + (size_t)blk * SEL_STRIDE;
+    for (u32 g = ga; g < gb; g++) {
+      const u32 j = mtf6_find(L, s.sel[g]);
+      L = mtf6_front(L, j);
+      sm[g] = (u8)j;
+      selbits += j + 1;
+    }
+    __syncthreads();
+  }
+  {
+    unsigned long long b2 = selbits;
+    __shared__ unsigned long long red2[HF_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) b2 += __shfl_xor_sync(FULL_MASK, b2, o);
+    if ((tid & 31) == 0) red2[tid >> 5] = b2;
+    __syncthreads();
+    b2 = 0;
+    for (int i = 0; i < HF_THREADS / 32; i++) b2 += red2[i];
+    bits += b2;
+  }
   if (tid == 0) {
     // header: 48 magic + 32 crc + 1 + 24 pidx + 16 + 16 per used range + 3 + 15 (lib/Bzip2.js:740-758, 847-849)
     unsigned long long hbits = 48 + 32 + 1 + 24 + 16 + 3 + 15;
     for (u32 r = 0; r < 16; r++) {
       const u32 w = used[blk * 8 + (r >> 1)];
       if ((w >> ((r & 1) * 16)) & 0xffffu) hbits += 16;
-    }
-    // selectors: MTF over the table ids, unary (lib/Bzip2.js:850-862)
-    u8 M[HUFF_MAXGROUPS];
-    u8* sm = selmtf_out + (size_t)blk * SEL_STRIDE;
-    for (u32 t = 0; t < ng; t++) M[t] = (u8)t;
-    for (u32 g = 0; g < nsel; g++) {
-      const u8 v = s.sel[g];
-      u32 j = 0;
-      while (M[j] != v) j++;
-      for (u32 k = j; k > 0; k--) M[k] = M[k - 1];
-      M[0] = v;
-      sm[g] = (u8)j;
-      hbits += j + 1;
     }
     // tables: 5 bits + per symbol 2*|delta| + 1 (lib/Bzip2.js:610-629)
     for (u32 t = 0; t < ng; t++) {

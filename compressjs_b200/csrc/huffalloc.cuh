@@ -13,18 +13,22 @@
 #define HA_FN static inline
 #endif
 
+// Every entry first() looks at is an extended parent pointer in [0, 2*len) (pass 1 has converted all
+// of a[0..len-3]), so `x % len` is one conditional subtract -- no integer division on the GPU.
+HA_FN int ha_mod(int x, int len) { return x >= len ? x - len : x; }
+
 // HuffmanAllocator.js:52-75
 HA_FN int ha_first(const int* a, int len, int i, int nodesToMove) {
   const int limit = i;
   int k = len - 2;
-  while (i >= nodesToMove && (a[i] % len) > limit) {
+  while (i >= nodesToMove && ha_mod(a[i], len) > limit) {
     k = i;
     i -= (limit - i + 1);
   }
   if (nodesToMove - 1 > i) i = nodesToMove - 1;
   while (k > i + 1) {
     const int t = (i + k) >> 1;
-    if ((a[t] % len) > limit) k = t; else i = t;
+    if (ha_mod(a[t], len) > limit) k = t; else i = t;
   }
   return k;
 }
@@ -51,7 +55,7 @@ HA_FN void ha_allocate(int* a, int len, int maxLen) {
   for (int depth = 1; depth < maxLen - 1 && nodesToRelocate > 1; depth++)
     nodesToRelocate = ha_first(a, len, nodesToRelocate - 1, 0);
   // pass 3
-  if ((a[0] % len) >= nodesToRelocate) {
+  if (ha_mod(a[0], len) >= nodesToRelocate) {
     // :131-148
     int firstNode = len - 2, nextNode = len - 1;
     for (int depth = 1, avail = 2; avail > 0; depth++) {

@@ -70,11 +70,17 @@ __global__ void __launch_bounds__(256) k_mtf_prefix(const u32* __restrict__ seg_
 }
 
 #define MR_WARPS 8
+// MTF rank of byte c = number of byte values that were used more recently than c.  Every byte value
+// carries a 15-bit recency key (larger = more recent): 255 - (position in the list at the chunk
+// start) before its first use inside the chunk, 256 + (position inside the chunk) afterwards.  The
+// 256 keys live in registers, 8 per lane as 4 x (2 x 16 bit) with the top bit of every half preset,
+// so "key > q" for two keys is one subtraction (bit 15 / 31 survive iff no borrow); the rank is a
+// popcount + one warp REDUX.  Nothing is shifted: using a byte only rewrites its own key.
 __global__ void __launch_bounds__(MR_WARPS * 32)
 k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, const u32* __restrict__ lastpos,
             const u32* __restrict__ used, u8* __restrict__ R, u32 nblk) {
   __shared__ u32 skey[MR_WARPS][256];
-  __shared__ __align__(8) u8 slist[MR_WARPS][256];
+  __shared__ u16 sk16[MR_WARPS][256];
   const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 gchunk = blockIdx.x * MR_WARPS + w;
   const u32 seg = gchunk / cps, ch = gchunk % cps;
@@ -84,7 +90,7 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
   const u32 start = ch * MTF_CHUNK;
   if (start >= n) return;
   const u32 count = min((u32)MTF_CHUNK, n - start);
-  // ---- list at the chunk start ----
+  // ---- list position of every byte value at the chunk start (rank by counting) ----
   const u32* lp = lastpos + (size_t)gchunk * 256;
   u32 mykey[8];
 #pragma unroll
@@ -106,14 +112,19 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
 #pragma unroll
     for (int i = 0; i < 8; i++) rk[i] += (k2 > mykey[i]) ? 1u : 0u;
   }
+  u32 kw[4];
 #pragma unroll
-  for (int i = 0; i < 8; i++) slist[w][rk[i]] = (u8)(lane * 8 + i);
+  for (int i = 0; i < 4; i++) {
+    const u32 a = 255u - rk[2 * i], b2 = 255u - rk[2 * i + 1];
+    kw[i] = 0x80008000u | a | (b2 << 16);
+    sk16[w][lane * 8 + 2 * i] = (u16)a;
+    sk16[w][lane * 8 + 2 * i + 1] = (u16)b2;
+  }
   __syncwarp();
-  u32 lo = reinterpret_cast<const u32*>(&slist[w][0])[lane * 2];
-  u32 hi = reinterpret_cast<const u32*>(&slist[w][0])[lane * 2 + 1];
   // ---- walk the chunk, 128 bytes per outer step ----
   const u8* src = U + ((size_t)seg << SEG_SHIFT) + start;
   u8* dst = R + ((size_t)seg << SEG_SHIFT) + start;
+  u32 prevc = 0x100;  // nothing yet
   for (u32 base = 0; base < count; base += 128) {
     u32 word = 0;
     {
@@ -128,25 +139,22 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
     for (u32 idx = 0; idx < lim; idx++) {
       const u32 wsrc = __shfl_sync(FULL_MASK, word, idx >> 2);
       const u32 c = (wsrc >> ((idx & 3) * 8)) & 255u;
-      const u32 cc = c * 0x01010101u;
-      const u32 m0 = __vcmpeq4(lo, cc), m1 = __vcmpeq4(hi, cc);
-      const u32 bal = __ballot_sync(FULL_MASK, (m0 | m1) != 0);
-      const u32 fl = __ffs(bal) - 1;
-      const u32 mypos = m0 ? ((__ffs(m0) - 1) >> 3) : (4 + ((__ffs(m1) - 1) >> 3));
-      const u32 pos = __shfl_sync(FULL_MASK, mypos, fl);
-      const u32 j = fl * 8 + pos;
-      if (j != 0) {
-        u32 carry = __shfl_up_sync(FULL_MASK, hi >> 24, 1);
-        if (lane == 0) carry = c;
-        u64 v = ((u64)hi << 32) | lo;
-        if (lane < fl) {
-          v = (v << 8) | carry;
-        } else if (lane == fl) {
-          const u64 lowmask = (1ull << (8 * pos)) - 1;
-          const u64 highmask = pos == 7 ? 0ull : ~((1ull << (8 * (pos + 1))) - 1);
-          v = (v & highmask) | (((v & lowmask) << 8) | carry);
-        }
-        lo = (u32)v; hi = (u32)(v >> 32);
+      if (c == prevc) continue;  // still the front of the list: rank 0, nothing changes
+      prevc = c;
+      const u32 qq = ((u32)sk16[w][c] + 1u) * 0x00010001u;
+      const u32 M = 0x80008000u;
+      const u32 cntl = __popc((kw[0] - qq) & M) + __popc((kw[1] - qq) & M) + __popc((kw[2] - qq) & M) + __popc((kw[3] - qq) & M);
+      const u32 j = __reduce_add_sync(FULL_MASK, cntl);
+      const u32 nk = 256u + base + idx;
+      if (lane == 0) sk16[w][c] = (u16)nk;
+      if (lane == (c >> 3)) {
+        const u32 val = (c & 1) ? ((0x8000u | nk) << 16) : (0x8000u | nk);
+        const u32 msk = (c & 1) ? 0x0000ffffu : 0xffff0000u;
+        const u32 wi = (c >> 1) & 3;
+        kw[0] = wi == 0 ? ((kw[0] & msk) | val) : kw[0];
+        kw[1] = wi == 1 ? ((kw[1] & msk) | val) : kw[1];
+        kw[2] = wi == 2 ? ((kw[2] & msk) | val) : kw[2];
+        kw[3] = wi == 3 ? ((kw[3] & msk) | val) : kw[3];
       }
       if (lane == (idx >> 2)) outw |= j << ((idx & 3) * 8);
     }

@@ -1,9 +1,11 @@
 // radix.cuh -- segmented LSD radix sort (8-bit digits), single pass over the data per digit:
-//   k_radix_hist : one read of the keys -> per-(segment, pass) digit histograms
-//   k_radix_pass : "onesweep" pass = read (key,val) once, rank inside the tile with
-//                  warp match/shuffle, chain the per-digit tile offsets with a decoupled
-//                  look-back, stage the tile in shared memory in bucket order and write
-//                  every bucket run out coalesced.
+//   k_radix_hist : one read of the keys -> per-(segment, pass) digit histograms (only for the
+//                  64-bit round keys; the initial 4-byte-prefix sort gets its histograms for free
+//                  from the block's byte histogram, see bwt.cu)
+//   k_radix_pass : "onesweep" pass = read (key,val) once, rank inside the tile with warp
+//                  match + one leader lane per digit group bumping a warp-private shared-memory
+//                  counter, chain the per-digit tile offsets with a decoupled look-back, stage the
+//                  tile in shared memory in bucket order and write every bucket run out coalesced.
 // Segments are the independent bzip2 blocks of a batch (slot = seg << seg_shift | i), or a
 // single flat segment for the compacted "still unsorted" suffixes of a doubling round.
 // This is the hot kernel of the forward BWT (reference: lib/BWT.js:372-417 does the same
@@ -39,17 +41,9 @@ k_radix_hist(const KeyT* __restrict__ keys, const u32* __restrict__ seg_n, u32 t
   if (start >= n) return;
   const u32 count = min((u32)RH_TILE, n - start);
   const KeyT* p = keys + ((size_t)seg << seg_shift) + start;
-  for (u32 i0 = 0; i0 < count; i0 += RH_THREADS) {  // warp-uniform trip count
-    const u32 i = i0 + threadIdx.x;
-    const bool valid = i < count;
-    KeyT k = valid ? p[i] : (KeyT)0;
-    for (u32 ps = 0; ps < npass; ps++) {
-      u32 d = valid ? ((u32)(k >> (begin_bit + ps * RADIX_BITS)) & (RADIX - 1)) : RADIX;
-      // aggregate equal digits inside the warp first: constant digits (high key bits) would
-      // otherwise serialise 32-way on one shared-memory counter
-      u32 m = __match_any_sync(FULL_MASK, d);
-      if (valid && (m & lanemask_lt()) == 0) atomicAdd(&h[ps * RADIX + d], (u32)__popc(m));
-    }
+  for (u32 i = threadIdx.x; i < count; i += RH_THREADS) {
+    const KeyT k = p[i];
+    for (u32 ps = 0; ps < npass; ps++) atomicAdd(&h[ps * RADIX + ((u32)(k >> (begin_bit + ps * RADIX_BITS)) & (RADIX - 1))], 1u);
   }
   __syncthreads();
   for (u32 i = threadIdx.x; i < npass * RADIX; i += RH_THREADS)
@@ -67,51 +61,66 @@ struct RadixSmem {
   u32 tile;
 };
 
+// hist_stride / hist_pass_stride let several passes share one histogram (the 4-byte-prefix keys of
+// all rotations have the same digit histogram in every pass: the block's byte histogram).
 // iota != 0: values are synthesised as the global slot index (first pass of the initial sort).
 template <typename KeyT>
 __global__ void __launch_bounds__(RP_THREADS)
 k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __restrict__ kout,
              u32* __restrict__ vout, const u32* __restrict__ seg_n, u32 tiles_per_seg, u32 seg_shift,
-             const u32* __restrict__ hist, u32 npass, u32 pass, u32 shift, u32* ticket, u32* status, int iota) {
+             const u32* __restrict__ hist, u32 hist_seg_stride, u32 hist_off, u32 shift, u32* ticket, u32* status, int iota) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RadixSmem<KeyT>& s = *reinterpret_cast<RadixSmem<KeyT>*>(smem_raw);
   const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s.tile = atomicAdd(ticket, 1u);
-  for (u32 i = tid; i < RP_WARPS * RADIX; i += RP_THREADS) (&s.whist[0][0])[i] = 0;
+#pragma unroll
+  for (u32 i = 0; i < RP_WARPS; i++) s.whist[i][tid] = 0;
   __syncthreads();
   const u32 tile = s.tile;
-  const u32 seg = tile / tiles_per_seg, lt = tile % tiles_per_seg;
+  const u32 seg = tile / tiles_per_seg, lt = tile - seg * tiles_per_seg;
   const u32 n = seg_n[seg];
   const u32 start = lt * RP_TILE;
   if (start >= n) return;  // every later tile of this segment is empty too: nobody waits on us
   const u32 count = min((u32)RP_TILE, n - start);
   const size_t base = ((size_t)seg << seg_shift) + start;
+  const KeyT* kp = kin + base + w * (32 * RP_ITEMS) + lane;
+  const u32 woff = w * (32 * RP_ITEMS) + lane;  // tile offset of this thread's item 0
+  u32* wh = s.whist[w];
 
-  // ---- load, warp-striped (coalesced) ----
   KeyT key[RP_ITEMS];
-  u32 val[RP_ITEMS];
-  u32 rnk[RP_ITEMS];
+  u32 rnk[RP_ITEMS / 2];  // two 16-bit in-bucket ranks per register (a tile holds 4096 records)
+  if (count == RP_TILE) {
+    // ---- full tile: no per-item predicates ----
 #pragma unroll
-  for (int k = 0; k < RP_ITEMS; k++) {
-    u32 off = w * (32 * RP_ITEMS) + k * 32 + lane;
-    bool valid = off < count;
-    key[k] = valid ? kin[base + off] : (KeyT)0;
-    val[k] = valid ? (iota ? (u32)(base + off) : vin[base + off]) : 0u;
-  }
-  // ---- rank inside the warp: match + popc, warp-private digit counters ----
+    for (int k = 0; k < RP_ITEMS; k++) key[k] = kp[k * 32];
 #pragma unroll
-  for (int k = 0; k < RP_ITEMS; k++) {
-    u32 off = w * (32 * RP_ITEMS) + k * 32 + lane;
-    bool valid = off < count;
-    u32 d = valid ? ((u32)(key[k] >> shift) & (RADIX - 1)) : RADIX;
-    u32 m = __match_any_sync(FULL_MASK, d);
-    u32 before = __popc(m & lanemask_lt());
-    u32 prev = 0;
-    if (valid) prev = s.whist[w][d];
-    __syncwarp();
-    if (valid && before == 0) s.whist[w][d] = prev + __popc(m);
-    __syncwarp();
-    rnk[k] = prev + before;
+    for (int k = 0; k < RP_ITEMS; k++) {
+      const u32 d = (u32)(key[k] >> shift) & (RADIX - 1);
+      const u32 m = __match_any_sync(FULL_MASK, d);
+      const u32 leader = 31 - __clz(m);
+      const u32 before = __popc(m & lanemask_lt());
+      u32 prev = 0;
+      if (lane == leader) { prev = wh[d]; wh[d] = prev + before + 1; }  // leader is the highest lane: before+1 == popc(m)
+      prev = __shfl_sync(FULL_MASK, prev, leader);
+      const u32 r = prev + before;
+      if (k & 1) rnk[k >> 1] |= r << 16; else rnk[k >> 1] = r;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < RP_ITEMS; k++) key[k] = (woff + k * 32 < count) ? kp[k * 32] : (KeyT)0;
+#pragma unroll
+    for (int k = 0; k < RP_ITEMS; k++) {
+      const bool valid = woff + k * 32 < count;
+      const u32 d = valid ? ((u32)(key[k] >> shift) & (RADIX - 1)) : RADIX;
+      const u32 m = __match_any_sync(FULL_MASK, d);
+      const u32 leader = 31 - __clz(m);
+      const u32 before = __popc(m & lanemask_lt());
+      u32 prev = 0;
+      if (valid && lane == leader) { prev = wh[d]; wh[d] = prev + before + 1; }
+      prev = __shfl_sync(FULL_MASK, prev, leader);
+      const u32 r = prev + before;
+      if (k & 1) rnk[k >> 1] |= r << 16; else rnk[k >> 1] = r;
+    }
   }
   __syncthreads();
   // ---- per digit: prefix over warps, tile totals, digit scan, chained scan over tiles ----
@@ -120,17 +129,17 @@ k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
     u32 acc = 0;
 #pragma unroll
     for (int ww = 0; ww < RP_WARPS; ww++) {
-      u32 c = s.whist[ww][d];
+      const u32 c = s.whist[ww][d];
       s.whist[ww][d] = acc;
       acc += c;
     }
     const u32 total = acc;
     u32 dummy;
-    u32 ex = block_excl_add<RP_THREADS, u32>(total, s.ws, &dummy);
+    const u32 ex = block_excl_add<RP_THREADS, u32>(total, s.ws, &dummy);
     s.excl[d] = ex;
     // bucket start inside the segment, from the up-front histogram
-    u32 hcount = hist[((size_t)seg * npass + pass) * RADIX + d];
-    u32 hbase = block_excl_add<RP_THREADS, u32>(hcount, s.ws, &dummy);
+    const u32 hcount = hist[(size_t)seg * hist_seg_stride + hist_off + d];
+    const u32 hbase = block_excl_add<RP_THREADS, u32>(hcount, s.ws, &dummy);
     // decoupled look-back over the earlier tiles of this segment
     u32* st = status + (size_t)tile * RADIX + d;
     u32 excl_tiles = 0;
@@ -153,29 +162,34 @@ k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
     s.gbase[d] = (int)(hbase + excl_tiles) - (int)ex;
   }
   __syncthreads();
-  // ---- stage the tile in bucket order ----
+  // ---- stage the tile in bucket order (values are fetched only now: fewer live registers) ----
+  {
+    const u32* vp = vin + base + woff;
+    const u32 vbase = (u32)base + woff;
 #pragma unroll
-  for (int k = 0; k < RP_ITEMS; k++) {
-    u32 off = w * (32 * RP_ITEMS) + k * 32 + lane;
-    if (off < count) {
-      u32 d = (u32)(key[k] >> shift) & (RADIX - 1);
-      u32 p = s.excl[d] + s.whist[w][d] + rnk[k];
-      s.key[p] = key[k];
-      s.val[p] = val[k];
+    for (int k = 0; k < RP_ITEMS; k++) {
+      if (count == RP_TILE || woff + k * 32 < count) {
+        const u32 d = (u32)(key[k] >> shift) & (RADIX - 1);
+        const u32 r = (k & 1) ? (rnk[k >> 1] >> 16) : (rnk[k >> 1] & 0xffffu);
+        const u32 p = s.excl[d] + wh[d] + r;
+        s.key[p] = key[k];
+        s.val[p] = iota ? (vbase + k * 32) : vp[k * 32];
+      }
     }
   }
   __syncthreads();
   // ---- write every bucket run out coalesced ----
-  const size_t segbase = (size_t)seg << seg_shift;
+  KeyT* ko = kout + ((size_t)seg << seg_shift);
+  u32* vo = vout + ((size_t)seg << seg_shift);
 #pragma unroll
   for (int k = 0; k < RP_ITEMS; k++) {
-    u32 p = k * RP_THREADS + tid;
-    if (p < count) {
-      KeyT kk = s.key[p];
-      u32 d = (u32)(kk >> shift) & (RADIX - 1);
-      size_t dst = segbase + (size_t)((int)p + s.gbase[d]);
-      kout[dst] = kk;
-      vout[dst] = s.val[p];
+    const u32 p = k * RP_THREADS + tid;
+    if (count == RP_TILE || p < count) {
+      const KeyT kk = s.key[p];
+      const u32 d = (u32)(kk >> shift) & (RADIX - 1);
+      const u32 dst = (u32)((int)p + s.gbase[d]);
+      ko[dst] = kk;
+      vo[dst] = s.val[p];
     }
   }
 }
