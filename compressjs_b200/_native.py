@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2bz.so")
+LIB_PATH = os.environ.get("B2_LIB") or os.path.join(_HERE, "libb2bz.so")
 _LIB = None
 
 EXPORTS = [

@@ -28,7 +28,7 @@
 #define BK_THREADS 256
 #define BK_ITEMS 16
 __global__ void __launch_bounds__(BK_THREADS)
-k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ key32, u32* __restrict__ hist) {
+k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u64* __restrict__ rec, u32* __restrict__ hist) {
   __shared__ u32 h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -37,7 +37,7 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
   const u32 start = lt * (BK_THREADS * BK_ITEMS);
   if (start >= n) return;
   const u8* t = T + ((size_t)b << SEG_SHIFT);
-  u32* ko = key32 + ((size_t)b << SEG_SHIFT);
+  u64* ko = rec + ((size_t)b << SEG_SHIFT);
 #pragma unroll 4
   for (int k = 0; k < BK_ITEMS; k++) {
     const u32 i = start + k * BK_THREADS + threadIdx.x;
@@ -46,7 +46,7 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
       u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
       u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
       const u32 c0 = t[i];
-      ko[i] = (c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3];
+      ko[i] = ((u64)((c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3]) << 32) | ((b << SEG_SHIFT) | i);
       atomicAdd(&h[c0], 1u);
     }
   }
@@ -179,9 +179,10 @@ k_rerank(const u32* __restrict__ key32, const u64* __restrict__ key64, const u32
 // block, compaction offsets as one flat chain over all tiles.
 #define RI_PAD(j) ((j) + ((j) >> 5))
 __global__ void __launch_bounds__(RR_THREADS)
-k_rerank_init(const u32* __restrict__ key32, const u32* __restrict__ vals, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ rank,
+k_rerank_init(const u64* __restrict__ rec, u32* __restrict__ SA, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ rank,
               u32* __restrict__ next_head, u32* __restrict__ next_idx, u32* next_count, u32* ticket, u64* st_new, u64* st_cnt, u32 ntiles) {
   __shared__ u32 sk[RR_TILE + RR_TILE / 32 + 2];
+  __shared__ u32 sg[RR_TILE + RR_TILE / 32 + 2];
   __shared__ u32 ws[RR_THREADS / 32 + 1];
   __shared__ u32 s_tile, s_cn, s_cc, s_prev, s_next;
   const u32 tid = threadIdx.x;
@@ -193,10 +194,15 @@ k_rerank_init(const u32* __restrict__ key32, const u32* __restrict__ vals, const
   const u32 start = lt * RR_TILE;
   const u32 cnt = start < n ? min((u32)RR_TILE, n - start) : 0u;
   const size_t base = ((size_t)b << SEG_SHIFT) + start;
-  for (u32 j = tid; j < cnt; j += RR_THREADS) sk[RI_PAD(j)] = key32[base + j];
+  for (u32 j = tid; j < cnt; j += RR_THREADS) {
+    const u64 rv = rec[base + j];
+    sk[RI_PAD(j)] = (u32)(rv >> 32);
+    sg[RI_PAD(j)] = (u32)rv;
+    SA[base + j] = (u32)rv;
+  }
   if (tid == 0 && cnt) {
-    s_prev = start ? key32[base - 1] : 0u;
-    s_next = (start + cnt < n) ? key32[base + cnt] : 0u;
+    s_prev = start ? (u32)(rec[base - 1] >> 32) : 0u;
+    s_next = (start + cnt < n) ? (u32)(rec[base + cnt] >> 32) : 0u;
   }
   __syncthreads();
   u32 vn[RR_ITEMS], nc[RR_ITEMS];
@@ -236,7 +242,7 @@ k_rerank_init(const u32* __restrict__ key32, const u32* __restrict__ vals, const
     if (p < cnt) {
       run_n = max(run_n, vn[j]);
       const u32 lastnew = run_n - 1;  // position (inside the block) of this suffix's group head
-      const u32 g = vals[base + p];
+      const u32 g = sg[RI_PAD(p)];
       rank[g] = lastnew;
       if (nc[j]) { next_head[run_c] = (b << SEG_SHIFT) | lastnew; next_idx[run_c] = g; }
       run_c += nc[j];
@@ -284,32 +290,34 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   for (u32 b = 0; b < nblk; b++) { n_max = h_n[b] > n_max ? h_n[b] : n_max; n_total += h_n[b]; }
   if (n_total == 0) return;
   const u32 nslots = nblk << SEG_SHIFT;
-  DBuf<u32> keyA(c, nslots), keyB(c, nslots), valA(c, nslots), valB(c, nslots), rank(c, nslots);
+  DBuf<u64> recA(c, nslots), recB(c, nslots);
+  DBuf<u32> saBuf(c, nslots), rank(c, nslots);
   DBuf<u32> headA(c, n_total), idxA(c, n_total), cnt(c, 1), ticket(c, 1);
   const u32 rr_tiles_init = (nslots + RR_TILE - 1) / RR_TILE;
   DBuf<u64> st(c, (size_t)3 * rr_tiles_init);
-  u32 *kin = keyA, *kout = keyB, *vin = valA, *vout = valB;
+  u64 *kin = recA, *kout = recB;
+  u32 *vin = nullptr, *vout = nullptr;
 
   DBuf<u32> bytehist(c, (size_t)nblk * 256);
   CUDA_CHECK(cudaMemsetAsync(bytehist, 0, (size_t)nblk * 256 * 4, c.stream));
   const u32 bk_tps = (n_max + BK_THREADS * BK_ITEMS - 1) / (BK_THREADS * BK_ITEMS);
   k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist);
   KLAUNCH(c); KCHECK();
-  c.stats.bwt_bytes += n_total * 5;
-  radix_sort<u32>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 0, 4, true, n_total, bytehist.p);
-  // kin/vin now hold the sorted keys / suffix ids; vin doubles as the suffix array
-  u32* SA = vin;
+  c.stats.bwt_bytes += n_total * 9;
+  // keys-only sort of the packed records on their upper 32 bits (the 4-byte prefix)
+  radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist.p);
+  u32* SA = saBuf;
   CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
   CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
   CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4, c.stream));
   {
     const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;
     const u32 ri_tiles = ri_tps * nblk;  // <= rr_tiles_init
-    k_rerank_init<<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, vin, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init,
+    k_rerank_init<<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, SA, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init,
                                                          ri_tiles);
     KLAUNCH(c); KCHECK();
   }
-  c.stats.bwt_bytes += n_total * (8 + 4);
+  c.stats.bwt_bytes += n_total * (8 + 4 + 4);
   u32 M = 0;
   CUDA_CHECK(cudaMemcpyAsync(&M, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));

@@ -118,7 +118,7 @@ struct HdecWarp {
   // speculative window decode of the symbol stream
   u32 win[20];          // 544 bits of the stream, big-endian words
   u16 wsym[HD_WIN];     // symbol that would start at every bit offset of the window
-  u8 wlen[HD_WIN];      // its code length (0 = no valid code there)
+  u8 wlen[HD_WIN + 32]; // its code length (0 = no valid code there); tail stays 0
   u16 spos[HUFF_GROUP + 2];
   u32 c_cnt, c_pos, c_flag;
 };
@@ -263,6 +263,8 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     u32 m = 0, selector = 0;
     int status = 0;
     bool done = false;
+    s.wlen[HD_WIN + lane] = 0;
+    __syncwarp();
     while (!done) {
       if (selector >= ns) { status = DEC_DATA_ERROR; break; }          // :291
       const u32 g = sel[selector++];
@@ -309,16 +311,38 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
         }
         __syncwarp();
         if (lane == 0) {
-          u32 pos = 0, cnt = 0, flag = 0;
-          while (cnt < remaining && pos < HD_WIN) {
-            const u32 l = s.wlen[pos];
-            if (l == 0) { flag = 2; break; }
-            const u32 sy = s.wsym[pos];
-            s.spos[cnt++] = (u16)pos;
+          // lean serial part: only pos += len[pos]; everything else is checked by the whole warp below
+          u32 pos = 0, cnt = 0;
+          const u32 lim = remaining;
+#pragma unroll 5
+          for (; cnt < lim; cnt++) {
+            s.spos[cnt] = (u16)pos;
+            const u32 l = s.wlen[pos];   // wlen[HD_WIN ..] is 0: the walk parks at the window edge
+            if (l == 0) break;
             pos += l;
-            if (sy >= eob && sy > 1) { flag = 1; break; }                // end of block (:345)
           }
-          s.c_cnt = cnt; s.c_pos = pos; s.c_flag = flag;
+          s.c_cnt = cnt; s.c_pos = pos;
+        }
+        __syncwarp();
+        {
+          // whole warp: first end-of-block symbol on the chain, invalid code inside the window
+          u32 cntw = s.c_cnt;
+          const u32 posw = s.c_pos;
+          u32 flag = 0;
+          u32 first_eob = 0xffffffffu;
+          for (u32 i = lane; i < cntw; i += 32) {
+            const u32 sy = s.wsym[s.spos[i]];
+            if (sy >= eob && sy > 1) { first_eob = i; break; }
+          }
+          first_eob = __reduce_min_sync(FULL_MASK, first_eob);
+          if (first_eob != 0xffffffffu) {
+            flag = 1;
+            cntw = first_eob + 1;
+            if (lane == 0) { s.c_cnt = cntw; s.c_pos = (u32)s.spos[first_eob] + s.wlen[s.spos[first_eob]]; }
+          } else if (cntw < remaining && posw < HD_WIN) {
+            flag = 2;  // the walk stopped on an offset without a valid code (lib/Bzip2.js:299/306)
+          }
+          if (lane == 0) s.c_flag = flag;
         }
         __syncwarp();
         const u32 cnt = s.c_cnt, flag = s.c_flag;

@@ -21,6 +21,24 @@
 #define RP_WARPS (RP_THREADS / 32)
 #define RH_THREADS 256
 #define RH_TILE (RH_THREADS * 32)
+// MATCH.ANY runs on the narrow ADU pipe (~2 cycles per distinct value in the warp, ~60 cycles for
+// random digits); eight ballots on the bits of the digit give the same mask from the ALU side.
+// RP_HW_MATCH of the RP_ITEMS items use the hardware instruction so that both pipes stay busy.
+#ifndef RP_HW_MATCH
+#define RP_HW_MATCH 4
+#endif
+template <bool HW>
+__device__ __forceinline__ u32 match_digit(u32 d) {
+  if (HW) return __match_any_sync(FULL_MASK, d);
+  u32 m = FULL_MASK;
+#pragma unroll
+  for (int b = 0; b < RADIX_BITS; b++) {
+    const bool bit = (d >> b) & 1u;
+    const u32 bal = __ballot_sync(FULL_MASK, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
 
 // status word of the per-digit chained scan: 2 flag bits + 30-bit count
 #define RS_AGG 0x40000000u
@@ -50,10 +68,10 @@ k_radix_hist(const KeyT* __restrict__ keys, const u32* __restrict__ seg_n, u32 t
     if (h[i]) atomicAdd(&hist[(size_t)seg * npass * RADIX + i], h[i]);
 }
 
-template <typename KeyT>
+template <typename KeyT, bool HAS_VALS>
 struct RadixSmem {
   KeyT key[RP_TILE];
-  u32 val[RP_TILE];
+  u32 val[HAS_VALS ? RP_TILE : 1];
   u32 whist[RP_WARPS][RADIX];
   u32 excl[RADIX];   // exclusive prefix of the digit totals inside this tile
   int gbase[RADIX];  // global destination of bucket d's first element minus excl[d]
@@ -64,13 +82,15 @@ struct RadixSmem {
 // hist_stride / hist_pass_stride let several passes share one histogram (the 4-byte-prefix keys of
 // all rotations have the same digit histogram in every pass: the block's byte histogram).
 // iota != 0: values are synthesised as the global slot index (first pass of the initial sort).
-template <typename KeyT>
+// HAS_VALS = false: keys-only sort (the initial BWT sort packs (4-byte prefix << 32 | suffix id) into
+// one 64-bit record, so every record is a single 8-byte load, stage and store).
+template <typename KeyT, bool HAS_VALS>
 __global__ void __launch_bounds__(RP_THREADS)
 k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __restrict__ kout,
              u32* __restrict__ vout, const u32* __restrict__ seg_n, u32 tiles_per_seg, u32 seg_shift,
              const u32* __restrict__ hist, u32 hist_seg_stride, u32 hist_off, u32 shift, u32* ticket, u32* status, int iota) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RadixSmem<KeyT>& s = *reinterpret_cast<RadixSmem<KeyT>*>(smem_raw);
+  RadixSmem<KeyT, HAS_VALS>& s = *reinterpret_cast<RadixSmem<KeyT, HAS_VALS>*>(smem_raw);
   const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s.tile = atomicAdd(ticket, 1u);
 #pragma unroll
@@ -96,7 +116,7 @@ k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
 #pragma unroll
     for (int k = 0; k < RP_ITEMS; k++) {
       const u32 d = (u32)(key[k] >> shift) & (RADIX - 1);
-      const u32 m = __match_any_sync(FULL_MASK, d);
+      const u32 m = (k % (RP_ITEMS / (RP_HW_MATCH ? RP_HW_MATCH : 1)) == 0 && RP_HW_MATCH) ? match_digit<true>(d) : match_digit<false>(d);
       const u32 leader = 31 - __clz(m);
       const u32 before = __popc(m & lanemask_lt());
       u32 prev = 0;
@@ -173,7 +193,7 @@ k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
         const u32 r = (k & 1) ? (rnk[k >> 1] >> 16) : (rnk[k >> 1] & 0xffffu);
         const u32 p = s.excl[d] + wh[d] + r;
         s.key[p] = key[k];
-        s.val[p] = iota ? (vbase + k * 32) : vp[k * 32];
+        if (HAS_VALS) s.val[p] = iota ? (vbase + k * 32) : vp[k * 32];
       }
     }
   }
@@ -189,7 +209,7 @@ k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
       const u32 d = (u32)(kk >> shift) & (RADIX - 1);
       const u32 dst = (u32)((int)p + s.gbase[d]);
       ko[dst] = kk;
-      vo[dst] = s.val[p];
+      if (HAS_VALS) vo[dst] = s.val[p];
     }
   }
 }

@@ -5,14 +5,14 @@
 
 // shared_hist != nullptr: a ready [nseg][256] histogram that is valid for EVERY pass (initial BWT sort);
 // otherwise the per-pass histograms are computed by k_radix_hist from the keys.
-template <typename KeyT>
+template <typename KeyT, bool HAS_VALS = true>
 static void radix_sort(Ctx& c, KeyT*& kin, u32*& vin, KeyT*& kout, u32*& vout, const u32* d_seg_n, u32 nseg, u32 seg_shift,
                        u32 max_seg_n, u32 begin_bit, u32 npass, bool iota_first, u64 total_elems, const u32* shared_hist = nullptr) {
   if (npass == 0 || total_elems == 0) return;
   static bool attr_set = false;  // per translation unit (kernels are instantiated per TU)
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<u32>)));
-    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<u64>)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<KeyT, HAS_VALS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(RadixSmem<KeyT, HAS_VALS>)));
     attr_set = true;
   }
   const u32 tps = (max_seg_n + RP_TILE - 1) / RP_TILE;
@@ -32,12 +32,12 @@ static void radix_sort(Ctx& c, KeyT*& kin, u32*& vin, KeyT*& kout, u32*& vout, c
   for (u32 p = 0; p < npass; p++) {
     const int iota = (iota_first && p == 0) ? 1 : 0;
     size_t ev = c.begin(ST_RADIX);
-    k_radix_pass<KeyT><<<(unsigned)ntiles, RP_THREADS, sizeof(RadixSmem<KeyT>), c.stream>>>(
+    k_radix_pass<KeyT, HAS_VALS><<<(unsigned)ntiles, RP_THREADS, sizeof(RadixSmem<KeyT, HAS_VALS>), c.stream>>>(
         kin, vin, kout, vout, d_seg_n, tps, seg_shift, shared_hist ? shared_hist : hist.p, shared_hist ? RADIX : npass * RADIX,
         shared_hist ? 0 : p * RADIX, begin_bit + p * RADIX_BITS, ticket.p + p, status.p + (size_t)p * ntiles * RADIX, iota);
     c.end(ev);
     KLAUNCH(c); KCHECK();
-    const u64 bytes = total_elems * (2 * sizeof(KeyT) + (iota ? 4 : 8));
+    const u64 bytes = total_elems * (2 * sizeof(KeyT) + (HAS_VALS ? (iota ? 4 : 8) : 0));
     c.stats.radix_launches++;
     c.stats.radix_bytes += bytes;
     c.stats.bwt_bytes += bytes;
