@@ -577,21 +577,29 @@ __global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restric
   segs[(size_t)ci * IB_SEGS + sid] = sg;
 }
 
-// order the segments along the chain that starts at the start row
-__global__ void k_ibwt_chain(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Seg* __restrict__ segs,
-                             Visit* __restrict__ visits, u32* __restrict__ nvisits) {
-  const u32 ci = blockIdx.x * blockDim.x + threadIdx.x;
+// order the segments along the chain that starts at the start row.  One CTA per block: the segment
+// table (32 KB) is staged in shared memory so that the serial walk costs a shared-memory load per step.
+__global__ void __launch_bounds__(128)
+k_ibwt_chain(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Seg* __restrict__ segs,
+             Visit* __restrict__ visits, u32* __restrict__ nvisits) {
+  __shared__ Seg ss[IB_SEGS];
+  const u32 ci = blockIdx.x;
   if (ci >= ncand) return;
   const CandRes* r = res + ci;
-  if (r->status != 0) { nvisits[ci] = 0; return; }
+  if (r->status != 0) { if (threadIdx.x == 0) nvisits[ci] = 0; return; }
   const u32 n = r->n;
+  const u32 nseg = min((u32)IB_SEGS, (n >> IB_SHIFT) + 2);
+  for (u32 i = threadIdx.x; i < nseg; i += blockDim.x) ss[i] = segs[(size_t)ci * IB_SEGS + i];
+  if (threadIdx.x == 0) ss[IB_SEGS - 1] = segs[(size_t)ci * IB_SEGS + IB_SEGS - 1];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   const u32* p = P + ((size_t)ci << SEG_SHIFT);
   const u32 r0 = p[r->orig] >> 8;
   u32 cur = ((r0 & (IB_STEP - 1)) == 0) ? (r0 >> IB_SHIFT) : (IB_SEGS - 1);
   u32 off = 0, nv = 0;
   Visit* v = visits + (size_t)ci * IB_VCAP;
   while (off < n) {
-    const Seg sg = segs[(size_t)ci * IB_SEGS + cur];
+    const Seg sg = ss[cur];
     const u32 len = min(sg.len, n - off);
     if (nv >= IB_VCAP) { nv = 0xffffffffu; break; }  // degenerate (periodic) block: fall back to one serial walk
     Visit vv;
@@ -878,7 +886,7 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
           const u32* Ps = Pp + ((size_t)s0 << SEG_SHIFT);
           k_ibwt_walk1<<<(sc * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS);
           KLAUNCH(c); KCHECK();
-          k_ibwt_chain<<<(sc + 31) / 32, 32, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0);
+          k_ibwt_chain<<<sc, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0);
           KLAUNCH(c); KCHECK();
           k_ibwt_walk2<<<(sc * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0,
                                                                        rle.p + ((k0 + s0) << SEG_SHIFT));

@@ -70,17 +70,25 @@ __global__ void __launch_bounds__(256) k_mtf_prefix(const u32* __restrict__ seg_
 }
 
 #define MR_WARPS 8
-// MTF rank of byte c = number of byte values that were used more recently than c.  Every byte value
-// carries a 15-bit recency key (larger = more recent): 255 - (position in the list at the chunk
-// start) before its first use inside the chunk, 256 + (position inside the chunk) afterwards.  The
-// 256 keys live in registers, 8 per lane as 4 x (2 x 16 bit) with the top bit of every half preset,
-// so "key > q" for two keys is one subtraction (bit 15 / 31 survive iff no borrow); the rank is a
-// popcount + one warp REDUX.  Nothing is shifted: using a byte only rewrites its own key.
+#define MB_BUCKETS 36   // recency keys live in [0, 256 + 4096): 34 buckets of 128 values (+ slack)
+struct MtfWarp {
+  u32 skey[256];              // scratch for the start-of-chunk ranking
+  u16 K[256];                 // recency key of every byte value (larger = used more recently)
+  u32 bm[MB_BUCKETS][4];      // bitmap of the key values that are currently somebody's key
+  u32 S[MB_BUCKETS];          // S[b] = number of live keys in buckets above b
+  u32 Pw[16];                 // the window's previous-use times, two 16-bit values per word
+};
+// MTF rank of a byte = number of byte values used more recently than it.  Every byte value carries
+// a 15-bit recency key: 255 - (list position at the chunk start) until it is used inside the chunk,
+// 256 + (position inside the chunk) afterwards.  A warp ranks 32 bytes per step:
+//   * P_i = time of the previous use of lane i's byte (an earlier lane of the window, or its key)
+//   * rank_i = #{keys alive before the window that are > P_i}        (bucket suffix sums + bitmap)
+//            + #{k in (prev_i, i) : P_k < P_i}                       (first use after P_i inside the window)
+//   * only the last use of a byte inside the window rewrites its key.
 __global__ void __launch_bounds__(MR_WARPS * 32)
 k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, const u32* __restrict__ lastpos,
             const u32* __restrict__ used, u8* __restrict__ R, u32 nblk) {
-  __shared__ u32 skey[MR_WARPS][256];
-  __shared__ u16 sk16[MR_WARPS][256];
+  __shared__ MtfWarp sm[MR_WARPS];
   const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 gchunk = blockIdx.x * MR_WARPS + w;
   const u32 seg = gchunk / cps, ch = gchunk % cps;
@@ -90,6 +98,7 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
   const u32 start = ch * MTF_CHUNK;
   if (start >= n) return;
   const u32 count = min((u32)MTF_CHUNK, n - start);
+  MtfWarp& s = sm[w];
   // ---- list position of every byte value at the chunk start (rank by counting) ----
   const u32* lp = lastpos + (size_t)gchunk * 256;
   u32 mykey[8];
@@ -103,68 +112,98 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
     else if (isused) key = 0x200u + (255u - c);  // not seen yet: ascending byte value
     else key = 255u - c;                    // never occurs: behind everything
     mykey[i] = key;
-    skey[w][c] = key;
+    s.skey[c] = key;
   }
   __syncwarp();
   u32 rk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (u32 c2 = 0; c2 < 256; c2++) {
-    const u32 k2 = skey[w][c2];
+    const u32 k2 = s.skey[c2];
 #pragma unroll
     for (int i = 0; i < 8; i++) rk[i] += (k2 > mykey[i]) ? 1u : 0u;
   }
-  u32 kw[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const u32 a = 255u - rk[2 * i], b2 = 255u - rk[2 * i + 1];
-    kw[i] = 0x80008000u | a | (b2 << 16);
-    sk16[w][lane * 8 + 2 * i] = (u16)a;
-    sk16[w][lane * 8 + 2 * i + 1] = (u16)b2;
-  }
+  for (int i = 0; i < 8; i++) s.K[lane * 8 + i] = (u16)(255u - rk[i]);
+  // all 256 start keys 0..255 are alive: buckets 0 and 1 full, the rest empty
+  for (u32 i = lane; i < MB_BUCKETS * 4; i += 32) (&s.bm[0][0])[i] = (i < 8) ? 0xffffffffu : 0u;
   __syncwarp();
-  // ---- walk the chunk, 128 bytes per outer step ----
   const u8* src = U + ((size_t)seg << SEG_SHIFT) + start;
   u8* dst = R + ((size_t)seg << SEG_SHIFT) + start;
-  u32 prevc = 0x100;  // nothing yet
-  for (u32 base = 0; base < count; base += 128) {
-    u32 word = 0;
-    {
-      const u32 o = base + lane * 4;
-      if (o + 4 <= count) word = *reinterpret_cast<const u32*>(src + o);  // start and slots are 4-aligned
-      else {
-        for (u32 b = 0; b < 4; b++) if (o + b < count) word |= (u32)src[o + b] << (8 * b);
-      }
-    }
-    u32 outw = 0;
-    const u32 lim = min(128u, count - base);
-    for (u32 idx = 0; idx < lim; idx++) {
-      const u32 wsrc = __shfl_sync(FULL_MASK, word, idx >> 2);
-      const u32 c = (wsrc >> ((idx & 3) * 8)) & 255u;
-      if (c == prevc) continue;  // still the front of the list: rank 0, nothing changes
-      prevc = c;
-      const u32 qq = ((u32)sk16[w][c] + 1u) * 0x00010001u;
-      const u32 M = 0x80008000u;
-      const u32 cntl = __popc((kw[0] - qq) & M) + __popc((kw[1] - qq) & M) + __popc((kw[2] - qq) & M) + __popc((kw[3] - qq) & M);
-      const u32 j = __reduce_add_sync(FULL_MASK, cntl);
-      const u32 nk = 256u + base + idx;
-      if (lane == 0) sk16[w][c] = (u16)nk;
-      if (lane == (c >> 3)) {
-        const u32 val = (c & 1) ? ((0x8000u | nk) << 16) : (0x8000u | nk);
-        const u32 msk = (c & 1) ? 0x0000ffffu : 0xffff0000u;
-        const u32 wi = (c >> 1) & 3;
-        kw[0] = wi == 0 ? ((kw[0] & msk) | val) : kw[0];
-        kw[1] = wi == 1 ? ((kw[1] & msk) | val) : kw[1];
-        kw[2] = wi == 2 ? ((kw[2] & msk) | val) : kw[2];
-        kw[3] = wi == 3 ? ((kw[3] & msk) | val) : kw[3];
-      }
-      if (lane == (idx >> 2)) outw |= j << ((idx & 3) * 8);
+  const u32 H = 0x80008000u, ONE = 0x00010001u;
+  for (u32 base = 0; base < count; base += 32) {
+    const bool valid = base + lane < count;
+    const u32 c = valid ? (u32)src[base + lane] : (256u + lane);
+    // ---- bucket suffix sums of the keys alive before this window ----
+    if (lane < MB_BUCKETS) {
+      // handled below with a full-warp reverse scan (MB_BUCKETS > 32 -> two steps)
     }
     {
-      const u32 o = base + lane * 4;
-      if (o + 4 <= count) *reinterpret_cast<u32*>(dst + o) = outw;
-      else {
-        for (u32 b = 0; b < 4; b++) if (o + b < count) dst[o + b] = (u8)(outw >> (8 * b));
-      }
+      u32 c0 = __popc(s.bm[lane][0]) + __popc(s.bm[lane][1]) + __popc(s.bm[lane][2]) + __popc(s.bm[lane][3]);
+      u32 c1 = 0;
+      if (lane < MB_BUCKETS - 32) c1 = __popc(s.bm[32 + lane][0]) + __popc(s.bm[32 + lane][1]) + __popc(s.bm[32 + lane][2]) + __popc(s.bm[32 + lane][3]);
+      // inclusive suffix sums over lanes (high lanes first)
+      u32 hi = c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(FULL_MASK, hi, o); if (lane + o < 32) hi += t; }
+      const u32 tot_hi = __shfl_sync(FULL_MASK, hi, 0);
+      u32 lo = c0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_down_sync(FULL_MASK, lo, o); if (lane + o < 32) lo += t; }
+      s.S[lane] = lo - c0 + tot_hi;
+      if (lane < MB_BUCKETS - 32) s.S[32 + lane] = hi - c1;
     }
+    // ---- who used my byte last? ----
+    const u32 m = __match_any_sync(FULL_MASK, c);
+    const u32 pm = m & lanemask_lt();
+    const int prev = pm ? (31 - __clz(pm)) : -1;
+    const bool is_last = (m >> lane) <= 1u;  // no higher lane holds the same byte
+    const u32 tb = 256u + base;
+    const u32 q = valid ? (u32)s.K[c] : 0u;
+    const u32 Pi = prev >= 0 ? (tb + (u32)prev) : q;
+    // publish P (two lanes per word)
+    {
+      const u32 other = __shfl_down_sync(FULL_MASK, Pi, 1);
+      if (!(lane & 1)) s.Pw[lane >> 1] = Pi | (other << 16);
+    }
+    __syncwarp();
+    // ---- keys alive before the window and more recent than P_i (only when P_i is such a key) ----
+    u32 rank = 0;
+    if (prev < 0 && valid) {
+      const u32 b = q >> 7, off = q & 127u, wi = off >> 5;
+      rank = s.S[b];
+      const u32 w0 = s.bm[b][0], w1 = s.bm[b][1], w2 = s.bm[b][2], w3 = s.bm[b][3];
+      const u32 cur = wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
+      rank += __popc(cur & ((0xfffffffeu) << (off & 31u)));
+      if (wi < 1) rank += __popc(w1);
+      if (wi < 2) rank += __popc(w2);
+      if (wi < 3) rank += __popc(w3);
+    }
+    // ---- first uses after P_i inside the window: k in (prev_i, i) with P_k < P_i ----
+    {
+      const u32 PiPi = ((Pi * ONE) | H) - ONE;          // (P_i | 0x8000) - 1 in both halves
+      const u32 lanes2 = ((lane * ONE) | H) - ONE;        // for k < i
+      const u32 pe = (u32)(prev + 1) * ONE;               // for k >= prev + 1
+      u32 acc = 0;
+#pragma unroll
+      for (u32 j = 0; j < 16; j++) {
+        const u32 Pk = s.Pw[j];
+        const u32 kk = (2 * j) | ((2 * j + 1) << 16);
+        const u32 z1 = PiPi - Pk;                         // bit15/31: P_k < P_i
+        const u32 z2 = lanes2 - kk;                       // k < i
+        const u32 z3 = ((kk + ONE) | H) - ONE - pe;       // k + 1 > prev + 1 - 1 ... k >= prev + 1
+        acc |= ((z1 & z2 & z3) & H) >> j;
+      }
+      rank += __popc(acc);
+    }
+    if (valid) dst[base + lane] = (u8)rank;
+    // ---- the last use of every byte in the window rewrites its key ----
+    if (valid && is_last) {
+      atomicAnd(&s.bm[q >> 7][(q & 127u) >> 5], ~(1u << (q & 31u)));
+      s.K[c] = (u16)(tb + lane);
+    }
+    const u32 newbits = __ballot_sync(FULL_MASK, valid && is_last);
+    __syncwarp();
+    if (lane == 0) s.bm[tb >> 7][(tb & 127u) >> 5] = newbits;  // windows are 32-aligned: this word is ours alone
+    __syncwarp();
   }
 }
 
