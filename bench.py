@@ -119,7 +119,11 @@ def run_reference(args):
         return
     from oracle import oracle as O
     O.build()
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 32))  # one 900k block (~60 MB of working set) per thread; more threads only thrash the host caches
     per_step_blocks = max(2, cores)  # one 900k block per core and step keeps the run in minutes
     mb = int(os.environ.get("B2_BENCH_MB", "1024"))
     data = gen_ascii(min(mb << 20, per_step_blocks * 900000 + 1000), SEED)

@@ -20,6 +20,8 @@ struct Ctx {
   std::vector<b2_block_trace> trace;
   u32 bwt_batch = 296;  // bzip2 blocks processed together in one batch (2 CTAs x 148 SMs for the per-block kernels)
   bool timing = true;
+  // plan handed from b2_bzip2_plan to the next b2_bzip2_encode_range_dev on the same (unchanged) buffer
+  void* plan_cache = nullptr; const void* plan_ptr = nullptr; size_t plan_n = 0; int plan_level = 0;
 
   void* dalloc(size_t bytes) {
     void* p = nullptr;

@@ -301,15 +301,29 @@ __global__ void k_file_ends(u32* out, int level, const u64* state, int write_hea
 void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n, size_t first_block,
                            size_t block_count, int bit_phase, bool whole_file, u64* out_bits, std::vector<u32>* crcs_out,
                            size_t* total_blocks) {
-  Rle1Plan plan;
-  {
+  // b2_bzip2_plan() leaves its plan for the encode_range call that follows on the same buffer
+  Rle1Plan* planp = nullptr;
+  const bool plan_only = !whole_file && block_count == 0;
+  if (!whole_file && !plan_only && c.plan_cache && c.plan_ptr == d_in && c.plan_n == n && c.plan_level == level) {
+    planp = static_cast<Rle1Plan*>(c.plan_cache);
+    c.plan_cache = nullptr;
+  } else {
+    if (c.plan_cache) { delete static_cast<Rle1Plan*>(c.plan_cache); c.plan_cache = nullptr; }
+    planp = new Rle1Plan();
     StageScope s(c, ST_RLE1);
-    rle1_plan(c, d_in, n, level, plan);
+    rle1_plan(c, d_in, n, level, *planp);
   }
+  struct PlanOwner { Rle1Plan* p; bool keep; ~PlanOwner() { if (!keep) delete p; } } owner{planp, false};
+  Rle1Plan& plan = *planp;
   const size_t nb_all = plan.nblocks;
   if (total_blocks) *total_blocks = nb_all;
   c.trace.clear();
-  if (!whole_file && block_count == 0) { *out_n = 0; return; }
+  if (plan_only) {
+    *out_n = 0;
+    c.plan_cache = planp; c.plan_ptr = d_in; c.plan_n = n; c.plan_level = level;
+    owner.keep = true;
+    return;
+  }
   if (((size_t)d_out) & 3) throw B2Error{B2_ERR_BAD_ARG, "output buffer must be 4-byte aligned"};
   size_t first = whole_file ? 0 : std::min(first_block, nb_all);
   size_t count = whole_file ? nb_all : std::min(block_count, nb_all - first);
