@@ -14,7 +14,9 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
 u32 crc32_device(Ctx& c, const u8* d_p, size_t n);
 void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n,
                            size_t first_block, size_t block_count, int bit_phase, bool whole_file, u64* out_bits,
-                           std::vector<u32>* crcs_out, size_t* total_blocks);
+                           std::vector<u32>* crcs_out, size_t* total_blocks, long long spec_first = -2, size_t spec_count = 0,
+                           u64* spec_range = nullptr);
+void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst);
 int bzip2_decompress_device(Ctx& c, const u8* d_in, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n,
                             bool single_block, u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len,
                             u8** d_out_alloc);
@@ -288,6 +290,29 @@ int b2_bzip2_plan(const void* d_in, size_t n, int level, size_t* total_blocks) {
     c.reset_call();
     size_t dummy = 0;
     bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, total_blocks);
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return 0;
+  });
+}
+
+int b2_bitshift_dev(const void* d_src, uint64_t nbits, int phase, void* d_dst) {
+  return guarded([&]() {
+    if (phase < 0 || phase > 7 || (((size_t)d_src | (size_t)d_dst) & 3)) throw B2Error{B2_ERR_BAD_ARG, "bad phase or unaligned buffers"};
+    Ctx& c = ctx_locked();
+    bitshift_device(c, d_src, nbits, phase, d_dst);
+    return 0;
+  });
+}
+
+int b2_bzip2_plan_spec(const void* d_in, size_t n, int level, int rank, int world, uint64_t* info) {
+  return guarded([&]() {
+    if (level < 1 || level > 9) throw B2Error{B2_ERR_BAD_LEVEL, "Invalid block size multiplier"};
+    if (world < 1 || rank < 0 || rank >= world) throw B2Error{B2_ERR_BAD_ARG, "bad rank/world"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    size_t dummy = 0;
+    bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, nullptr, -1,
+                          ((size_t)rank << 32) | (size_t)world, info);
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     return 0;
   });

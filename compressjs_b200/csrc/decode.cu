@@ -107,6 +107,7 @@ struct BitReader {
 // ---- header + Huffman decode: one warp per candidate ----------------------------------------
 #define HD_WARPS 4
 #define HD_WIN 512
+#define HD_STAGE 64
 struct HdecWarp {
   int limit[HUFF_MAXGROUPS][22];
   int base[HUFF_MAXGROUPS][22];
@@ -116,10 +117,12 @@ struct HdecWarp {
   int minlen[HUFF_MAXGROUPS], maxlen[HUFF_MAXGROUPS];
   int status; u32 ngroups, nsel, symcount;
   // speculative window decode of the symbol stream
-  u32 win[20];          // 544 bits of the stream, big-endian words
-  u16 wsym[HD_WIN];     // symbol that would start at every bit offset of the window
+  u32 win[HD_STAGE + 20]; // staged stream words (big-endian), refilled every ~2048 bits
+  u16 wsym[HD_WIN + 32]; // symbol that would start at every bit offset of the window; tail stays 0
   u8 wlen[HD_WIN + 32]; // its code length (0 = no valid code there); tail stays 0
-  u16 spos[HUFF_GROUP + 2];
+  u16 spos[HUFF_GROUP + 6];
+  u16 J1[HD_WIN + 32], J2[HD_WIN + 32], J4[HD_WIN + 32];  // chain jump tables: 1, 2 and 4 symbols ahead
+  u16 q4[16];
   u32 c_cnt, c_pos, c_flag;
 };
 
@@ -264,6 +267,8 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     int status = 0;
     bool done = false;
     s.wlen[HD_WIN + lane] = 0;
+    s.wsym[HD_WIN + lane] = 0;
+    u64 stage_w0 = ~0ull;  // index of the stream word held in win[0]
     __syncwarp();
     while (!done) {
       if (selector >= ns) { status = DEC_DATA_ERROR; break; }          // :291
@@ -272,77 +277,100 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
       const int minLen = s.minlen[g], maxLen = s.maxlen[g];
       u32 remaining = HUFF_GROUP;
       while (remaining && !done) {
-        // stage 17 words (544 bits) starting at the word that holds bit P
+        // (re)stage HD_STAGE + 18 words when the 544-bit window would leave the staged range
         const u64 w0 = P >> 5;
+        if (stage_w0 == ~0ull || w0 < stage_w0 || w0 + 18 > stage_w0 + HD_STAGE + 18) {
+          __syncwarp();
+          for (u32 i = lane; i < HD_STAGE + 18; i += 32) {
+            const u64 wi = w0 + i;
+            const u32 wv = wi < nwords ? words[wi] : 0u;
+            s.win[i] = __byte_perm(wv, 0, 0x0123);
+          }
+          stage_w0 = w0;
+          __syncwarp();
+        }
         const u32 shiftbase = (u32)(P & 31);
-        if (lane < 18) {
-          const u64 wi = w0 + lane;
-          const u32 wv = wi < nwords ? words[wi] : 0u;
-          s.win[lane] = __byte_perm(wv, 0, 0x0123);
+        {
+          // lane l decodes offsets l, l+32, ...: same bit shift every time, one new word per step
+          const u32 sh = (shiftbase + lane) & 31;
+          const u32* wp = s.win + (u32)(w0 - stage_w0) + ((shiftbase + lane) >> 5);
+          u32 hiw = wp[0];
+#pragma unroll 4
+          for (u32 k = 0; k < HD_WIN / 32; k++) {
+            const u32 low = wp[k + 1];
+            const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
+            hiw = low;
+            u32 sym = 0, len = 0;
+            const u32 ent = lut[bits20 >> 10];
+            if (ent) {
+              sym = ent & 511u; len = ent >> 9;
+            } else {
+              int i = minLen;
+              int j = (int)(bits20 >> (20 - i));
+              for (;;) {
+                if (i > maxLen) { i = 0; break; }                        // :299 -> marks "no code here"
+                if (j <= s.limit[g][i]) break;
+                i++;
+                if (i > 20) { i = 0; break; }
+                j = (int)(bits20 >> (20 - i));
+              }
+              if (i) {
+                const int jj = j - s.base[g][i];
+                if (jj >= 0 && jj < HUFF_MAXSYM) { sym = s.permute[g][jj]; len = (u32)i; }  // :306
+              }
+            }
+            s.wsym[lane + 32 * k] = (u16)sym;
+            s.wlen[lane + 32 * k] = (u8)len;
+          }
         }
         __syncwarp();
-#pragma unroll 4
-        for (u32 o = lane; o < HD_WIN; o += 32) {
-          const u32 bp = shiftbase + o;
-          const u32 wi = bp >> 5, sh = bp & 31;
-          const u64 v64 = ((u64)s.win[wi] << 32) | s.win[wi + 1];
-          const u32 bits20 = (u32)((v64 << sh) >> 44);
-          u32 sym = 0, len = 0;
-          const u32 ent = lut[bits20 >> 10];
-          if (ent) {
-            sym = ent & 511u; len = ent >> 9;
-          } else {
-            int i = minLen;
-            int j = (int)(bits20 >> (20 - i));
-            for (;;) {
-              if (i > maxLen) { i = 0; break; }                        // :299 -> marks "no code here"
-              if (j <= s.limit[g][i]) break;
-              i++;
-              if (i > 20) { i = 0; break; }
-              j = (int)(bits20 >> (20 - i));
-            }
-            if (i) {
-              const int jj = j - s.base[g][i];
-              if (jj >= 0 && jj < HUFF_MAXSYM) { sym = s.permute[g][jj]; len = (u32)i; }  // :306
-            }
-          }
-          s.wsym[o] = (u16)sym;
-          s.wlen[o] = (u8)len;
+        // jump tables: J1[o] = o + len[o] (an offset without a code, or beyond the window, maps to itself)
+#pragma unroll
+        for (u32 k = 0; k < (HD_WIN + 32) / 32; k++) {
+          const u32 o = lane + 32 * k;
+          s.J1[o] = (u16)min(o + (u32)s.wlen[o], (u32)(HD_WIN + 31));
+        }
+        __syncwarp();
+#pragma unroll
+        for (u32 k = 0; k < (HD_WIN + 32) / 32; k++) {
+          const u32 o = lane + 32 * k;
+          s.J2[o] = s.J1[s.J1[o]];
+        }
+        __syncwarp();
+#pragma unroll
+        for (u32 k = 0; k < (HD_WIN + 32) / 32; k++) {
+          const u32 o = lane + 32 * k;
+          s.J4[o] = s.J2[s.J2[o]];
         }
         __syncwarp();
         if (lane == 0) {
-          // lean serial part: only pos += len[pos]; everything else is checked by the whole warp below
-          u32 pos = 0, cnt = 0;
-          const u32 lim = remaining;
-#pragma unroll 5
-          for (; cnt < lim; cnt++) {
-            s.spos[cnt] = (u16)pos;
-            const u32 l = s.wlen[pos];   // wlen[HD_WIN ..] is 0: the walk parks at the window edge
-            if (l == 0) break;
-            pos += l;
-          }
-          s.c_cnt = cnt; s.c_pos = pos;
+          // the only serial part: 13 dependent shared-memory loads cover 52 symbols
+          u32 pos = 0;
+#pragma unroll
+          for (u32 i = 0; i < 13; i++) { s.q4[i] = (u16)pos; pos = s.J4[pos]; }
+        }
+        __syncwarp();
+        if (lane < 13) {
+          const u32 p0 = s.q4[lane], p1 = s.J1[p0], p2 = s.J1[p1], p3 = s.J1[p2];
+          s.spos[4 * lane] = (u16)p0; s.spos[4 * lane + 1] = (u16)p1; s.spos[4 * lane + 2] = (u16)p2; s.spos[4 * lane + 3] = (u16)p3;
         }
         __syncwarp();
         {
-          // whole warp: first end-of-block symbol on the chain, invalid code inside the window
-          u32 cntw = s.c_cnt;
-          const u32 posw = s.c_pos;
-          u32 flag = 0;
-          u32 first_eob = 0xffffffffu;
-          for (u32 i = lane; i < cntw; i += 32) {
-            const u32 sy = s.wsym[s.spos[i]];
-            if (sy >= eob && sy > 1) { first_eob = i; break; }
+          // whole warp: where does the group stop inside this window?
+          const u32 lim = remaining;  // <= 50
+          u32 first_stop = 0xffffffffu, first_eob = 0xffffffffu;
+          for (u32 i = lane; i < lim; i += 32) {
+            const u32 p = s.spos[i];
+            if (s.wlen[p] == 0 && first_stop == 0xffffffffu) first_stop = i;  // no code here, or past the window
+            const u32 sy = s.wsym[p];
+            if (sy >= eob && sy > 1 && first_eob == 0xffffffffu) first_eob = i;
           }
+          first_stop = __reduce_min_sync(FULL_MASK, first_stop);
           first_eob = __reduce_min_sync(FULL_MASK, first_eob);
-          if (first_eob != 0xffffffffu) {
-            flag = 1;
-            cntw = first_eob + 1;
-            if (lane == 0) { s.c_cnt = cntw; s.c_pos = (u32)s.spos[first_eob] + s.wlen[s.spos[first_eob]]; }
-          } else if (cntw < remaining && posw < HD_WIN) {
-            flag = 2;  // the walk stopped on an offset without a valid code (lib/Bzip2.js:299/306)
-          }
-          if (lane == 0) s.c_flag = flag;
+          u32 cntw = lim, flag = 0;
+          if (first_eob < first_stop && first_eob < lim) { cntw = first_eob + 1; flag = 1; }
+          else if (first_stop < lim) { cntw = first_stop; flag = (s.spos[first_stop] < HD_WIN) ? 2u : 0u; }  // :299/:306 vs. window exhausted
+          if (lane == 0) { s.c_cnt = cntw; s.c_pos = s.spos[cntw]; s.c_flag = flag; }
         }
         __syncwarp();
         const u32 cnt = s.c_cnt, flag = s.c_flag;

@@ -17,13 +17,16 @@ struct Rle1Plan {
   DBuf<u64> tile_prefix;  // per raw tile: W(tile start)
   DBuf<BlkInfo> blocks;   // device block table
   std::vector<BlkInfo> h_blocks;
-  size_t nblocks = 0;
+  size_t nblocks = 0;      // entries of h_blocks
+  size_t first_index = 0;  // global block index of h_blocks[0] (range plans)
+  size_t total_guess = 0;  // ceil(W(N) / blockSize)
   u64 ntiles = 0;
 };
 
 #define RLE_TILE 4096
 
 void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan);
+void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, long long spec_first, size_t spec_count, bool tiles_only);
 // materialise blocks [first, first+count) of the plan into the slot layout at d_T (u8[count<<20]);
 // d_n receives their lengths, d_crc their CRCs.
 void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc);

@@ -300,7 +300,7 @@ __global__ void k_file_ends(u32* out, int level, const u64* state, int write_hea
 // blocks [first_block, first_block+block_count) starting at bit `bit_phase` of d_out.
 void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n, size_t first_block,
                            size_t block_count, int bit_phase, bool whole_file, u64* out_bits, std::vector<u32>* crcs_out,
-                           size_t* total_blocks) {
+                           size_t* total_blocks, long long spec_first, size_t spec_count, u64* spec_range) {
   // b2_bzip2_plan() leaves its plan for the encode_range call that follows on the same buffer
   Rle1Plan* planp = nullptr;
   const bool plan_only = !whole_file && block_count == 0;
@@ -311,11 +311,30 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
     if (c.plan_cache) { delete static_cast<Rle1Plan*>(c.plan_cache); c.plan_cache = nullptr; }
     planp = new Rle1Plan();
     StageScope s(c, ST_RLE1);
-    rle1_plan(c, d_in, n, level, *planp);
+    if (spec_first >= -1 && plan_only && spec_range) {
+      // speculative range plan (multi-GPU): total guess first, then only this rank's blocks
+      rle1_plan_ex(c, d_in, n, level, *planp, -1, 0, true);
+      const size_t total = planp->total_guess;
+      size_t f = (size_t)spec_first, cnt = spec_count;
+      if (spec_first == -1) {  // caller passes (rank, world) in spec_count's two halves
+        const size_t rank = spec_count >> 32, world = spec_count & 0xffffffffu;
+        f = rank * total / world;
+        cnt = (rank + 1) * total / world - f;
+      }
+      rle1_plan_ex(c, d_in, n, level, *planp, (long long)f, cnt, false);
+      spec_range[0] = planp->nblocks ? planp->h_blocks.front().s : 0;
+      spec_range[1] = planp->nblocks ? planp->h_blocks.back().e : 0;
+      spec_range[2] = f;
+      spec_range[3] = cnt;
+      spec_range[4] = planp->nblocks;
+      spec_range[5] = total;
+    } else {
+      rle1_plan(c, d_in, n, level, *planp);
+    }
   }
   struct PlanOwner { Rle1Plan* p; bool keep; ~PlanOwner() { if (!keep) delete p; } } owner{planp, false};
   Rle1Plan& plan = *planp;
-  const size_t nb_all = plan.nblocks;
+  const size_t nb_all = plan.first_index + plan.nblocks;  // exact plans: first_index == 0
   if (total_blocks) *total_blocks = nb_all;
   c.trace.clear();
   if (plan_only) {
@@ -327,6 +346,8 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
   if (((size_t)d_out) & 3) throw B2Error{B2_ERR_BAD_ARG, "output buffer must be 4-byte aligned"};
   size_t first = whole_file ? 0 : std::min(first_block, nb_all);
   size_t count = whole_file ? nb_all : std::min(block_count, nb_all - first);
+  if (first < plan.first_index) throw B2Error{B2_ERR_BAD_ARG, "block range is not covered by the cached range plan"};
+  const size_t pofs = plan.first_index;  // h_blocks[k] is global block pofs + k
   const size_t cap_words = out_cap / 4;
   if (cap_words < 8) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
   CUDA_CHECK(cudaMemsetAsync(d_out, 0, cap_words * 4, c.stream));
@@ -355,10 +376,10 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
     for (size_t k0 = 0; k0 < count; k0 += B) {
       const u32 nb = (u32)std::min<size_t>(B, count - k0);
       u32 nmax = 0;
-      for (u32 b = 0; b < nb; b++) { hn[b] = plan.h_blocks[first + k0 + b].n; nmax = std::max(nmax, hn[b]); }
+      for (u32 b = 0; b < nb; b++) { hn[b] = plan.h_blocks[first - pofs + k0 + b].n; nmax = std::max(nmax, hn[b]); }
       {
         StageScope s(c, ST_RLE1);
-        rle1_materialize(c, d_in, n, plan, first + k0, nb, T, dn, dcrc);
+        rle1_materialize(c, d_in, n, plan, first - pofs + k0, nb, T, dn, dcrc);
       }
       {
         StageScope s(c, ST_BWT);
@@ -388,7 +409,7 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
       for (u32 b = 0; b < nb; b++) {
         b2_block_trace& t = tr[k0 + b];
-        const BlkInfo& bi = plan.h_blocks[first + k0 + b];
+        const BlkInfo& bi = plan.h_blocks[first - pofs + k0 + b];
         t.n = (int32_t)bi.n; t.pidx = (int32_t)hp[b]; t.m = (int32_t)hm[b]; t.alpha = (int32_t)hhb[b].alpha;
         t.ngroups = (int32_t)hhb[b].ngroups; t.nsel = (int32_t)hhb[b].nsel; t.crc = all_crc[k0 + b]; t.pad = 0;
         t.raw_start = bi.s; t.raw_len = bi.e - bi.s; t.bit_start = hoff[b]; t.bit_len = hhb[b].body_bits;
@@ -413,4 +434,28 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
   }
   if (crcs_out) *crcs_out = all_crc;
   c.trace = tr;
+}
+
+// ---- fragment shift for the multi-GPU gather -------------------------------------------------
+// dst holds src's first nbits starting at bit `phase` (MSB first); bits outside the fragment are 0.
+__global__ void k_bitshift(const u32* __restrict__ src, u64 nbits, u32 phase, u32* __restrict__ dst, u64 nwords_out) {
+  const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwords_out) return;
+  const u64 src_words = (nbits + 31) >> 5;
+  const u32 cur = w < src_words ? bswap32(src[w]) : 0u;
+  const u32 prv = (w > 0 && w - 1 < src_words) ? bswap32(src[w - 1]) : 0u;
+  u32 v = phase ? ((prv << (32 - phase)) | (cur >> phase)) : cur;
+  // clear everything behind bit (phase + nbits)
+  const u64 endbit = (u64)phase + nbits;
+  const u64 wstart = w << 5;
+  if (endbit <= wstart) v = 0;
+  else if (endbit < wstart + 32) v &= ~(0xffffffffu >> (u32)(endbit - wstart));
+  dst[w] = bswap32(v);
+}
+void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst) {
+  const u64 nwords = ((u64)phase + nbits + 31) >> 5;
+  if (nwords == 0) return;
+  k_bitshift<<<(unsigned)((nwords + 255) / 256), 256, 0, c.stream>>>((const u32*)src, nbits, (u32)phase, (u32*)dst, nwords);
+  KLAUNCH(c); KCHECK();
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }

@@ -16,7 +16,9 @@
 #define RADIX_BITS 8
 #define RADIX 256
 #define RP_THREADS 256
+#ifndef RP_ITEMS
 #define RP_ITEMS 16
+#endif
 #define RP_TILE (RP_THREADS * RP_ITEMS)
 #define RP_WARPS (RP_THREADS / 32)
 #define RH_THREADS 256

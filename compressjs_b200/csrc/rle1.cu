@@ -17,6 +17,7 @@
 //                      writes its literal (+ count byte) into the slot layout.
 //   CRC k_crc_pieces : 256-byte pieces, pure polynomial remainders shifted by x^(8*bytes after)
 //                      and XOR-combined per block (CRC is linear), then the init/final XOR.
+#include <algorithm>
 #include "enc.h"
 
 #define RT_THREADS 256
@@ -303,13 +304,53 @@ __device__ u64 find_run_end(const u8* in, u64 s, u64 cap, BlocksShared& sh) {
 
 __global__ void __launch_bounds__(RT_THREADS)
 k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ carry, const u64* __restrict__ prefix, u64 ntiles,
-             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks) {
+             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks, u64 u_start) {
   __shared__ BlocksShared sh;
   const u32 tid = threadIdx.x;
   const u64 Wtotal = prefix[ntiles];
   u64 s = 0, Ws = 0;
   bool Ws_valid = true;  // W(0) = 0
   u32 k = 0;
+  if (u_start > 0) {
+    // speculative start (multi-GPU range plan): the first raw position x with W(x) >= u_start, i.e. where a
+    // block boundary falls if no block before it was shifted by a run-phase slip (verified by the caller)
+    if (u_start > Wtotal) { if (tid == 0) *nblocks_out = 0; return; }
+    u64 lo = 0, hi = ntiles;
+    while (hi - lo > 1) {
+      const u64 span = hi - lo;
+      const u64 pi = lo + 1 + (span - 1) * (u64)tid / RT_THREADS;
+      const bool valid = pi < hi && (tid == 0 || pi != lo + 1 + (span - 1) * (u64)(tid - 1) / RT_THREADS);
+      const bool pr = valid && prefix[pi] < u_start;
+      const u32 tr = block_max256(pr ? tid + 1 : 0, sh.sc.red);
+      const u32 fl = block_min256((valid && !pr) ? tid : 0xffffffffu, sh.sc.red);
+      u64 nlo = lo, nhi = hi;
+      if (tr) nlo = lo + 1 + (span - 1) * (u64)(tr - 1) / RT_THREADS;
+      if (fl != 0xffffffffu) nhi = lo + 1 + (span - 1) * (u64)fl / RT_THREADS;
+      lo = nlo; hi = nhi;
+    }
+    const u64 t = lo;
+    TileView v;
+    tile_view(in, N, t * RLE_TILE, carry[t], sh.sc, v);
+    u32 found = 0xffffffffu;
+    {
+      u64 acc = prefix[t] + v.excl;
+      for (u32 j = 0; j < v.cnt; j++) {
+        acc += v.w[j];
+        if (acc >= u_start) { found = tid * RT_PER + j; break; }
+      }
+    }
+    const u32 f = block_min256(found, sh.sc.red);
+    if (f / RT_PER == tid) {
+      u64 acc = prefix[t] + v.excl;
+      for (u32 j = 0; j <= f % RT_PER; j++) acc += v.w[j];
+      sh.r64 = acc;
+    }
+    __syncthreads();
+    Ws = sh.r64;
+    __syncthreads();
+    s = t * RLE_TILE + f + 1;
+    Ws_valid = true;
+  }
   while (s < N && k < maxblocks) {
     BlkInfo bi;
     bi.s = s;
@@ -568,25 +609,44 @@ u32 crc32_device(Ctx& c, const u8* d_p, size_t n) {
 }
 
 // ---- host drivers ---------------------------------------------------------------------------
-void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) {
+// spec_first < 0: exact plan of the whole input.  Otherwise only blocks [spec_first, spec_first+spec_count) are
+// walked, starting from the speculative boundary W(s) = spec_first * BS (see k_rle_blocks); plan.first_index
+// records the global index of h_blocks[0] and plan.total_guess = ceil(W(N) / BS).
+void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, long long spec_first, size_t spec_count, bool tiles_only) {
   crc_setup();
   plan.nblocks = 0;
   plan.h_blocks.clear();
+  plan.first_index = 0;
+  plan.total_guess = 0;
   if (n == 0) return;
   const u32 BS = (u32)level * 100000 - 19;  // lib/Bzip2.js:892-900
   const u64 ntiles = (n + RLE_TILE - 1) / RLE_TILE;
-  plan.ntiles = ntiles;
-  DBuf<TileSum> sums(c, ntiles);
-  plan.tile_carry.alloc(c, ntiles);
-  plan.tile_prefix.alloc(c, ntiles + 1);
-  k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums);
-  KLAUNCH(c); KCHECK();
-  k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix);
-  KLAUNCH(c); KCHECK();
-  const u32 maxblocks = (u32)(n / ((u64)BS * 4 / 5) + 2);
+  if (plan.ntiles != ntiles || !plan.tile_prefix.p) {
+    plan.ntiles = ntiles;
+    DBuf<TileSum> sums(c, ntiles);
+    plan.tile_carry.alloc(c, ntiles);
+    plan.tile_prefix.alloc(c, ntiles + 1);
+    k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums);
+    KLAUNCH(c); KCHECK();
+    k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix);
+    KLAUNCH(c); KCHECK();
+  }
+  u64 wtotal = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&wtotal, plan.tile_prefix.p + ntiles, 8, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  plan.total_guess = (size_t)((wtotal + BS - 1) / BS);
+  if (tiles_only) return;
+  u32 maxblocks = (u32)(n / ((u64)BS * 4 / 5) + 2);
+  u64 u_start = 0;
+  if (spec_first >= 0) {
+    maxblocks = (u32)std::min<size_t>(maxblocks, spec_count);
+    u_start = (u64)spec_first * BS;
+    plan.first_index = (size_t)spec_first;
+    if (maxblocks == 0) return;
+  }
   plan.blocks.alloc(c, maxblocks);
   DBuf<u32> dnb(c, 1);
-  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks);
+  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, u_start);
   KLAUNCH(c); KCHECK();
   u32 nb = 0;
   CUDA_CHECK(cudaMemcpyAsync(&nb, dnb, 4, cudaMemcpyDeviceToHost, c.stream));
@@ -596,7 +656,7 @@ void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) {
   if (nb) CUDA_CHECK(cudaMemcpyAsync(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb, cudaMemcpyDeviceToHost, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
-
+void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) { rle1_plan_ex(c, d_in, n, level, plan, -1, 0, false); }
 void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc) {
   if (count == 0) return;
   std::vector<u64> tbase(count + 1), pbase(count + 1);

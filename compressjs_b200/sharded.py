@@ -35,6 +35,14 @@ def block_range(nblocks, rank, world):
 def shift_right_bits(frag, nbits, phase):
     """Returns a uint8 tensor holding `frag`'s first nbits starting at bit `phase` (MSB first)."""
     nbytes = (phase + nbits + 7) // 8
+    if frag.is_cuda and nbits:
+        from . import _native
+        out = torch.empty(((phase + nbits + 31) // 32) * 4, dtype=torch.uint8, device=frag.device)
+        torch.cuda.current_stream().synchronize()
+        rc = _native.lib().b2_bitshift_dev(frag.data_ptr(), nbits, phase, out.data_ptr())
+        if rc:
+            raise RuntimeError("b2_bitshift_dev: " + _native.last_error())
+        return out[:nbytes]
     src = frag[: (nbits + 7) // 8]
     out = torch.zeros(nbytes, dtype=torch.uint8, device=frag.device)
     if nbits == 0:
@@ -78,16 +86,26 @@ def assemble(level, frags, bits, crcs_per_rank, device):
         offs.append(o)
         o += int(b)
     total_bits = o + 80
-    out = torch.zeros((total_bits + 7) // 8, dtype=torch.uint8, device=device)
+    nbytes_out = (total_bits + 7) // 8
+    out = torch.empty(nbytes_out, dtype=torch.uint8, device=device)
+    out[max(0, nbytes_out - 12):] = 0   # trailer region (OR-ed below)
     out[:4] = torch.tensor(list(b"BZh" + bytes([0x30 + level])), dtype=torch.uint8, device=device)
+    edge = {}                   # bytes shared by two neighbours: byte index -> OR of the contributions
     for r, f in enumerate(frags):
         if bits[r] == 0:
             continue
         b0 = offs[r] // 8
         nb = (offs[r] % 8 + int(bits[r]) + 7) // 8
-        out[b0: b0 + nb] |= f[:nb].to(device)
+        if nb > 2:
+            out[b0 + 1: b0 + nb - 1] = f[1: nb - 1].to(device)     # interior bytes belong to this fragment alone
+        for bi in {0, nb - 1}:
+            edge[b0 + bi] = edge.get(b0 + bi, 0) | int(f[bi])
+    for k, v in edge.items():
+        if k >= 4:
+            out[k] = v
     crcs = [c for rc in crcs_per_rank for c in rc]
     b0, tb = trailer_bytes(o, fold_stream_crc(crcs))
+    # the first trailer byte may share its byte with the last fragment (already written via `edge`)
     out[b0: b0 + len(tb)] |= torch.tensor(list(tb), dtype=torch.uint8, device=device)
     return out
 
@@ -119,7 +137,7 @@ def compress_sharded(encode_range, nblocks, level, device, group=None):
     if count:
         crct[:count] = torch.tensor([int(c) for c in crcs], dtype=torch.int64, device=device)
     if rank == 0:
-        glist = [torch.zeros(maxlen, dtype=torch.uint8, device=device) for _ in range(world)]
+        glist = [torch.empty(maxlen, dtype=torch.uint8, device=device) for _ in range(world)]
         clist = [torch.zeros(maxcnt, dtype=torch.int64, device=device) for _ in range(world)]
         dist.gather(pad, glist, dst=0, group=group)
         dist.gather(crct, clist, dst=0, group=group)
@@ -130,15 +148,8 @@ def compress_sharded(encode_range, nblocks, level, device, group=None):
     return None
 
 
-def gpu_encode_range_fn(d_in, level):
-    """encode_range callable backed by libb2bz.so for a uint8 CUDA tensor holding the whole input."""
+def _range_encoder(L, d_in, n, level):
     from . import _native
-    L = _native.lib()
-    n = d_in.numel()
-    total = C.c_size_t()
-    rc = L.b2_bzip2_plan(d_in.data_ptr(), n, level, C.byref(total))
-    if rc:
-        raise RuntimeError("b2_bzip2_plan: " + _native.last_error())
 
     def encode_range(first, count):
         if count == 0:
@@ -152,10 +163,65 @@ def gpu_encode_range_fn(d_in, level):
             raise RuntimeError("b2_bzip2_encode_range_dev: " + _native.last_error())
         return out, int(bits.value), list(crcs)
 
-    return encode_range, int(total.value)
+    return encode_range
+
+
+def gpu_encode_range_fn(d_in, level):
+    """encode_range callable backed by libb2bz.so for a uint8 CUDA tensor holding the whole input
+    (exact plan: every block boundary of the file is cut on this GPU)."""
+    from . import _native
+    L = _native.lib()
+    n = d_in.numel()
+    total = C.c_size_t()
+    rc = L.b2_bzip2_plan(d_in.data_ptr(), n, level, C.byref(total))
+    if rc:
+        raise RuntimeError("b2_bzip2_plan: " + _native.last_error())
+    return _range_encoder(L, d_in, n, level), int(total.value)
+
+
+def spec_plan_ok(infos, n):
+    """infos[r] = (raw_start, raw_end, first, planned, cut, total) of every rank's speculative plan."""
+    world = len(infos)
+    total = infos[0][5]
+    pos = 0
+    nxt = 0
+    for r in range(world):
+        s, e, first, planned, cut, tot = infos[r]
+        if tot != total or first != nxt or cut != planned:
+            return False
+        if planned:
+            if s != pos:
+                return False
+            pos = e
+        nxt = first + planned
+    return nxt == total and pos == n
 
 
 def compress_file_sharded(d_in, level=9, group=None):
-    """Whole-file bzip2 encode of a CUDA uint8 tensor present on every rank; stream on rank 0."""
+    """Whole-file bzip2 encode of a CUDA uint8 tensor present on every rank; stream on rank 0.
+
+    Block cutting: every rank cuts only ITS share of the blocks from a speculative start boundary
+    (b2_bzip2_plan_spec); the ranks then check that the pieces chain exactly (end(r) == start(r+1), ...).
+    If a run-phase slip makes the speculation fail anywhere, all ranks fall back to the exact plan."""
+    from . import _native
+    L = _native.lib()
+    n = d_in.numel()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        enc, nblocks = gpu_encode_range_fn(d_in, level)
+        return compress_sharded(enc, nblocks, level, d_in.device, group)
+    info = (C.c_uint64 * 6)()
+    rc = L.b2_bzip2_plan_spec(d_in.data_ptr(), n, level, rank, world, info)
+    if rc:
+        raise RuntimeError("b2_bzip2_plan_spec: " + _native.last_error())
+    mine = torch.tensor([int(v) for v in info], dtype=torch.int64, device=d_in.device)
+    allv = [torch.zeros(6, dtype=torch.int64, device=d_in.device) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    infos = [tuple(int(x) for x in v.tolist()) for v in allv]
+    if spec_plan_ok(infos, n):
+        enc = _range_encoder(L, d_in, n, level)
+        first, count = infos[rank][2], infos[rank][3]
+        return compress_sharded(lambda f, c: enc(first, count), infos[0][5], level, d_in.device, group)
     enc, nblocks = gpu_encode_range_fn(d_in, level)
     return compress_sharded(enc, nblocks, level, d_in.device, group)

@@ -79,6 +79,16 @@ int b2_bzip2_decompress_dev(const void* d_in, size_t n, int multistream, void* d
  * *out_bits long.  block_crcs (host, cap entries) receives the per-block CRCs so the
  * caller can fold the stream CRC.  total_blocks receives the number of blocks in the file. */
 int b2_bzip2_plan(const void* d_in, size_t n, int level, size_t* total_blocks);
+/* Speculative range plan for rank `rank` of `world`: cuts only this rank's share of the blocks, starting from
+ * the boundary implied by W-space arithmetic (exact unless a run-phase slip happened earlier in the file).
+ * info[0..5] = raw start, raw end, first block, planned count, blocks actually cut, total block guess.
+ * The ranks must verify end(r) == start(r+1), start(0) == 0, end(last) == n and cut == planned on every rank
+ * (compressjs_b200/sharded.py does); otherwise fall back to b2_bzip2_plan.  The plan is cached for the next
+ * b2_bzip2_encode_range_dev on the same buffer. */
+int b2_bzip2_plan_spec(const void* d_in, size_t n, int level, int rank, int world, uint64_t* info);
+/* dst := the first nbits of src moved to start at bit `phase` (0..7, MSB first), zero outside; dst must hold
+ * ceil((phase+nbits)/32)*4 bytes and may not overlap src.  Used to align a fragment to its global bit offset. */
+int b2_bitshift_dev(const void* d_src, uint64_t nbits, int phase, void* d_dst);
 int b2_bzip2_encode_range_dev(const void* d_in, size_t n, int level, size_t first, size_t count, int bit_phase,
                               void* d_out, size_t out_cap, uint64_t* out_bits, uint32_t* block_crcs);
 

@@ -35,3 +35,33 @@ def test_compress_file_sharded_single_rank():
     d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
     out = S.compress_file_sharded(d_in, 9)
     assert bytes(out.cpu().numpy().tobytes()) == O.bzip2_compress(data, 9)
+
+
+@pytest.mark.parametrize("kind", ["ascii", "runs"])
+def test_speculative_range_plan_chains_or_is_rejected(kind):
+    """b2_bzip2_plan_spec for simulated ranks: when the pieces chain (spec_plan_ok) the assembled stream must be
+    the reference stream; run-heavy data must be detected as a failed speculation, never silently mis-cut."""
+    import ctypes as C
+    from compressjs_b200 import sharded as S, _native
+    L = _native.lib()
+    data = T.ascii_random(7 * 99981 + 1234, 31) if kind == "ascii" else T.runs(6 * 99981, 32)
+    level, world = 1, 4
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    exp = O.bzip2_compress(data, level)
+    infos, frags, bits, crcs = [], [], [], []
+    for r in range(world):
+        info = (C.c_uint64 * 6)()
+        assert L.b2_bzip2_plan_spec(d_in.data_ptr(), len(data), level, r, world, info) == 0, _native.last_error()
+        infos.append(tuple(int(v) for v in info))
+        f, nb, cr = S._range_encoder(L, d_in, len(data), level)(infos[-1][2], infos[-1][4])
+        frags.append(f); bits.append(nb); crcs.append(cr)
+    ok = S.spec_plan_ok(infos, len(data))
+    if kind == "ascii":
+        assert ok
+    if ok:
+        sh, acc = [], 0
+        for r in range(world):
+            sh.append(S.shift_right_bits(frags[r], bits[r], (32 + acc) % 8))
+            acc += bits[r]
+        out = S.assemble(level, sh, bits, crcs, d_in.device)
+        assert bytes(out.cpu().numpy().tobytes()) == exp

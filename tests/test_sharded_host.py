@@ -90,3 +90,13 @@ def test_single_process_path():
     enc, nblocks, z = _oracle_encoder(data, 1)
     out = S.compress_sharded(enc, nblocks, 1, torch.device("cpu"))
     assert out.numpy().tobytes() == z
+
+
+def test_spec_plan_verification():
+    ok = [(0, 100, 0, 2, 2, 5), (100, 250, 2, 3, 3, 5)]
+    assert S.spec_plan_ok(ok, 250)
+    assert not S.spec_plan_ok([(0, 100, 0, 2, 2, 5), (101, 250, 2, 3, 3, 5)], 250)   # gap between ranks
+    assert not S.spec_plan_ok([(0, 100, 0, 2, 2, 5), (100, 240, 2, 3, 3, 5)], 250)   # does not reach the end
+    assert not S.spec_plan_ok([(0, 100, 0, 2, 2, 5), (100, 250, 2, 3, 2, 5)], 250)   # a rank cut fewer blocks
+    assert not S.spec_plan_ok([(0, 100, 0, 2, 2, 5), (100, 250, 2, 3, 3, 6)], 250)   # totals disagree
+    assert S.spec_plan_ok([(0, 250, 0, 1, 1, 1), (0, 0, 1, 0, 0, 1)], 250)           # rank without blocks
