@@ -295,7 +295,9 @@ def main():
                     "sharded.compress_file_sharded (pinned host in on every rank, stream gathered to rank 0 over NCCL, D2H on rank 0)"},
             "gpu_launches": int(agg["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_radix_pass (BWT onesweep pass)", "achieved": radix_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": radix_gbs / peak if peak else None, "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                         "frac": radix_gbs / peak if peak else None,
+                         "traffic": ((tr or {}).get("dram_bytes_per_record") or 0) * (agg["radix_bytes"] / max(agg["radix_launches"], 1) / 16.0) or None,
+                         "traffic_source": (tr or {}).get("source"),
                          "peak_source": peak_src, "launches": int(agg["radix_launches"]),
                          "algorithmic_bytes_per_launch": agg["radix_bytes"] / max(agg["radix_launches"], 1),
                          "avg_launch_ms": agg["ms_radix"] / max(agg["radix_launches"], 1),
@@ -304,6 +306,8 @@ def main():
             "stages_ms_per_step": {k: agg[k] / args.steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack", "ms_radix")},
             "clocks": clocks,
         }
+        if world > 1:
+            line["sharded_phases_ms_last_step_rank0"] = {k: round(v, 2) for k, v in SH.PHASES.items()}
         if world == 1:
             # decode leg: the stream just produced, HBM resident (b2_bzip2_decompress_dev) -- the second half of the metric
             d_dec = torch.empty(nbytes, dtype=torch.uint8, device="cuda")

@@ -163,11 +163,58 @@ __device__ void tile_view(const u8* __restrict__ in, u64 N, u64 tstart, u32 carr
 }
 
 // ---- A ---------------------------------------------------------------------------------
+// Fast path: a tile that contains no four equal consecutive bytes (looking 3 bytes back into the
+// previous tile) emits exactly one output byte per input byte, so its summary needs no scans.
 __global__ void __launch_bounds__(RT_THREADS) k_rle_summary(const u8* __restrict__ in, u64 N, TileSum* __restrict__ sums) {
   __shared__ TileScratch sc;
-  TileView v;
+  __shared__ u32 lastw[RT_THREADS];
   const u64 t = blockIdx.x;
   const u64 tstart = t * RLE_TILE;
+  const u32 tid = threadIdx.x;
+  const u64 remain = N - tstart;
+  const u32 len = remain < RLE_TILE ? (u32)remain : RLE_TILE;
+  const u8* p = in + tstart + tid * RT_PER;
+  if (len == RLE_TILE && ((((size_t)in) + tstart) & 15) == 0) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    lastw[tid] = q.w;
+    __syncthreads();
+    u32 prevw;  // the 4 bytes before this thread's 16 (only 3 are used)
+    if (tid) prevw = lastw[tid - 1];
+    else if (tstart >= 4) prevw = ((u32)in[tstart - 1] << 24) | ((u32)in[tstart - 2] << 16) | ((u32)in[tstart - 3] << 8);
+    else {
+      // near the start of the input: bytes that do not exist must not look equal
+      prevw = 0;
+      for (int k = 1; k <= 3; k++) {
+        const u32 b = (tstart >= (u64)k) ? in[tstart - k] : (u32)((u8)(~q.x) + k);
+        prevw |= b << (8 * (4 - k));
+      }
+    }
+    // x_i == x_{i-1} for every byte, via word-wise compare of the stream shifted by one byte
+    const u32 a[5] = {prevw, q.x, q.y, q.z, q.w};
+    u32 any4 = 0;
+#pragma unroll
+    for (int wv = 1; wv < 5; wv++) {
+      const u32 cur = a[wv], sh1 = __funnelshift_l(a[wv - 1], cur, 8);   // bytes shifted by one position
+      const u32 sh2 = __funnelshift_l(a[wv - 1], cur, 16), sh3 = __funnelshift_l(a[wv - 1], cur, 24);
+      const u32 e = __vcmpeq4(cur, sh1) & __vcmpeq4(cur, sh2) & __vcmpeq4(cur, sh3);
+      any4 |= e;
+    }
+    if (!__syncthreads_or(any4 != 0)) {
+      if (tid == 0) {
+        TileSum s;
+        s.fc = in[tstart];
+        s.lc = in[tstart + len - 1];
+        u32 lead = 1;
+        while (lead < 4 && in[tstart + lead] == s.fc) lead++;
+        u32 trail = 1;
+        while (trail < 4 && in[tstart + len - 1 - trail] == s.lc) trail++;
+        s.lead = lead; s.trail = trail; s.allsame = 0; s.rest = len - lead; s.pad = 0;
+        sums[t] = s;
+      }
+      return;
+    }
+  }
+  TileView v;
   tile_view(in, N, tstart, 0, sc, v);
   if (threadIdx.x == 0) {
     TileSum s;
@@ -380,6 +427,16 @@ k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ c
         // largest tile t >= tile(b) with prefix[t] < V
         u64 lo = b / RLE_TILE, hi = ntiles;  // pred(lo) true, pred(hi) false
         {
+          // W grows by ~1 per raw byte on ordinary data: try the tile that linear extrapolation predicts
+          const u64 plo = prefix[lo];
+          u64 tg = lo + ((V - plo) >> 12);
+          if (tg >= ntiles) tg = ntiles - 1;
+          const u64 pg = prefix[tg], pg1 = prefix[tg + 1];
+          if (pg < V && pg1 >= V) { lo = tg; hi = tg + 1; }
+          else if (pg < V) lo = tg;
+          else if (tg > lo) hi = tg;
+        }
+        if (hi - lo > 1) {
           // narrow with a guess window first (typical data: about BS raw bytes per block)
           const u64 a = ((BS - ofs) * 4 / 5) / RLE_TILE;
           const u64 g0 = lo + (a > 1 ? a - 1 : 0);

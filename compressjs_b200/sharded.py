@@ -19,9 +19,20 @@ with the gloo backend in the unit tests (tests/test_sharded_host.py), where the 
 is injected.
 """
 import ctypes as C
+import time
 
 import torch
 import torch.distributed as dist
+
+PHASES = {}   # wall-clock milliseconds of the last compress_file_sharded call per phase (rank local)
+
+
+def _tick(name, t0):
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    PHASES[name] = PHASES.get(name, 0.0) + (t1 - t0) * 1e3
+    return t1
 
 SQRTPI = 0x177245385090
 
@@ -116,7 +127,9 @@ def compress_sharded(encode_range, nblocks, level, device, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     first, count = block_range(nblocks, rank, world)
+    t0 = time.perf_counter()
     frag, nbits, crcs = encode_range(first, count)
+    t0 = _tick("encode_range", t0)
     if world == 1:
         return assemble(level, [frag], [nbits], [crcs], device)
     # 2. everybody learns every fragment's size
@@ -127,7 +140,9 @@ def compress_sharded(encode_range, nblocks, level, device, group=None):
     counts = [int(v[1]) for v in allv]
     off = 32 + sum(bits[:rank])
     phase = off % 8
+    t0 = _tick("allgather_sizes", t0)
     shifted = shift_right_bits(frag, nbits, phase)
+    t0 = _tick("shift", t0)
     # 3. gather the (padded) byte fragments and the block CRCs on rank 0
     maxlen = max((32 + sum(bits[:r])) % 8 + bits[r] + 7 for r in range(world)) // 8 + 1
     maxcnt = max(counts + [1])
@@ -139,12 +154,18 @@ def compress_sharded(encode_range, nblocks, level, device, group=None):
     if rank == 0:
         glist = [torch.empty(maxlen, dtype=torch.uint8, device=device) for _ in range(world)]
         clist = [torch.zeros(maxcnt, dtype=torch.int64, device=device) for _ in range(world)]
+        t0 = _tick("pad_alloc", t0)
         dist.gather(pad, glist, dst=0, group=group)
         dist.gather(crct, clist, dst=0, group=group)
+        t0 = _tick("nccl_gather", t0)
         crcs_per_rank = [clist[r][: counts[r]].tolist() for r in range(world)]
-        return assemble(level, glist, bits, crcs_per_rank, device)
+        out = assemble(level, glist, bits, crcs_per_rank, device)
+        _tick("assemble", t0)
+        return out
+    t0 = _tick("pad_alloc", t0)
     dist.gather(pad, None, dst=0, group=group)
     dist.gather(crct, None, dst=0, group=group)
+    _tick("nccl_gather", t0)
     return None
 
 
@@ -211,6 +232,8 @@ def compress_file_sharded(d_in, level=9, group=None):
     if world == 1:
         enc, nblocks = gpu_encode_range_fn(d_in, level)
         return compress_sharded(enc, nblocks, level, d_in.device, group)
+    PHASES.clear()
+    t0 = time.perf_counter()
     info = (C.c_uint64 * 6)()
     rc = L.b2_bzip2_plan_spec(d_in.data_ptr(), n, level, rank, world, info)
     if rc:
@@ -219,6 +242,7 @@ def compress_file_sharded(d_in, level=9, group=None):
     allv = [torch.zeros(6, dtype=torch.int64, device=d_in.device) for _ in range(world)]
     dist.all_gather(allv, mine, group=group)
     infos = [tuple(int(x) for x in v.tolist()) for v in allv]
+    _tick("plan_spec+verify", t0)
     if spec_plan_ok(infos, n):
         enc = _range_encoder(L, d_in, n, level)
         first, count = infos[rank][2], infos[rank][3]
