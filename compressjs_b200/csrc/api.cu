@@ -17,6 +17,9 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
                            std::vector<u32>* crcs_out, size_t* total_blocks, long long spec_first = -2, size_t spec_count = 0,
                            u64* spec_range = nullptr);
 void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst);
+void dec_shard_open(Ctx& c, const u8* d_in, size_t n, int rank, int world, u64* info);
+void dec_shard_export(u64* buf);
+int dec_shard_finish(Ctx& c, const u64* all, int multistream, u8* d_out, size_t out_cap, u64* res);
 int bzip2_decompress_device(Ctx& c, const u8* d_in, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n,
                             bool single_block, u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len,
                             u8** d_out_alloc);
@@ -292,6 +295,30 @@ int b2_bzip2_plan(const void* d_in, size_t n, int level, size_t* total_blocks) {
     bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, total_blocks);
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     return 0;
+  });
+}
+
+int b2_dec_shard_open(const void* d_in, size_t n, int rank, int world, uint64_t* info) {
+  return guarded([&]() {
+    if (world < 1 || rank < 0 || rank >= world) throw B2Error{B2_ERR_BAD_ARG, "bad rank/world"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    {
+      StageScope tot(c, ST_TOTAL);
+      dec_shard_open(c, (const u8*)d_in, n, rank, world, info);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.collect();
+    return 0;
+  });
+}
+int b2_dec_shard_export(uint64_t* buf) {
+  return guarded([&]() { dec_shard_export(buf); return 0; });
+}
+int b2_dec_shard_finish(const uint64_t* all, int multistream, void* d_out, size_t out_cap, uint64_t* res) {
+  return guarded([&]() {
+    Ctx& c = ctx_locked();
+    return dec_shard_finish(c, all, multistream, (u8*)d_out, out_cap, res);
   });
 }
 

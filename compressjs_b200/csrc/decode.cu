@@ -793,25 +793,49 @@ static std::string hexs(u32 v) {
 
 struct Event { int kind; size_t cand; u32 a, b; int code; std::string msg; };  // kind: 0 block, 1 eos, 2 error
 
-int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n, bool single_block,
-                            u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len, u8** d_out_alloc) {
-  *out_n = 0;
-  if (d_out_alloc) *d_out_alloc = nullptr;
+// One decode in flight.  open() parses the header, finds every block candidate and decodes the share
+// [lo, hi) of them (all of them on one GPU); finish() walks the chain over ALL candidates' results
+// (imported from the other ranks when sharded), expands + CRC-checks the blocks of the own share and
+// raises the reference's errors in stream order.
+struct DecSession {
+  Ctx* c = nullptr;
+  size_t n = 0;
+  u32 dbuf_size = 0;
+  DBuf<u8> din;
+  std::vector<Cand> cands;         // every magic found, sorted by position
+  std::vector<size_t> blk_idx;     // block candidates (index into cands)
+  std::vector<Cand> bc;            // the same as Cand records
+  std::vector<CandRes> hres;       // per block candidate (valid for [lo,hi) after open, for all after import)
+  size_t lo = 0, hi = 0;           // own share of the block candidates
+  bool single = false, eos_single = false;
+  DBuf<Cand> dcand;
+  DBuf<CandRes> dres;              // own share only
+  DBuf<u8> rle, cls;
+  DBuf<u32> tileoff;
+  int err_event = -1;              // index of the first failing event (sharded mode)
+};
+
+static const u32 UR_TPS = SEG_SIZE / UR_TILE;
+
+static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool single_block, u64 bitpos, int rank, int world) {
+  S.c = &c; S.n = n; S.single = single_block;
   // padded private copy of the input (aligned word reads past the end must be safe)
-  DBuf<u8> din(c, n + 32);
-  CUDA_CHECK(cudaMemsetAsync(din.p + (n & ~(size_t)3), 0, (n + 32) - (n & ~(size_t)3), c.stream));
-  if (n) CUDA_CHECK(cudaMemcpyAsync(din, d_in_user, n, cudaMemcpyDeviceToDevice, c.stream));
+  S.din.alloc(c, n + 32);
+  CUDA_CHECK(cudaMemsetAsync(S.din.p + (n & ~(size_t)3), 0, (n + 32) - (n & ~(size_t)3), c.stream));
+  if (n) CUDA_CHECK(cudaMemcpyAsync(S.din, d_in_user, n, cudaMemcpyDeviceToDevice, c.stream));
   u8 hdr[4] = {0, 0, 0, 0};
-  if (n >= 4) CUDA_CHECK(cudaMemcpyAsync(hdr, din, 4, cudaMemcpyDeviceToHost, c.stream));
+  if (n >= 4) CUDA_CHECK(cudaMemcpyAsync(hdr, S.din, 4, cudaMemcpyDeviceToHost, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
   // lib/Bzip2.js:105-124 _start_bunzip
   if (n < 4 || hdr[0] != 'B' || hdr[1] != 'Z' || hdr[2] != 'h') throw B2Error{DEC_NOT_BZIP, "Not bzip data: bad magic"};
   int level = hdr[3] - 0x30;
   if (level < 1 || level > 9) throw B2Error{DEC_NOT_BZIP, "Not bzip data: level out of range"};
-  u32 dbuf_size = 100000u * (u32)level;
+  S.dbuf_size = 100000u * (u32)level;
+  const u32 dbuf_size = S.dbuf_size;
+  const u8* din = S.din;
 
   // ---- 1. candidates ----
-  std::vector<Cand> cands;
+  std::vector<Cand>& cands = S.cands;
   {
     StageScope ss(c, ST_SCAN);
     const u32 cap = (u32)(n / 8000 + 1024);
@@ -829,32 +853,39 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.pos < b.pos; });
   }
-  // block candidates that are decoded
-  std::vector<size_t> blk_idx;  // index into cands
+  std::vector<size_t>& blk_idx = S.blk_idx;
   if (single_block) {
     // lib/Bzip2.js:482-503: seekBit(pos) then one _get_next_block
     const Cand* hit = nullptr;
     for (auto& cd : cands) if (cd.pos == bitpos) hit = &cd;
     if (!hit) throw B2Error{DEC_NOT_BZIP, "Not bzip data"};
-    if (hit->type == 2) { *out_n = 0; return 0; }
+    if (hit->type == 2) { S.eos_single = true; return; }
     blk_idx.push_back((size_t)(hit - cands.data()));
   } else {
     for (size_t i = 0; i < cands.size(); i++) if (cands[i].type == 1) blk_idx.push_back(i);
   }
-  const size_t nb = blk_idx.size();
-  std::vector<Cand> bc(nb);
-  for (size_t i = 0; i < nb; i++) bc[i] = cands[blk_idx[i]];
-  std::vector<CandRes> hres(nb);
-  // persistent per-candidate arrays
-  DBuf<Cand> dcand(c, nb ? nb : 1);
-  DBuf<CandRes> dres(c, nb ? nb : 1);
-  DBuf<u8> rle(c, (nb ? nb : 1) << SEG_SHIFT), cls(c, (nb ? nb : 1) << SEG_SHIFT);
-  const u32 ur_tps = SEG_SIZE / UR_TILE;
-  DBuf<u32> tileoff(c, (nb ? nb : 1) * (size_t)ur_tps);
-  if (nb) CUDA_CHECK(cudaMemcpyAsync(dcand, bc.data(), sizeof(Cand) * nb, cudaMemcpyHostToDevice, c.stream));
+  const size_t nb_all = blk_idx.size();
+  S.bc.resize(nb_all);
+  for (size_t i = 0; i < nb_all; i++) S.bc[i] = cands[blk_idx[i]];
+  S.hres.assign(nb_all, CandRes());
+  for (auto& r : S.hres) { memset(&r, 0, sizeof r); r.status = DEC_DATA_ERROR; }
+  S.lo = (size_t)rank * nb_all / (size_t)world;
+  S.hi = (size_t)(rank + 1) * nb_all / (size_t)world;
+  const size_t nb = S.hi - S.lo;
+  S.dcand.alloc(c, nb_all ? nb_all : 1);
+  S.dres.alloc(c, nb ? nb : 1);
+  S.rle.alloc(c, (nb ? nb : 1) << SEG_SHIFT);
+  S.cls.alloc(c, (nb ? nb : 1) << SEG_SHIFT);
+  S.tileoff.alloc(c, (nb ? nb : 1) * (size_t)UR_TPS);
+  if (nb_all) CUDA_CHECK(cudaMemcpyAsync(S.dcand, S.bc.data(), sizeof(Cand) * nb_all, cudaMemcpyHostToDevice, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  CandRes* hres = S.hres.data() + S.lo;  // own share
+  Cand* dcand = S.dcand.p + S.lo;
+  DBuf<CandRes>& dres = S.dres;
+  DBuf<u8>& rle = S.rle; DBuf<u8>& cls = S.cls; DBuf<u32>& tileoff = S.tileoff;
+  const u32 ur_tps = UR_TPS;
 
-  // ---- 2. decode every candidate block, in batches ----
+  // ---- 2. decode the own share of the candidate blocks, in batches ----
   const u32 DB = std::max(1u, c.bwt_batch);
   static bool attr = false;
   if (!attr) {
@@ -894,7 +925,7 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
         k_unmtf_b<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, lists, starts, tt);
         KLAUNCH(c); KCHECK();
       }
-      CUDA_CHECK(cudaMemcpyAsync(hres.data() + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hres + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
       u32 nmax = 0; u64 ntot = 0;
       for (u32 i = 0; i < cnt; i++) { hn[i] = hres[k0 + i].status == 0 ? hres[k0 + i].n : 0; nmax = std::max(nmax, hn[i]); ntot += hn[i]; }
@@ -931,16 +962,31 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
         k_unrle_scan<<<cnt * ur_tps, UR_THREADS, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), cls.p + (k0 << SEG_SHIFT), rb, ur_tps, ticket, lbst,
                                                                tileoff.p + k0 * ur_tps);
         KLAUNCH(c); KCHECK();
-        CUDA_CHECK(cudaMemcpyAsync(hres.data() + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
+        CUDA_CHECK(cudaMemcpyAsync(hres + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
       }
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
       c.stats.blocks += cnt;
     }
   }
 
+}
+
+// fills *first_err (event index, or -1) instead of throwing when `sharded`
+static int dec_finish(Ctx& c, DecSession& S, int multistream, u8* d_out, size_t out_cap, size_t* out_n, std::vector<u64>* tab_pos,
+                      std::vector<u32>* tab_len, u8** d_out_alloc, bool sharded, u64* shard_info) {
+  *out_n = 0;
+  if (d_out_alloc) *d_out_alloc = nullptr;
+  if (S.eos_single) return 0;
+  const size_t n = S.n;
+  const size_t nb_all = S.blk_idx.size();
+  std::vector<Cand>& cands = S.cands;
+  std::vector<Cand>& bc = S.bc;
+  std::vector<CandRes>& hres = S.hres;
+  const u32 dbuf_size = S.dbuf_size;
+  const u32 ur_tps = UR_TPS;
   // ---- 3. walk the chain in stream order (lib/Bzip2.js:454-481 / 508-548) ----
   std::vector<Event> events;
-  std::vector<u64> outbase(nb ? nb : 1, ~0ull);
+  std::vector<u64> outbase(nb_all ? nb_all : 1, ~0ull);
   u64 total_out = 0;
   auto find_cand = [&](u64 pos) -> long {
     size_t lo = 0, hi = cands.size();
@@ -948,7 +994,7 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
     return (lo < cands.size() && cands[lo].pos == pos) ? (long)lo : -1;
   };
   std::vector<long> cand_to_blk(cands.size(), -1);
-  for (size_t i = 0; i < nb; i++) cand_to_blk[blk_idx[i]] = (long)i;
+  for (size_t i = 0; i < nb_all; i++) cand_to_blk[S.blk_idx[i]] = (long)i;
   auto block_event = [&](size_t bi) -> bool {  // returns false when the walk must stop (error recorded)
     const CandRes& r = hres[bi];
     if (r.status != 0) {
@@ -962,7 +1008,7 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
     events.push_back({0, bi, 0, 0, 0, ""});
     return true;
   };
-  if (single_block) {
+  if (S.single) {
     block_event(0);
   } else {
     u64 pos = 32;
@@ -984,7 +1030,7 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
           // _start_bunzip on the byte stream (resyncs to the next byte)
           u8 h2[4] = {0, 0, 0, 0};
           const size_t avail = (size_t)std::min<u64>(4, n - bytepos);
-          CUDA_CHECK(cudaMemcpyAsync(h2, din.p + bytepos, avail, cudaMemcpyDeviceToHost, c.stream));
+          CUDA_CHECK(cudaMemcpyAsync(h2, S.din.p + bytepos, avail, cudaMemcpyDeviceToHost, c.stream));
           CUDA_CHECK(cudaStreamSynchronize(c.stream));
           if (avail != 4 || h2[0] != 'B' || h2[1] != 'Z' || h2[2] != 'h') { events.push_back({2, 0, 0, 0, DEC_NOT_BZIP, "Not bzip data: bad magic"}); break; }
           const int lv = h2[3] - 0x30;
@@ -997,27 +1043,40 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
     }
   }
 
-  // ---- 4. expand the chain blocks, CRC them ----
+  // ---- 4. expand the chain blocks of the own share, CRC them ----
+  // own output window: [my_off, my_off + my_len) of the decoded stream
+  u64 my_off = 0, my_len = 0;
+  {
+    bool first = true;
+    for (size_t i = S.lo; i < S.hi; i++)
+      if (outbase[i] != ~0ull) {
+        if (first) { my_off = outbase[i]; first = false; }
+        my_len = outbase[i] + hres[i].rawlen - my_off;
+      }
+  }
+  const size_t nb = S.hi - S.lo;
   u8* dout = d_out;
   DBuf<u8> own;
   if (!d_out) {
-    own.alloc(c, total_out ? total_out : 1);
+    own.alloc(c, my_len ? my_len : 1);
     dout = own.p;
-  } else if (total_out > out_cap) {
-    *out_n = (size_t)total_out;
+  } else if (my_len > out_cap) {
+    *out_n = (size_t)my_len;
     throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
   }
   std::vector<u32> got_crc(nb ? nb : 1, 0);
   if (nb) {
     StageScope ss(c, ST_UNRLE);
+    std::vector<u64> ob(nb);
+    for (size_t i = 0; i < nb; i++) ob[i] = outbase[S.lo + i] == ~0ull ? ~0ull : outbase[S.lo + i] - my_off;
     DBuf<u64> dob(c, nb);
-    CUDA_CHECK(cudaMemcpyAsync(dob, outbase.data(), 8 * nb, cudaMemcpyHostToDevice, c.stream));
-    k_unrle_emit<<<(unsigned)(nb * ur_tps), UR_THREADS, 0, c.stream>>>(rle, cls, dres, ur_tps, tileoff, dob, dout);
+    CUDA_CHECK(cudaMemcpyAsync(dob, ob.data(), 8 * nb, cudaMemcpyHostToDevice, c.stream));
+    k_unrle_emit<<<(unsigned)(nb * ur_tps), UR_THREADS, 0, c.stream>>>(S.rle, S.cls, S.dres, ur_tps, S.tileoff, dob, dout);
     KLAUNCH(c); KCHECK();
     std::vector<BlkInfo> ranges(nb);
     for (size_t i = 0; i < nb; i++) {
       memset(&ranges[i], 0, sizeof(BlkInfo));
-      if (outbase[i] != ~0ull) { ranges[i].s = outbase[i]; ranges[i].e = outbase[i] + hres[i].rawlen; }
+      if (ob[i] != ~0ull) { ranges[i].s = ob[i]; ranges[i].e = ob[i] + hres[S.lo + i].rawlen; }
     }
     DBuf<BlkInfo> dr(c, nb);
     DBuf<u32> dcrc(c, nb);
@@ -1027,18 +1086,68 @@ int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistre
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
   }
   // ---- 5. replay the events: first failure in stream order wins ----
-  for (auto& ev : events) {
+  S.err_event = -1;
+  int err_code = 0;
+  std::string err_msg;
+  for (size_t ei = 0; ei < events.size() && S.err_event < 0; ei++) {
+    const Event& ev = events[ei];
     if (ev.kind == 0) {
-      const u32 want = bc[ev.cand].next32, got = got_crc[ev.cand];
-      if (want != got) throw B2Error{DEC_DATA_ERROR, "Data error: Bad block CRC (got " + hexs(got) + " expected " + hexs(want) + ")"};
-      if (tab_pos) { tab_pos->push_back(bc[ev.cand].pos); tab_len->push_back(hres[ev.cand].rawlen); }
+      if (ev.cand >= S.lo && ev.cand < S.hi) {  // CRCs of foreign blocks are checked by their owners
+        const u32 want = bc[ev.cand].next32, got = got_crc[ev.cand - S.lo];
+        if (want != got) { S.err_event = (int)ei; err_code = DEC_DATA_ERROR; err_msg = "Data error: Bad block CRC (got " + hexs(got) + " expected " + hexs(want) + ")"; }
+      }
+      if (S.err_event < 0 && tab_pos) { tab_pos->push_back(bc[ev.cand].pos); tab_len->push_back(hres[ev.cand].rawlen); }
     } else if (ev.kind == 1) {
-      if (!tab_pos && ev.a != ev.b) throw B2Error{DEC_DATA_ERROR, "Data error: Bad stream CRC (got " + hexs(ev.a) + " expected " + hexs(ev.b) + ")"};
+      if (!tab_pos && ev.a != ev.b) { S.err_event = (int)ei; err_code = DEC_DATA_ERROR; err_msg = "Data error: Bad stream CRC (got " + hexs(ev.a) + " expected " + hexs(ev.b) + ")"; }
     } else {
-      throw B2Error{ev.code, ev.msg};
+      S.err_event = (int)ei; err_code = ev.code; err_msg = ev.msg;
     }
   }
-  *out_n = (size_t)total_out;
+  if (shard_info) { shard_info[0] = my_off; shard_info[1] = my_len; shard_info[2] = total_out; shard_info[3] = (u64)(long long)S.err_event; shard_info[4] = (u64)(long long)err_code; }
+  if (S.err_event >= 0) {
+    if (!sharded) throw B2Error{err_code, err_msg};
+    throw B2Error{err_code, err_msg};  // the caller (sharded) compares shard_info[3] across ranks and keeps the earliest
+  }
+  *out_n = (size_t)my_len;
   if (!d_out && d_out_alloc) { *d_out_alloc = own.p; own.p = nullptr; }
   return 0;
+}
+
+int bzip2_decompress_device(Ctx& c, const u8* d_in_user, size_t n, int multistream, u8* d_out, size_t out_cap, size_t* out_n, bool single_block,
+                            u64 bitpos, std::vector<u64>* tab_pos, std::vector<u32>* tab_len, u8** d_out_alloc) {
+  *out_n = 0;
+  if (d_out_alloc) *d_out_alloc = nullptr;
+  DecSession S;
+  dec_open(c, S, d_in_user, n, single_block, bitpos, 0, 1);
+  return dec_finish(c, S, multistream, d_out, out_cap, out_n, tab_pos, tab_len, d_out_alloc, false, nullptr);
+}
+
+// ---- sharded decode: open on every rank, exchange results, finish ------------
+static DecSession* g_shard = nullptr;
+void dec_shard_open(Ctx& c, const u8* d_in, size_t n, int rank, int world, u64* info) {
+  delete g_shard;
+  g_shard = new DecSession();
+  dec_open(c, *g_shard, d_in, n, false, 0, rank, world);
+  info[0] = g_shard->blk_idx.size(); info[1] = g_shard->lo; info[2] = g_shard->hi;
+}
+void dec_shard_export(u64* buf) {
+  if (!g_shard) throw B2Error{B2_ERR_BAD_ARG, "no sharded decode in flight"};
+  for (size_t i = g_shard->lo; i < g_shard->hi; i++) {
+    const CandRes& r = g_shard->hres[i];
+    u64* o = buf + (i - g_shard->lo) * 6;
+    o[0] = (u64)(long long)r.status; o[1] = r.detail; o[2] = r.endbit; o[3] = r.n; o[4] = r.rawlen; o[5] = 0;
+  }
+}
+int dec_shard_finish(Ctx& c, const u64* all, int multistream, u8* d_out, size_t out_cap, u64* res) {
+  if (!g_shard) throw B2Error{B2_ERR_BAD_ARG, "no sharded decode in flight"};
+  DecSession& S = *g_shard;
+  for (size_t i = 0; i < S.hres.size(); i++) {
+    if (i >= S.lo && i < S.hi) continue;
+    const u64* o = all + i * 6;
+    CandRes& r = S.hres[i];
+    r.status = (int)(long long)o[0]; r.detail = (u32)o[1]; r.endbit = o[2]; r.n = (u32)o[3]; r.rawlen = (u32)o[4];
+  }
+  size_t out_n = 0;
+  struct Closer { ~Closer() { delete g_shard; g_shard = nullptr; } } closer;
+  return dec_finish(c, S, multistream, d_out, out_cap, &out_n, nullptr, nullptr, nullptr, true, res);
 }

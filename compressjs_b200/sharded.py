@@ -249,3 +249,93 @@ def compress_file_sharded(d_in, level=9, group=None):
         return compress_sharded(lambda f, c: enc(first, count), infos[0][5], level, d_in.device, group)
     enc, nblocks = gpu_encode_range_fn(d_in, level)
     return compress_sharded(enc, nblocks, level, d_in.device, group)
+
+
+# ---- sharded decode -------------------------------------------------------------------------------
+def decode_shard_rows(L, d_in, rank, world):
+    """Stage 1 on one rank: returns (info, rows) -- rows = int64 tensor [own candidates, 6] on the CPU."""
+    from . import _native
+    info = (C.c_uint64 * 3)()
+    rc = L.b2_dec_shard_open(d_in.data_ptr(), d_in.numel(), rank, world, info)
+    if rc:
+        raise RuntimeError("b2_dec_shard_open: %s (code %d)" % (_native.last_error(), rc))
+    total, lo, hi = int(info[0]), int(info[1]), int(info[2])
+    buf = (C.c_uint64 * (6 * max(hi - lo, 1)))()
+    rc = L.b2_dec_shard_export(buf)
+    if rc:
+        raise RuntimeError("b2_dec_shard_export: " + _native.last_error())
+    rows = torch.tensor([int(v) if int(v) < 2 ** 63 else int(v) - 2 ** 64 for v in buf[: 6 * (hi - lo)]], dtype=torch.int64).reshape(-1, 6)
+    return (total, lo, hi), rows
+
+
+def decode_shard_finish(L, all_rows, multistream, device):
+    """Stage 2 on one rank: all_rows = [total candidates, 6] int64 (CPU).  Returns (own output tensor, res)."""
+    from . import _native
+    flat = [int(v) & (2 ** 64 - 1) for v in all_rows.reshape(-1).tolist()]
+    arr = (C.c_uint64 * max(len(flat), 1))(*flat)
+    res = (C.c_uint64 * 5)()
+    need = 0
+    for r in all_rows.tolist():
+        need += r[4] if r[0] == 0 else 0
+    out = torch.empty(max(need, 1), dtype=torch.uint8, device=device)   # upper bound: everything decodable
+    rc = L.b2_dec_shard_finish(arr, int(bool(multistream)), out.data_ptr(), out.numel(), res)
+    vals = [int(v) for v in res]
+    err_idx = vals[3] if vals[3] < 2 ** 63 else vals[3] - 2 ** 64
+    err_code = vals[4] if vals[4] < 2 ** 63 else vals[4] - 2 ** 64
+    msg = _native.last_error() if rc else ""
+    return out[: vals[1]] if rc == 0 else None, dict(off=vals[0], len=vals[1], total=vals[2], err_idx=err_idx if rc else -1,
+                                                      err_code=err_code if rc else 0, msg=msg)
+
+
+def decompress_file_sharded(d_in, multistream=False, group=None):
+    """Decode a .bz2 stream held on every rank; the decoded bytes are gathered on rank 0 (uint8 tensor)."""
+    from . import _native
+    from .bzip2 import Bzip2Error
+    L = _native.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    device = d_in.device
+    (total, lo, hi), rows = decode_shard_rows(L, d_in, rank, world)
+    if world > 1:
+        per = max((r + 1) * total // world - r * total // world for r in range(world))
+        pad = torch.zeros((max(per, 1), 6), dtype=torch.int64, device=device)
+        if hi > lo:
+            pad[: hi - lo] = rows.to(device)
+        allp = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(allp, pad, group=group)
+        parts = []
+        for r in range(world):
+            cnt = (r + 1) * total // world - r * total // world
+            parts.append(allp[r][:cnt].cpu())
+        all_rows = torch.cat(parts) if parts else rows
+    else:
+        all_rows = rows
+    out, res = decode_shard_finish(L, all_rows, multistream, device)
+    # earliest failing event over all ranks wins (every rank sees the same event list)
+    mine = torch.tensor([res["err_idx"] if res["err_idx"] >= 0 else 2 ** 62, res["err_code"], res["off"], res["len"], res["total"]],
+                        dtype=torch.int64, device=device)
+    if world > 1:
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine, group=group)
+    else:
+        allv = [mine]
+    errs = [(int(v[0]), int(v[1]), r) for r, v in enumerate(allv) if int(v[0]) < 2 ** 62]
+    if errs:
+        idx, code, who = min(errs)
+        raise Bzip2Error(code, res["msg"] if who == rank else "Data error")
+    if world == 1:
+        return out
+    # gather the shards on rank 0
+    maxlen = max(int(v[3]) for v in allv)
+    padb = torch.empty(max(maxlen, 1), dtype=torch.uint8, device=device)
+    padb[: out.numel()] = out
+    if rank == 0:
+        glist = [torch.empty_like(padb) for _ in range(world)]
+        dist.gather(padb, glist, dst=0, group=group)
+        full = torch.empty(int(allv[0][4]), dtype=torch.uint8, device=device)
+        for r in range(world):
+            o, ln = int(allv[r][2]), int(allv[r][3])
+            full[o: o + ln] = glist[r][:ln]
+        return full
+    dist.gather(padb, None, dst=0, group=group)
+    return None

@@ -92,6 +92,17 @@ int b2_bitshift_dev(const void* d_src, uint64_t nbits, int phase, void* d_dst);
 int b2_bzip2_encode_range_dev(const void* d_in, size_t n, int level, size_t first, size_t count, int bit_phase,
                               void* d_out, size_t out_cap, uint64_t* out_bits, uint32_t* block_crcs);
 
+/* ---- sharded decode (BASELINE config 5) ----------------------------------- */
+/* Every rank holds the compressed stream.  open: scan the magics and decode this rank's share of the
+ * candidate blocks; info = {block candidates in the file, first, one-past-last of the own share}.
+ * export: 6 x uint64 per own candidate (status, detail, end bit, block length, decoded length, 0).
+ * finish: `all` = the exported rows of ALL candidates in order (all-gathered by the caller); walks the
+ * block chain, expands and CRC-checks the own blocks into d_out; res = {offset of the own output in the
+ * decoded stream, its length, total decoded length, index of the first failing event or -1, its code}. */
+int b2_dec_shard_open(const void* d_in, size_t n, int rank, int world, uint64_t* info);
+int b2_dec_shard_export(uint64_t* buf);
+int b2_dec_shard_finish(const uint64_t* all, int multistream, void* d_out, size_t out_cap, uint64_t* res);
+
 /* ---- instrumentation -------------------------------------------------------------- */
 typedef struct b2_stats {
   /* GPU milliseconds of the last call, from CUDA events on the library's stream */

@@ -65,3 +65,37 @@ def test_speculative_range_plan_chains_or_is_rejected(kind):
             acc += bits[r]
         out = S.assemble(level, sh, bits, crcs, d_in.device)
         assert bytes(out.cpu().numpy().tobytes()) == exp
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_sharded_decode_stages(world):
+    """b2_dec_shard_open/export/finish with simulated ranks: the per-rank outputs concatenate to the input."""
+    import bz2
+    from compressjs_b200 import sharded as S, _native
+    L = _native.lib()
+    data = T.texty(7 * 99981 + 321, 41)
+    z = bz2.compress(data, 1)
+    d_in = torch.frombuffer(bytearray(z), dtype=torch.uint8).cuda()
+    # every simulated rank needs its own session: stage 1 rows first (sessions are one at a time, so redo stage 1 per rank)
+    rows_all = []
+    for r in range(world):
+        (total, lo, hi), rows = S.decode_shard_rows(L, d_in, r, world)
+        rows_all.append(rows)
+    all_rows = torch.cat(rows_all)
+    assert all_rows.shape[0] == total
+    out = bytearray(len(data))
+    for r in range(world):
+        S.decode_shard_rows(L, d_in, r, world)  # reopen this rank's session
+        o, res = S.decode_shard_finish(L, all_rows, False, d_in.device)
+        assert o is not None, res
+        assert res["total"] == len(data)
+        out[res["off"]: res["off"] + res["len"]] = bytes(o.cpu().numpy().tobytes())
+    assert bytes(out) == data
+
+
+def test_sharded_decode_single_process_api():
+    import bz2
+    from compressjs_b200 import sharded as S
+    data = T.ascii_random(3 * 99981 + 77, 42)
+    d_in = torch.frombuffer(bytearray(bz2.compress(data, 1)), dtype=torch.uint8).cuda()
+    assert bytes(S.decompress_file_sharded(d_in).cpu().numpy().tobytes()) == data
