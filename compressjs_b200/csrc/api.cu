@@ -74,6 +74,8 @@ static Ctx& ctx_locked() {
     CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     const char* b = getenv("B2_BWT_BATCH");
     if (b && atoi(b) > 0) c->bwt_batch = (u32)atoi(b);
+    const char* w8 = getenv("B2_BWT_PREFIX8");
+    if (w8 && *w8) { c->bwt_wide_forced = true; c->bwt_wide = atoi(w8) != 0; }
     g_ctx = c;
   } else {
     CUDA_CHECK(cudaSetDevice(g_ctx->device));

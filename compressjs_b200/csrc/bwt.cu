@@ -28,7 +28,7 @@
 #define BK_THREADS 256
 #define BK_ITEMS 16
 __global__ void __launch_bounds__(BK_THREADS)
-k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u64* __restrict__ rec, u32* __restrict__ hist) {
+k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u64* __restrict__ rec, u32* __restrict__ hist, u32 koff) {
   __shared__ u32 h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -42,16 +42,68 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
   for (int k = 0; k < BK_ITEMS; k++) {
     const u32 i = start + k * BK_THREADS + threadIdx.x;
     if (i < n) {
-      u32 i1 = i + 1; if (i1 >= n) i1 -= n;
+      u32 i0 = i + koff; if (i0 >= n) i0 %= n;
+      u32 i1 = i0 + 1; if (i1 >= n) i1 -= n;
       u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
       u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
-      const u32 c0 = t[i];
+      const u32 c0 = t[i0];
       ko[i] = ((u64)((c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3]) << 32) | ((b << SEG_SHIFT) | i);
       atomicAdd(&h[c0], 1u);
     }
   }
   __syncthreads();
   if (h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(BK_THREADS) k_byte_hist(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ hist) {
+  __shared__ u32 h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 b = blockIdx.x / tps, lt = blockIdx.x % tps;
+  const u32 n = seg_n[b];
+  const u32 start = lt * (BK_THREADS * BK_ITEMS);
+  if (start >= n) return;
+  const u8* t = T + ((size_t)b << SEG_SHIFT);
+  for (int k = 0; k < BK_ITEMS; k++) {
+    const u32 i = start + k * BK_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[t[i]], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
+}
+// four bytes of block text starting at (i + off) mod n, big endian
+__device__ __forceinline__ u32 word_at(const u8* __restrict__ t, u32 n, u32 i, u32 off) {
+  u32 i0 = i + off; if (i0 >= n) i0 %= n;
+  u32 i1 = i0 + 1; if (i1 >= n) i1 -= n;
+  u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
+  u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
+  return ((u32)t[i0] << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3];
+}
+// 8-byte mode, between the two 4-pass sorts: the records are ordered by bytes 4..7; re-key them with
+// bytes 0..3 (the stable second sort then yields the order by the first 8 bytes).
+__global__ void k_rekey(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 nslots, u64* __restrict__ rec) {
+  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nslots) return;
+  const u32 b = g >> SEG_SHIFT, n = seg_n[b];
+  if ((g & SEG_MASK) >= n) return;
+  const u32 idx = (u32)rec[g];
+  rec[g] = ((u64)word_at(T + ((size_t)b << SEG_SHIFT), n, idx & SEG_MASK, 0) << 32) | idx;
+}
+// text-likeness of a batch from its byte histograms: expected number of 4-byte-prefix collisions per
+// suffix, n * (sum p_c^2)^4, averaged over the blocks (0.01 for uniform ASCII, >> 1 for text)
+__global__ void k_text_score(const u32* __restrict__ hist, const u32* __restrict__ seg_n, u32 nblk, float* __restrict__ score) {
+  __shared__ float acc[256];
+  float a = 0.f;
+  for (u32 b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const float n = (float)seg_n[b];
+    if (n < 1.f) continue;
+    float s2 = 0.f;
+    for (u32 c = 0; c < 256; c++) { const float p = (float)hist[b * 256 + c] / n; s2 += p * p; }
+    a += n * s2 * s2 * s2 * s2;
+  }
+  acc[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (u32 i = 0; i < blockDim.x; i++) t += acc[i]; *score = t / (float)nblk; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -178,13 +230,15 @@ k_rerank(const u32* __restrict__ key32, const u64* __restrict__ key64, const u32
 // 32-bit keys staged in padded shared memory (conflict-free blocked reads).  Group head chain per
 // block, compaction offsets as one flat chain over all tiles.
 #define RI_PAD(j) ((j) + ((j) >> 5))
+template <bool WIDE>
 __global__ void __launch_bounds__(RR_THREADS)
-k_rerank_init(const u64* __restrict__ rec, u32* __restrict__ SA, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ rank,
+k_rerank_init(const u64* __restrict__ rec, const u8* __restrict__ T, u32* __restrict__ SA, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ rank,
               u32* __restrict__ next_head, u32* __restrict__ next_idx, u32* next_count, u32* ticket, u64* st_new, u64* st_cnt, u32 ntiles) {
   __shared__ u32 sk[RR_TILE + RR_TILE / 32 + 2];
   __shared__ u32 sg[RR_TILE + RR_TILE / 32 + 2];
+  __shared__ u32 s2[WIDE ? RR_TILE + RR_TILE / 32 + 2 : 1];   // bytes 4..7 of every suffix (8-byte mode)
   __shared__ u32 ws[RR_THREADS / 32 + 1];
-  __shared__ u32 s_tile, s_cn, s_cc, s_prev, s_next;
+  __shared__ u32 s_tile, s_cn, s_cc, s_prev, s_next, s_prev2, s_next2;
   const u32 tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
@@ -199,10 +253,15 @@ k_rerank_init(const u64* __restrict__ rec, u32* __restrict__ SA, const u32* __re
     sk[RI_PAD(j)] = (u32)(rv >> 32);
     sg[RI_PAD(j)] = (u32)rv;
     SA[base + j] = (u32)rv;
+    if (WIDE) s2[RI_PAD(j)] = word_at(T + ((size_t)b << SEG_SHIFT), n, (u32)rv & SEG_MASK, 4);
   }
   if (tid == 0 && cnt) {
     s_prev = start ? (u32)(rec[base - 1] >> 32) : 0u;
     s_next = (start + cnt < n) ? (u32)(rec[base + cnt] >> 32) : 0u;
+    if (WIDE) {
+      s_prev2 = start ? word_at(T + ((size_t)b << SEG_SHIFT), n, (u32)rec[base - 1] & SEG_MASK, 4) : 0u;
+      s_next2 = (start + cnt < n) ? word_at(T + ((size_t)b << SEG_SHIFT), n, (u32)rec[base + cnt] & SEG_MASK, 4) : 0u;
+    }
   }
   __syncthreads();
   u32 vn[RR_ITEMS], nc[RR_ITEMS];
@@ -215,10 +274,16 @@ k_rerank_init(const u64* __restrict__ rec, u32* __restrict__ SA, const u32* __re
       const u32 k = sk[RI_PAD(p)];
       const bool hasprev = p > 0 || start > 0;
       const u32 kp = p > 0 ? sk[RI_PAD(p - 1)] : s_prev;
-      const bool nh = !hasprev || kp != k;
       const bool hasnext = (p + 1 < cnt) || (start + cnt < n);
       const u32 kn = (p + 1 < cnt) ? sk[RI_PAD(p + 1)] : s_next;
-      const bool single = nh && (!hasnext || kn != k);
+      bool eqp = kp == k, eqn = kn == k;
+      if (WIDE) {
+        const u32 k2 = s2[RI_PAD(p)];
+        eqp = eqp && (p > 0 ? s2[RI_PAD(p - 1)] : s_prev2) == k2;
+        eqn = eqn && ((p + 1 < cnt) ? s2[RI_PAD(p + 1)] : s_next2) == k2;
+      }
+      const bool nh = !hasprev || !eqp;
+      const bool single = nh && (!hasnext || !eqn);
       vn[j] = nh ? start + p + 1 : 0u;
       nc[j] = single ? 0u : 1u;
       mn = max(mn, vn[j]); cs += nc[j];
@@ -301,11 +366,40 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   DBuf<u32> bytehist(c, (size_t)nblk * 256);
   CUDA_CHECK(cudaMemsetAsync(bytehist, 0, (size_t)nblk * 256 * 4, c.stream));
   const u32 bk_tps = (n_max + BK_THREADS * BK_ITEMS - 1) / (BK_THREADS * BK_ITEMS);
-  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist);
+  // Text-like batches (many 4-byte-prefix collisions) sort on the first EIGHT bytes before the doubling
+  // rounds start: bytes 4..7 first, then a stable sort on bytes 0..3 -- two cheap keys-only sorts replace
+  // the h=4 round over nearly all suffixes.  The mode of a batch follows the score of the previous batch
+  // of the same call (first batch: 4-byte mode unless B2_BWT_PREFIX8=1), so no extra host sync is needed.
+  if (!c.bwt_wide_forced && !c.bwt_mode_known) {
+    // first batch of a call: decide from the byte histogram (one cheap extra pass over the text + one small sync)
+    DBuf<u32> h0(c, (size_t)nblk * 256);
+    DBuf<float> sc0(c, 1);
+    CUDA_CHECK(cudaMemsetAsync(h0, 0, (size_t)nblk * 256 * 4, c.stream));
+    k_byte_hist<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, h0);
+    KLAUNCH(c); KCHECK();
+    k_text_score<<<1, 256, 0, c.stream>>>(h0, d_n, nblk, sc0);
+    KLAUNCH(c); KCHECK();
+    float sc = 0.f;
+    CUDA_CHECK(cudaMemcpyAsync(&sc, sc0, 4, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.bwt_wide = sc > 0.5f;
+    c.bwt_mode_known = true;
+  }
+  bool wide = c.bwt_wide;
+  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist, wide ? 4u : 0u);
   KLAUNCH(c); KCHECK();
   c.stats.bwt_bytes += n_total * 9;
-  // keys-only sort of the packed records on their upper 32 bits (the 4-byte prefix)
+  DBuf<float> dscore(c, 1);
+  k_text_score<<<1, 256, 0, c.stream>>>(bytehist, d_n, nblk, dscore);
+  KLAUNCH(c); KCHECK();
+  // keys-only sort of the packed records on their upper 32 bits
   radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist.p);
+  if (wide) {
+    k_rekey<<<(nslots + 255) / 256, 256, 0, c.stream>>>(d_T, d_n, nslots, kin);
+    KLAUNCH(c); KCHECK();
+    c.stats.bwt_bytes += n_total * 20;
+    radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist.p);
+  }
   u32* SA = saBuf;
   CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
   CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
@@ -313,14 +407,19 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   {
     const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;
     const u32 ri_tiles = ri_tps * nblk;  // <= rr_tiles_init
-    k_rerank_init<<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, SA, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init,
-                                                         ri_tiles);
+    if (wide)
+      k_rerank_init<true><<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, d_T, SA, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init, ri_tiles);
+    else
+      k_rerank_init<false><<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, d_T, SA, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init, ri_tiles);
     KLAUNCH(c); KCHECK();
   }
   c.stats.bwt_bytes += n_total * (8 + 4 + 4);
   u32 M = 0;
+  float score = 0.f;
   CUDA_CHECK(cudaMemcpyAsync(&M, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_CHECK(cudaMemcpyAsync(&score, dscore, 4, cudaMemcpyDeviceToHost, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  if (!c.bwt_wide_forced) c.bwt_wide = score > 0.5f;  // next batch of this call
 
   if (M > 0) {
     // the initial-sort key buffers are free now; the rounds need 64-bit keys for at most M records
@@ -330,7 +429,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
     const u32 keybits = SEG_SHIFT + bits_for(nslots - 1);
     const u32 npass = (keybits + RADIX_BITS - 1) / RADIX_BITS;
     DBuf<u32> dM(c, 1);
-    u32 h = 4, rounds = 0;
+    u32 h = wide ? 8 : 4, rounds = 0;
     while (M > 0) {
       const int tiebreak = h >= n_max ? 1 : 0;
       rounds++;

@@ -20,6 +20,7 @@ struct Ctx {
   std::vector<b2_block_trace> trace;
   u32 bwt_batch = 296;  // bzip2 blocks processed together in one batch (2 CTAs x 148 SMs for the per-block kernels)
   bool timing = true;
+  bool bwt_wide = false, bwt_wide_forced = false, bwt_mode_known = false;  // 8-byte initial sort for text-like batches (see bwt.cu)
   // plan handed from b2_bzip2_plan to the next b2_bzip2_encode_range_dev on the same (unchanged) buffer
   void* plan_cache = nullptr; const void* plan_ptr = nullptr; size_t plan_n = 0; int plan_level = 0;
 
@@ -56,6 +57,7 @@ struct Ctx {
   void reset_call() {
     ev_used = 0;
     ev_tags.clear();
+    bwt_mode_known = false;
     memset(&stats, 0, sizeof stats);
   }
   void collect();  // after the final sync: fold event pairs into stats

@@ -269,6 +269,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     s.wlen[HD_WIN + lane] = 0;
     s.wsym[HD_WIN + lane] = 0;
     u64 stage_w0 = ~0ull;  // index of the stream word held in win[0]
+    u32 wlim = HD_WIN;     // bit offsets decoded per window: adapts to the size of the previous group
     __syncwarp();
     while (!done) {
       if (selector >= ns) { status = DEC_DATA_ERROR; break; }          // :291
@@ -296,7 +297,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
           const u32* wp = s.win + (u32)(w0 - stage_w0) + ((shiftbase + lane) >> 5);
           u32 hiw = wp[0];
 #pragma unroll 4
-          for (u32 k = 0; k < HD_WIN / 32; k++) {
+          for (u32 k = 0; k < wlim / 32; k++) {
             const u32 low = wp[k + 1];
             const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
             hiw = low;
@@ -323,22 +324,22 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
             s.wlen[lane + 32 * k] = (u8)len;
           }
         }
+        s.wlen[wlim + lane] = 0;   // everything behind the decoded window parks the chain
+        s.wsym[wlim + lane] = 0;
         __syncwarp();
         // jump tables: J1[o] = o + len[o] (an offset without a code, or beyond the window, maps to itself)
-#pragma unroll
-        for (u32 k = 0; k < (HD_WIN + 32) / 32; k++) {
+        const u32 jn = (wlim + 32) / 32;
+        for (u32 k = 0; k < jn; k++) {
           const u32 o = lane + 32 * k;
-          s.J1[o] = (u16)min(o + (u32)s.wlen[o], (u32)(HD_WIN + 31));
+          s.J1[o] = (u16)min(o + (u32)s.wlen[o], wlim + 31u);
         }
         __syncwarp();
-#pragma unroll
-        for (u32 k = 0; k < (HD_WIN + 32) / 32; k++) {
+        for (u32 k = 0; k < jn; k++) {
           const u32 o = lane + 32 * k;
           s.J2[o] = s.J1[s.J1[o]];
         }
         __syncwarp();
-#pragma unroll
-        for (u32 k = 0; k < (HD_WIN + 32) / 32; k++) {
+        for (u32 k = 0; k < jn; k++) {
           const u32 o = lane + 32 * k;
           s.J4[o] = s.J2[s.J2[o]];
         }
@@ -369,7 +370,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
           first_eob = __reduce_min_sync(FULL_MASK, first_eob);
           u32 cntw = lim, flag = 0;
           if (first_eob < first_stop && first_eob < lim) { cntw = first_eob + 1; flag = 1; }
-          else if (first_stop < lim) { cntw = first_stop; flag = (s.spos[first_stop] < HD_WIN) ? 2u : 0u; }  // :299/:306 vs. window exhausted
+          else if (first_stop < lim) { cntw = first_stop; flag = (s.spos[first_stop] < wlim) ? 2u : 0u; }  // :299/:306 vs. window exhausted
           if (lane == 0) { s.c_cnt = cntw; s.c_pos = s.spos[cntw]; s.c_flag = flag; }
         }
         __syncwarp();
@@ -379,6 +380,11 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
         m += cnt;
         remaining -= cnt;
         P += s.c_pos;
+        {
+          // next window: enough for a whole group at the current bits/symbol plus slack
+          const u32 est = cnt ? (s.c_pos * HUFF_GROUP) / cnt + 64u : HD_WIN;
+          wlim = min((u32)HD_WIN, max(96u, (est + 31u) & ~31u));
+        }
         if (flag == 2) { status = DEC_DATA_ERROR; done = true; }
         else if (flag == 1) done = true;
         __syncwarp();

@@ -12,7 +12,14 @@ mb = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 kind = sys.argv[2] if len(sys.argv) > 2 else "ascii"
 mode = sys.argv[3] if len(sys.argv) > 3 else "both"
 n = mb << 20
-data = T.ascii_random(n) if kind == "ascii" else (T.texty(min(n, 8 << 20), 3) * (n // (8 << 20) + 1))[:n]
+if kind == "ascii":
+    data = T.ascii_random(n)
+elif kind == "enwik":
+    from tools.workloads import enwik_like
+    n = mb * 1000000
+    data = enwik_like(n).tobytes()
+else:
+    data = (T.texty(min(n, 8 << 20), 3) * (n // (8 << 20) + 1))[:n]
 L = _native.lib()
 L.b2_init(0)
 d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
