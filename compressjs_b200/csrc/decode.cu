@@ -106,13 +106,14 @@ struct BitReader {
 
 // ---- header + Huffman decode: one warp per candidate ----------------------------------------
 #define HD_WARPS 4
+#define HD_LUT_BITS 9   // 6 tables x 512 entries: keeps a warp's state under 19 KB so that 12 blocks fit per SM
 #define HD_WIN 512
 #define HD_STAGE 64
 struct HdecWarp {
   int limit[HUFF_MAXGROUPS][22];
   int base[HUFF_MAXGROUPS][22];
   u16 permute[HUFF_MAXGROUPS][HUFF_MAXSYM + 2];
-  u16 lut[HUFF_MAXGROUPS][1024];
+  u16 lut[HUFF_MAXGROUPS][1 << HD_LUT_BITS];
   u8 len[HUFF_MAXGROUPS][HUFF_MAXSYM + 2];
   int minlen[HUFF_MAXGROUPS], maxlen[HUFF_MAXGROUPS];
   int status; u32 ngroups, nsel, symcount;
@@ -229,14 +230,14 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     s.base[g][minLen] = 0;
   }
   __syncwarp();
-  // ---- 10-bit LUT derived from the reference's decode loop (lib/Bzip2.js:296-307) ----
-  for (u32 e = lane; e < gc * 1024; e += 32) {
-    const u32 g = e >> 10, p = e & 1023;
+  // ---- LUT (HD_LUT_BITS bits) derived from the reference's decode loop (lib/Bzip2.js:296-307) ----
+  for (u32 e = lane; e < gc << HD_LUT_BITS; e += 32) {
+    const u32 g = e >> HD_LUT_BITS, p = e & ((1u << HD_LUT_BITS) - 1);
     const int minLen = s.minlen[g], maxLen = s.maxlen[g];
-    u16 ent = 0;  // 0 = needs more than 10 bits (or fails): take the slow path
+    u16 ent = 0;  // 0 = needs more than HD_LUT_BITS bits (or fails): take the slow path
     int i = minLen;
-    if (i <= 10) {
-      int j = (int)(p >> (10 - i));
+    if (i <= HD_LUT_BITS) {
+      int j = (int)(p >> (HD_LUT_BITS - i));
       for (;;) {
         if (i > maxLen) break;
         if (j <= s.limit[g][i]) {
@@ -245,8 +246,8 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
           break;
         }
         i++;
-        if (i > 10) break;
-        j = (j << 1) | (int)((p >> (10 - i)) & 1);
+        if (i > HD_LUT_BITS) break;
+        j = (j << 1) | (int)((p >> (HD_LUT_BITS - i)) & 1);
       }
     }
     s.lut[g][p] = ent;
@@ -302,7 +303,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
             const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
             hiw = low;
             u32 sym = 0, len = 0;
-            const u32 ent = lut[bits20 >> 10];
+            const u32 ent = lut[bits20 >> (20 - HD_LUT_BITS)];
             if (ent) {
               sym = ent & 511u; len = ent >> 9;
             } else {
@@ -578,10 +579,10 @@ __global__ void k_ibwt_pack(const u8* __restrict__ tt, const u32* __restrict__ t
   if ((g & SEG_MASK) < seg_n[g >> SEG_SHIFT]) P[g] = ((tvec[g] & SEG_MASK) << 8) | tt[g];
 }
 
-#define IB_SHIFT 8
+#define IB_SHIFT 7
 #define IB_STEP (1u << IB_SHIFT)
 #define IB_SEGS (SEG_SIZE / IB_STEP + 1)  // sampled rows per block + the start row
-#define IB_VCAP 8192
+#define IB_VCAP 16384
 #define IB_SUB 28  // blocks walked together: their packed T-vectors (3.6 MB each) stay L2 resident
 
 struct Seg { u32 len, next; };
@@ -616,7 +617,8 @@ __global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restric
 __global__ void __launch_bounds__(128)
 k_ibwt_chain(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Seg* __restrict__ segs,
              Visit* __restrict__ visits, u32* __restrict__ nvisits) {
-  __shared__ Seg ss[IB_SEGS];
+  extern __shared__ __align__(8) unsigned char chain_smem[];
+  Seg* ss = reinterpret_cast<Seg*>(chain_smem);
   const u32 ci = blockIdx.x;
   if (ci >= ncand) return;
   const CandRes* r = res + ci;
@@ -892,10 +894,13 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   const u32 ur_tps = UR_TPS;
 
   // ---- 2. decode the own share of the candidate blocks, in batches ----
-  const u32 DB = std::max(1u, c.bwt_batch);
+  // the per-block Huffman stage is one warp per block and latency bound: give it every block at once
+  // (about 19 MB of scratch per block; 180 GB of HBM take thousands)
+  const u32 DB = std::max(c.bwt_batch, 2048u);
   static bool attr = false;
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HdecWarp) * HD_WARPS)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_ibwt_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Seg) * IB_SEGS)));
     attr = true;
   }
   if (nb) {
@@ -951,7 +956,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
           const u32* Ps = Pp + ((size_t)s0 << SEG_SHIFT);
           k_ibwt_walk1<<<(sc * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS);
           KLAUNCH(c); KCHECK();
-          k_ibwt_chain<<<sc, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0);
+          k_ibwt_chain<<<sc, 128, sizeof(Seg) * IB_SEGS, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0);
           KLAUNCH(c); KCHECK();
           k_ibwt_walk2<<<(sc * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0,
                                                                        rle.p + ((k0 + s0) << SEG_SHIFT));
