@@ -412,25 +412,30 @@ struct ChunkSum {
   u32 bad;
 };
 
-// move list[idx] to the front; returns the moved value.  List = 8 bytes per lane (lo, hi).
+// move list[idx] to the front; returns the moved value (valid in lane 0; other lanes get junk in the
+// upper bytes).  List = 8 bytes per lane (lo, hi).  Every lane builds two byte-permute selectors:
+// the bytes at positions <= p shift up by one (p = 7 below lane idx/8, idx%8 in that lane, none above),
+// byte 0 takes the carry (previous lane's top byte, or the moved value in lane 0).
+__device__ __forceinline__ u32 shl_clamp(u32 a, u32 n) {
+  u32 r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));  // PTX clamps shift amounts > 31: result 0
+  return r;
+}
 __device__ __forceinline__ u32 mtf_take(u32& lo, u32& hi, u32 idx, u32 lane) {
   const u32 fl = idx >> 3, pos = idx & 7;
-  const u64 v0 = ((u64)hi << 32) | lo;
-  const u32 mine = (u32)(v0 >> (8 * pos)) & 255u;
+  const u32 mine = __byte_perm(lo, hi, pos);
   const u32 c = __shfl_sync(FULL_MASK, mine, fl);
-  if (idx != 0) {
-    u32 carry = __shfl_up_sync(FULL_MASK, hi >> 24, 1);
-    if (lane == 0) carry = c;
-    u64 v = v0;
-    if (lane < fl) v = (v << 8) | carry;
-    else if (lane == fl) {
-      const u64 lowmask = (1ull << (8 * pos)) - 1;
-      const u64 highmask = pos == 7 ? 0ull : ~((1ull << (8 * (pos + 1))) - 1);
-      v = (v & highmask) | (((v & lowmask) << 8) | carry);
-    }
-    lo = (u32)v; hi = (u32)(v >> 32);
-  }
-  return c;
+  const u32 up = __shfl_up_sync(FULL_MASK, hi, 1);
+  const u32 cw = lane == 0 ? c : up;
+  const u32 xl = lane == 0 ? (0x3210u ^ 0x2104u) : (0x3210u ^ 0x2107u);  // carry byte: cw byte 0 / byte 3
+  const u32 q4 = lane < fl ? 32u : (lane == fl ? 4 * pos + 4 : 0u);
+  const u32 M = shl_clamp(1u, q4) - 1u;
+  const u32 sel_lo = 0x3210u ^ (xl & M);
+  const u32 sel_hi = 0x3210u ^ (0x1317u & (M >> 16));
+  const u32 nhi = __byte_perm(hi, lo, sel_hi);
+  lo = __byte_perm(lo, cw, sel_lo);
+  hi = nhi;
+  return c & 255u;
 }
 
 __global__ void __launch_bounds__(UM_WARPS * 32)
