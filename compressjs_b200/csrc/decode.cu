@@ -439,7 +439,8 @@ __device__ __forceinline__ u32 mtf_take(u32& lo, u32& hi, u32 idx, u32 lane) {
 }
 
 __global__ void __launch_bounds__(UM_WARPS * 32)
-k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, ChunkSum* __restrict__ sums, u8* __restrict__ perms) {
+k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, ChunkSum* __restrict__ sums, u8* __restrict__ perms,
+          u8* __restrict__ symb) {
   const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 gchunk = blockIdx.x * UM_WARPS + w;
   const u32 ci = gchunk / cps, ch = gchunk % cps;
@@ -455,27 +456,36 @@ k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncan
   u32 lo = 0x03020100u + lane * 0x08080808u, hi = 0x07060504u + lane * 0x08080808u;  // identity list
   u64 leadval = 0; u32 nlead = 0, rest = 0, krun = 0, bad = 0;
   bool seen_lit = false;
+  // symb[i] = position IN THE CHUNK'S START LIST of the byte that symbol i stands for (the list front for
+  // a run digit): k_unmtf_map turns it into the byte once k_unmtf_scan knows the start lists.
+  u8* sb = symb + ((size_t)ci << SEG_SHIFT) + start;
+  u32 front = 0;
+  u32 nxt = lane < count ? s[lane] : 0xffffu;
   for (u32 base = 0; base < count; base += 32) {
-    const u32 mine = (base + lane < count) ? s[base + lane] : 0xffffu;
+    const u32 mine = nxt;
+    nxt = (base + 32 + lane < count) ? s[base + 32 + lane] : 0xffffu;
     const u32 lim = min(32u, count - base);
+    u32 keep = 0;
     for (u32 t = 0; t < lim; t++) {
       const u32 sy = __shfl_sync(FULL_MASK, mine, t);
       if (sy <= 1) {
         if (!seen_lit) {
-          if (nlead < 40) leadval += (u64)(sy + 1) << nlead; else bad = 1;
+          if (nlead < 21) leadval += (u64)(sy + 1) << nlead; else bad = 1;   // >= 2^21 bytes: over any dbufSize
           nlead++;
         } else {
-          if (krun < 31) rest += (sy + 1) << krun; else bad = 1;
+          if (krun < 21) rest = min(rest + ((sy + 1) << krun), 0x3fffffffu); else bad = 1;  // saturate: no wrap-around
           krun++;
         }
       } else {
         seen_lit = true; krun = 0;
         if (sy <= symTotal) {
-          mtf_take(lo, hi, sy - 1, lane);
+          front = mtf_take(lo, hi, sy - 1, lane);
           rest++;
         }
       }
+      if (lane == t) keep = front;
     }
+    if (base + lane < count) sb[base + lane] = (u8)keep;
   }
   if (lane == 0) {
     ChunkSum cs;
@@ -527,9 +537,12 @@ k_unmtf_scan(CandRes* __restrict__ res, u32 ncand, u32 cps, u32 dbuf_size, const
   }
 }
 
+// Second pass, fully lane parallel: byte = sym_to_byte[start list[symb]], run digit i of a run weighs
+// (digit+1) << i (lib/Bzip2.js:312-361); output offsets by a warp scan of the weights.
 __global__ void __launch_bounds__(UM_WARPS * 32)
-k_unmtf_b(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, const u8* __restrict__ lists,
-          const ChunkStart* __restrict__ starts, u8* __restrict__ tt) {
+k_unmtf_map(const u16* __restrict__ sym, const u8* __restrict__ symb, const CandRes* __restrict__ res, u32 ncand, u32 cps,
+            const u8* __restrict__ lists, const ChunkStart* __restrict__ starts, u8* __restrict__ tt) {
+  __shared__ u8 Ts[UM_WARPS][256];
   const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 gchunk = blockIdx.x * UM_WARPS + w;
   const u32 ci = gchunk / cps, ch = gchunk % cps;
@@ -541,33 +554,44 @@ k_unmtf_b(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncan
   if (start >= m) return;
   const u32 count = min((u32)UM_CHUNK, m - start);
   const u16* s = sym + ((size_t)ci << SEG_SHIFT) + start;
+  const u8* sb = symb + ((size_t)ci << SEG_SHIFT) + start;
   const u32 symTotal = r->sym_total;
-  const u32* lp = reinterpret_cast<const u32*>(lists + (size_t)gchunk * 256);
-  u32 lo = lp[lane * 2], hi = lp[lane * 2 + 1];
+  u8* T = Ts[w];
+  {
+    const u8* lp = lists + (size_t)gchunk * 256;
+    const u8* s2b = r->sym_to_byte;
+    for (u32 i = lane; i < 256; i += 32) T[i] = s2b[lp[i]];
+  }
+  __syncwarp();
   const ChunkStart st = starts[gchunk];
   u32 k = st.k, o = st.off;
   u8* out = tt + ((size_t)ci << SEG_SHIFT);
-  const u8* s2b = r->sym_to_byte;
   for (u32 base = 0; base < count; base += 32) {
-    const u32 mine = (base + lane < count) ? s[base + lane] : 0xffffu;
-    const u32 lim = min(32u, count - base);
-    for (u32 t = 0; t < lim; t++) {
-      const u32 sy = __shfl_sync(FULL_MASK, mine, t);
-      if (sy <= 1) {
-        const u32 wgt = (sy + 1) << k;
-        k++;
-        const u8 b = s2b[__shfl_sync(FULL_MASK, lo & 255u, 0)];
-        for (u32 x = lane; x < wgt; x += 32) out[o + x] = b;
-        o += wgt;
-      } else {
-        k = 0;
-        if (sy <= symTotal) {
-          const u32 c = mtf_take(lo, hi, sy - 1, lane);
-          if (lane == 0) out[o] = s2b[c];
-          o++;
-        }
-      }
+    const bool valid = base + lane < count;
+    const u32 sy = valid ? s[base + lane] : 0xffffu;
+    const u32 b = T[valid ? sb[base + lane] : 0];
+    const bool isrun = sy <= 1;
+    const u32 runmask = __ballot_sync(FULL_MASK, isrun);
+    const u32 nonrun_below = ~runmask & lanemask_lt();
+    const u32 kk = nonrun_below ? lane - (31 - __clz(nonrun_below)) - 1 : lane + k;
+    const u32 wgt = isrun ? (sy + 1) << kk : (sy <= symTotal ? 1u : 0u);
+    const u32 inc = warp_incl_add(wgt);
+    const u32 tot = __shfl_sync(FULL_MASK, inc, 31);
+    const u32 oo = o + inc - wgt;
+    if (wgt == 1) out[oo] = (u8)b;
+    // runs longer than one byte: short ones by their own lane, long ones by the whole warp
+    const bool shortrun = wgt > 1 && wgt <= 16;
+    if (shortrun) for (u32 x = 0; x < wgt; x++) out[oo + x] = (u8)b;
+    u32 big = __ballot_sync(FULL_MASK, wgt > 16);
+    while (big) {
+      const u32 l = __ffs(big) - 1;
+      big &= big - 1;
+      const u32 bo = __shfl_sync(FULL_MASK, oo, l), bw = __shfl_sync(FULL_MASK, wgt, l), bb = __shfl_sync(FULL_MASK, b, l);
+      for (u32 x = lane; x < bw; x += 32) out[bo + x] = (u8)bb;
     }
+    o += tot;
+    const u32 nonrun = ~runmask;
+    k = nonrun ? (u32)__clz(nonrun) : k + 32;  // run digits at the end of this batch
   }
 }
 
@@ -911,7 +935,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   if (nb) {
     const u32 nbm = (u32)std::min<size_t>(DB, nb);
     DBuf<u16> sym(c, (size_t)nbm << SEG_SHIFT);
-    DBuf<u8> selbuf(c, (size_t)nbm * SEL_CAP), tt(c, (size_t)nbm << SEG_SHIFT);
+    DBuf<u8> selbuf(c, (size_t)nbm * SEL_CAP), tt(c, (size_t)nbm << SEG_SHIFT), symb(c, (size_t)nbm << SEG_SHIFT);
     const u32 cps = SEG_SIZE / UM_CHUNK;
     DBuf<ChunkSum> sums(c, (size_t)nbm * cps);
     DBuf<u8> perms(c, (size_t)nbm * cps * 256), lists(c, (size_t)nbm * cps * 256);
@@ -934,11 +958,11 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
       {
         StageScope ss(c, ST_UNMTF);
         const u32 chunks = cnt * cps;
-        k_unmtf_a<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, sums, perms);
+        k_unmtf_a<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, sums, perms, symb);
         KLAUNCH(c); KCHECK();
         k_unmtf_scan<<<cnt, 32, 0, c.stream>>>(rb, cnt, cps, dbuf_size, sums, perms, lists, starts);
         KLAUNCH(c); KCHECK();
-        k_unmtf_b<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, lists, starts, tt);
+        k_unmtf_map<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, symb, rb, cnt, cps, lists, starts, tt);
         KLAUNCH(c); KCHECK();
       }
       CUDA_CHECK(cudaMemcpyAsync(hres + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
