@@ -612,7 +612,6 @@ __global__ void k_ibwt_pack(const u8* __restrict__ tt, const u32* __restrict__ t
 #define IB_STEP (1u << IB_SHIFT)
 #define IB_SEGS (SEG_SIZE / IB_STEP + 1)  // sampled rows per block + the start row
 #define IB_VCAP 16384
-#define IB_SUB 28  // blocks walked together: their packed T-vectors (3.6 MB each) stay L2 resident
 
 struct Seg { u32 len, next; };
 struct Visit { u32 row, off, len; };
@@ -980,8 +979,11 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
         u32* Pp = kout;  // the other key buffer is free now
         k_ibwt_pack<<<(nslots + 255) / 256, 256, 0, c.stream>>>(tt, vin, dn, nslots, Pp);
         KLAUNCH(c); KCHECK();
-        for (u32 s0 = 0; s0 < cnt; s0 += IB_SUB) {
-          const u32 sc = std::min<u32>(IB_SUB, cnt - s0);
+        // all blocks of the batch walk together: the launch lasts as long as its longest segment walk, so fewer,
+        // bigger launches win over keeping the packed T-vectors L2 resident (measured: 75 ms -> 36 ms per GiB)
+        const u32 ib_sub = cnt;
+        for (u32 s0 = 0; s0 < cnt; s0 += ib_sub) {
+          const u32 sc = std::min<u32>(ib_sub, cnt - s0);
           const u32* Ps = Pp + ((size_t)s0 << SEG_SHIFT);
           k_ibwt_walk1<<<(sc * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS);
           KLAUNCH(c); KCHECK();
