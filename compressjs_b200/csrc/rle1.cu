@@ -593,8 +593,14 @@ __device__ __forceinline__ u32 crc_xpow(u64 bytes) {
 }
 
 #define CRC_PIECE 256
-// pieces are aligned from the END of each block's raw range; piece j covers
-// [e - (j+1)*256, e - j*256) clipped at s.  acc[k] ^= R(piece) * x^(8*256*j).
+// Piece j of a block is the j-th 256-byte ADDRESS-aligned window of the buffer that intersects the block's raw
+// range [s,e): every full piece is read with aligned 16-byte loads.  A piece that ends inside the block ends
+// on a window boundary, 256*k + (e' mod 256) bytes before the block end (e' = e + buffer misalignment), so
+// acc[2k] ^= R(piece) * x^(8*256*k) and the common factor x^(8*(e' mod 256)) is applied once in k_crc_final;
+// the piece that ends the block goes to acc[2k+1] unshifted.
+__host__ __device__ __forceinline__ u64 crc_piece_count(u64 s, u64 e, u32 mis) {
+  return e > s ? (e - 1 + mis) / CRC_PIECE - (s + mis) / CRC_PIECE + 1 : 0;
+}
 __global__ void __launch_bounds__(256)
 k_crc_pieces(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u64* __restrict__ piece_base,
              u64 total_pieces, u32* __restrict__ acc) {
@@ -609,15 +615,16 @@ k_crc_pieces(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 
     if (piece_base[mid] <= gid) lo = mid; else hi = mid;
   }
   const BlkInfo bi = blocks[first + lo];
+  const u32 mis = (u32)((size_t)in & (CRC_PIECE - 1));
   const u64 j = gid - piece_base[lo];
-  const u64 pend = bi.e - j * CRC_PIECE;
-  const u64 pbeg = (pend - bi.s > CRC_PIECE) ? pend - CRC_PIECE : bi.s;
+  const u64 A = ((bi.s + mis) / CRC_PIECE + j) * CRC_PIECE;  // window start, in misalignment-shifted offsets
+  const u64 pbeg = A > bi.s + mis ? A - mis : bi.s;
+  const u64 pend = A + CRC_PIECE < bi.e + mis ? A + CRC_PIECE - mis : bi.e;
   u32 crc = 0;
   const u8* p = in + pbeg;
   const u32 len = (u32)(pend - pbeg);
-  u32 i = 0;
-  if (len == CRC_PIECE && (((size_t)p) & 15) == 0) {
-    for (; i < CRC_PIECE; i += 16) {
+  if (len == CRC_PIECE) {
+    for (u32 i = 0; i < CRC_PIECE; i += 16) {
       uint4 q = *reinterpret_cast<const uint4*>(p + i);
       u32 a[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -626,17 +633,25 @@ k_crc_pieces(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 
         for (int b = 0; b < 4; b++) crc = (crc << 8) ^ tab[((crc >> 24) ^ (a[w] >> (8 * b))) & 0xff];
     }
   } else {
-    for (; i < len; i++) crc = (crc << 8) ^ tab[((crc >> 24) ^ p[i]) & 0xff];
+    for (u32 i = 0; i < len; i++) crc = (crc << 8) ^ tab[((crc >> 24) ^ p[i]) & 0xff];
   }
-  if (j) crc = gf_mulmod(crc, crc_xpow(j * CRC_PIECE));
-  atomicXor(&acc[lo], crc);
+  if (pend == bi.e) {
+    atomicXor(&acc[2 * lo + 1], crc);
+  } else {
+    const u64 k = (bi.e - pend) / CRC_PIECE;
+    if (k) crc = gf_mulmod(crc, crc_xpow(k * CRC_PIECE));
+    atomicXor(&acc[2 * lo], crc);
+  }
 }
-__global__ void k_crc_final(const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u32* __restrict__ acc, u32* __restrict__ crc_out) {
+__global__ void k_crc_final(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u32* __restrict__ acc,
+                            u32* __restrict__ crc_out) {
   u32 k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
   const BlkInfo bi = blocks[first + k];
   const u64 len = bi.e - bi.s;
-  crc_out[k] = ~(acc[k] ^ gf_mulmod(0xffffffffu, crc_xpow(len)));
+  const u32 mis = (u32)((size_t)in & (CRC_PIECE - 1));
+  const u32 body = gf_mulmod(acc[2 * k], crc_xpow((bi.e + mis) % CRC_PIECE)) ^ acc[2 * k + 1];
+  crc_out[k] = ~(body ^ gf_mulmod(0xffffffffu, crc_xpow(len)));
 }
 
 // single-buffer CRC (b2_crc32_bzip2)
@@ -647,17 +662,17 @@ u32 crc32_device(Ctx& c, const u8* d_p, size_t n) {
   bi.s = 0; bi.e = n; bi.b = 0; bi.n = 0;
   DBuf<BlkInfo> db(c, 1);
   DBuf<u64> pb(c, 1);
-  DBuf<u32> acc(c, 1), out(c, 1);
+  DBuf<u32> acc(c, 2), out(c, 1);
   u64 zero = 0;
   CUDA_CHECK(cudaMemcpyAsync(db, &bi, sizeof bi, cudaMemcpyHostToDevice, c.stream));
   CUDA_CHECK(cudaMemcpyAsync(pb, &zero, 8, cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(acc, 0, 4, c.stream));
-  const u64 pieces = (n + CRC_PIECE - 1) / CRC_PIECE;
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, 8, c.stream));
+  const u64 pieces = crc_piece_count(0, n, (u32)((size_t)d_p & (CRC_PIECE - 1)));
   if (pieces) {
     k_crc_pieces<<<(unsigned)((pieces + 255) / 256), 256, 0, c.stream>>>(d_p, db, 0, 1, pb, pieces, acc);
     KLAUNCH(c); KCHECK();
   }
-  k_crc_final<<<1, 32, 0, c.stream>>>(db, 0, 1, acc, out);
+  k_crc_final<<<1, 32, 0, c.stream>>>(d_p, db, 0, 1, acc, out);
   KLAUNCH(c); KCHECK();
   u32 h = 0;
   CUDA_CHECK(cudaMemcpyAsync(&h, out, 4, cudaMemcpyDeviceToHost, c.stream));
@@ -723,21 +738,21 @@ void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, si
     const BlkInfo& bi = plan.h_blocks[first + k];
     tbase[k] = tt; pbase[k] = pp;
     tt += (bi.e - 1) / RLE_TILE - bi.s / RLE_TILE + 1;
-    pp += (bi.e - bi.s + CRC_PIECE - 1) / CRC_PIECE;
+    pp += crc_piece_count(bi.s, bi.e, (u32)((size_t)d_in & (CRC_PIECE - 1)));
     hn[k] = bi.n;
   }
   tbase[count] = tt; pbase[count] = pp;
   DBuf<u64> dtb(c, count + 1), dpb(c, count + 1);
-  DBuf<u32> acc(c, count);
+  DBuf<u32> acc(c, 2 * count);
   CUDA_CHECK(cudaMemcpyAsync(dtb, tbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
   CUDA_CHECK(cudaMemcpyAsync(dpb, pbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
   CUDA_CHECK(cudaMemcpyAsync(d_n, hn.data(), 4 * count, cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * count, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * count, c.stream));
   k_rle_emit<<<(unsigned)tt, RT_THREADS, 0, c.stream>>>(d_in, n, plan.tile_carry, plan.tile_prefix, plan.blocks, (u32)first, (u32)count, dtb, d_T);
   KLAUNCH(c); KCHECK();
   k_crc_pieces<<<(unsigned)((pp + 255) / 256), 256, 0, c.stream>>>(d_in, plan.blocks, (u32)first, (u32)count, dpb, pp, acc);
   KLAUNCH(c); KCHECK();
-  k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(plan.blocks, (u32)first, (u32)count, acc, d_crc);
+  k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d_in, plan.blocks, (u32)first, (u32)count, acc, d_crc);
   KLAUNCH(c); KCHECK();
   // tbase/pbase/hn are pageable host vectors: make sure the async copies are done before they die
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
@@ -753,18 +768,18 @@ void crc_ranges(Ctx& c, const u8* d_data, const BlkInfo* d_ranges, const std::ve
   u64 pp = 0;
   for (size_t k = 0; k < count; k++) {
     pbase[k] = pp;
-    pp += (h_ranges[k].e - h_ranges[k].s + CRC_PIECE - 1) / CRC_PIECE;
+    pp += crc_piece_count(h_ranges[k].s, h_ranges[k].e, (u32)((size_t)d_data & (CRC_PIECE - 1)));
   }
   pbase[count] = pp;
   DBuf<u64> dpb(c, count + 1);
-  DBuf<u32> acc(c, count);
+  DBuf<u32> acc(c, 2 * count);
   CUDA_CHECK(cudaMemcpyAsync(dpb, pbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * count, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * count, c.stream));
   if (pp) {
     k_crc_pieces<<<(unsigned)((pp + 255) / 256), 256, 0, c.stream>>>(d_data, d_ranges, 0, (u32)count, dpb, pp, acc);
     KLAUNCH(c); KCHECK();
   }
-  k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d_ranges, 0, (u32)count, acc, d_crc_out);
+  k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d_data, d_ranges, 0, (u32)count, acc, d_crc_out);
   KLAUNCH(c); KCHECK();
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }

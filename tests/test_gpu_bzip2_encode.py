@@ -87,3 +87,29 @@ def test_multi_batch_and_trace():
     _check(data, 1)
     st = _native.stats()
     assert st["blocks"] >= 5 and st["kernel_launches"] > 20
+
+
+@pytest.mark.parametrize("skew", [1, 7, 255])
+def test_device_entry_with_unaligned_input_pointer(skew):
+    """b2_bzip2_compress_dev / b2_crc32 on a device pointer that is not 16-byte aligned (the CRC pieces are cut
+    on address-aligned windows; lib/CRC32.js:72-103 has no such notion, the result must not depend on it)."""
+    import ctypes as C
+    import torch
+    from compressjs_b200 import _native
+    L = _native.lib()
+    data = T.texty(250000, 5) + T.runs(70000, 6) + T.ascii_random(123457, 7)
+    buf = torch.zeros(len(data) + 512, dtype=torch.uint8, device="cuda")
+    buf[skew:skew + len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    cap = L.b2_bzip2_bound(len(data))
+    out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    out_n = C.c_size_t()
+    rc = L.b2_bzip2_compress_dev(buf.data_ptr() + skew, len(data), 1, out.data_ptr(), cap, C.byref(out_n))
+    assert rc == 0, _native.last_error()
+    got = out[:out_n.value].cpu().numpy().tobytes()
+    assert got == O.bzip2_compress(data, 1)
+    # decode into an unaligned output pointer as well (per-block CRC check of the decoded ranges)
+    dec = torch.zeros(len(data) + 512, dtype=torch.uint8, device="cuda")
+    dn = C.c_size_t()
+    rc = L.b2_bzip2_decompress_dev(out.data_ptr(), out_n.value, 0, dec.data_ptr() + skew, len(data), C.byref(dn))
+    assert rc == 0 and dn.value == len(data), _native.last_error()
+    assert dec[skew:skew + len(data)].cpu().numpy().tobytes() == data
