@@ -17,6 +17,8 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
                            std::vector<u32>* crcs_out, size_t* total_blocks, long long spec_first = -2, size_t spec_count = 0,
                            u64* spec_range = nullptr);
 void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst);
+void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, u8* d_out, size_t out_cap, u8* h_out, size_t* out_n,
+                         bool pinned_in);
 void dec_shard_open(Ctx& c, const u8* d_in, size_t n, int rank, int world, u64* info);
 void dec_shard_export(u64* buf);
 int dec_shard_finish(Ctx& c, const u64* all, int multistream, u8* d_out, size_t out_cap, u64* res);
@@ -42,6 +44,11 @@ void Ctx::collect() {
   stats.ms_huff = acc[ST_HUFF]; stats.ms_pack = acc[ST_PACK]; stats.ms_scan = acc[ST_SCAN];
   stats.ms_hdec = acc[ST_HDEC]; stats.ms_unmtf = acc[ST_UNMTF]; stats.ms_ibwt = acc[ST_IBWT];
   stats.ms_unrle = acc[ST_UNRLE]; stats.ms_radix = acc[ST_RADIX];
+  // overlapped copies of the pipelined host path: span from the first to the last copy on their stream
+  for (int w = 0; w < 2; w++) {
+    float ms = 0.f;
+    if (copy_used[w] && cudaEventElapsedTime(&ms, copy_ev[w][0], copy_ev[w][1]) == cudaSuccess) (w ? stats.ms_d2h : stats.ms_h2d) += ms;
+  }
 }
 
 static int pick_device() {
@@ -68,6 +75,9 @@ static Ctx& ctx_locked() {
     c->device = dev;
     memset(&c->stats, 0, sizeof c->stats);
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) CUDA_CHECK(cudaEventCreate(&c->copy_ev[w][k]));
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;
@@ -97,6 +107,18 @@ static void* pinned_alloc(size_t bytes) {
   CUDA_CHECK(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
   g_pinned_live[p] = cap;
   return p;
+}
+
+// give a live pinned buffer back to the cache (caller holds g_mu)
+static void pinned_release(void* p) {
+  auto it = g_pinned_live.find(p);
+  if (it == g_pinned_live.end()) return;
+  size_t cap = it->second;
+  g_pinned_live.erase(it);
+  size_t cached = 0;
+  for (auto& kv : g_pinned_free) cached += kv.first;
+  if (cached + cap > ((size_t)8 << 30)) cudaFreeHost(p);
+  else g_pinned_free.insert({cap, p});
 }
 
 template <typename F>
@@ -138,6 +160,9 @@ void b2_shutdown(void) {
   g_pinned_free.clear();
   for (auto& e : g_ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   cudaStreamDestroy(g_ctx->stream);
+  cudaStreamDestroy(g_ctx->h2d_stream);
+  cudaStreamDestroy(g_ctx->d2h_stream);
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaEventDestroy(g_ctx->copy_ev[w][k]);
   delete g_ctx;
   g_ctx = nullptr;
 }
@@ -147,14 +172,8 @@ const char* b2_last_error(void) { return g_err.c_str(); }
 void b2_free(void* p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_pinned_live.find(p);
-  if (it == g_pinned_live.end()) { free(p); return; }
-  size_t cap = it->second;
-  g_pinned_live.erase(it);
-  size_t cached = 0;
-  for (auto& kv : g_pinned_free) cached += kv.first;
-  if (cached + cap > ((size_t)8 << 30)) cudaFreeHost(p);
-  else g_pinned_free.insert({cap, p});
+  if (g_pinned_live.find(p) == g_pinned_live.end()) { free(p); return; }
+  pinned_release(p);
 }
 
 void b2_get_stats(b2_stats* s) {
@@ -265,20 +284,18 @@ int b2_bzip2_compress(const uint8_t* in, size_t n, int level, uint8_t** out, siz
     Ctx& c = ctx_locked();
     c.reset_call();
     size_t cap = b2_bzip2_bound(n), produced = 0;
-    void* host = nullptr;
-    {
+    void* host = pinned_alloc(cap);
+    try {
       StageScope tot(c, ST_TOTAL);
       DBuf<u8> din(c, n ? n : 1), dout(c, cap);
-      {
-        StageScope s(c, ST_H2D);
-        if (n) CUDA_CHECK(cudaMemcpyAsync(din, in, n, cudaMemcpyHostToDevice, c.stream));
-      }
-      bzip2_compress_device(c, din, n, level, dout, cap, &produced, 0, (size_t)-1, 0, true, nullptr, nullptr, nullptr);
-      host = pinned_alloc(produced);
-      {
-        StageScope s(c, ST_D2H);
-        CUDA_CHECK(cudaMemcpyAsync(host, dout, produced, cudaMemcpyDeviceToHost, c.stream));
-      }
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));  // the buffers are used from the copy streams as well
+      cudaPointerAttributes pa;
+      const bool pinned_in = n && cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      bzip2_compress_host(c, in, n, level, din, dout, cap, (u8*)host, &produced, pinned_in);
+    } catch (...) {
+      pinned_release(host);
+      throw;
     }
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     c.collect();

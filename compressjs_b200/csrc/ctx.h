@@ -13,6 +13,9 @@ struct EventPair {
 struct Ctx {
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // host-buffer entry points: copies overlapped with the encode
+  cudaEvent_t copy_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  bool copy_used[2] = {false, false};
   b2_stats stats;
   std::vector<EventPair> ev_pool;   // reusable events
   size_t ev_used = 0;
@@ -54,7 +57,11 @@ struct Ctx {
     if (!timing) return;
     CUDA_CHECK(cudaEventRecord(ev_pool[i].b, stream));
   }
+  // first / last copy of a call on a copy stream (which: 0 = host to device, 1 = device to host)
+  void copy_begin(cudaStream_t s, int which) { CUDA_CHECK(cudaEventRecord(copy_ev[which][0], s)); copy_used[which] = true; }
+  void copy_end(cudaStream_t s, int which) { CUDA_CHECK(cudaEventRecord(copy_ev[which][1], s)); }
   void reset_call() {
+    copy_used[0] = copy_used[1] = false;
     ev_used = 0;
     ev_tags.clear();
     bwt_mode_known = false;

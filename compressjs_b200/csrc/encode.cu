@@ -15,6 +15,10 @@
 //                   global 32-bit word grid, then the tile is written out coalesced
 //                   (only the two boundary words need atomics)
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
 #include <vector>
 #include "enc.h"
 
@@ -285,11 +289,12 @@ void pack_batch(Ctx& c, const u16* d_sym, const u8* d_sel, const u8* d_selmtf, c
 }
 
 // ---- file header / trailer ---------------------------------------------------------------
-__global__ void k_file_ends(u32* out, int level, const u64* state, int write_header) {
+__global__ void k_file_header(u32* out, int level) {
   if (threadIdx.x || blockIdx.x) return;
-  if (write_header) {
-    gput(out, 0, 8, 'B'); gput(out, 8, 8, 'Z'); gput(out, 16, 8, 'h'); gput(out, 24, 8, (u32)('0' + level));  // lib/Bzip2.js:903-906
-  }
+  gput(out, 0, 8, 'B'); gput(out, 8, 8, 'Z'); gput(out, 16, 8, 'h'); gput(out, 24, 8, (u32)('0' + level));  // lib/Bzip2.js:903-906
+}
+__global__ void k_file_trailer(u32* out, const u64* state) {
+  if (threadIdx.x || blockIdx.x) return;
   u64 p = state[0];
   gput(out, p, 24, 0x177245u); p += 24;  // SQRTPI lib/Bzip2.js:50
   gput(out, p, 24, 0x385090u); p += 24;
@@ -298,6 +303,125 @@ __global__ void k_file_ends(u32* out, int level, const u64* state, int write_hea
 
 // compressFile on device buffers.  whole_file: header + all blocks + trailer.  Otherwise encodes
 // blocks [first_block, first_block+block_count) starting at bit `bit_phase` of d_out.
+// One output stream being written: the running bit position lives on the device (state[0]); blocks of one or more
+// RLE1 plans are appended batch by batch.  Shared by the device-resident entry points and the pipelined host path.
+struct EncSession {
+  Ctx& c;
+  int level; u8* d_out; size_t cap_words; bool whole_file; int bit_phase;
+  DBuf<u64> state; DBuf<u32> flag;
+  std::vector<u32> all_crc;
+  std::vector<b2_block_trace> tr;
+  u32 cap_blocks = 0;
+  DBuf<u8> T, U, dsel, dselmtf;
+  DBuf<u16> sym;
+  DBuf<u32> dn, dcrc, dpidx, dm, dfreq, dused;
+  DBuf<HuffBlk> dhb;
+  DBuf<u64> dbitoff;
+  std::vector<u32> hn, hm, hp;
+  std::vector<HuffBlk> hhb;
+  std::vector<u64> hoff;
+  std::function<void(u64)> on_batch;  // called after every batch with the bit position reached (host synchronised)
+
+  EncSession(Ctx& c_, int level_, u8* d_out_, size_t out_cap, bool whole_file_, int bit_phase_)
+      : c(c_), level(level_), d_out(d_out_), cap_words(out_cap / 4), whole_file(whole_file_), bit_phase(bit_phase_) {
+    if (((size_t)d_out) & 3) throw B2Error{B2_ERR_BAD_ARG, "output buffer must be 4-byte aligned"};
+    if (cap_words < 8) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
+    CUDA_CHECK(cudaMemsetAsync(d_out, 0, cap_words * 4, c.stream));
+    state.alloc(c, 4);
+    flag.alloc(c, 1);
+    u64 h_state[4] = {whole_file ? 32ull : (u64)bit_phase, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(state, h_state, sizeof h_state, cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaMemsetAsync(flag, 0, 4, c.stream));
+    if (whole_file) {  // the header goes first: finished words are handed out while later batches are still encoding
+      k_file_header<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), level);
+      KLAUNCH(c); KCHECK();
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  }
+  void reserve(u32 nb) {
+    if (nb <= cap_blocks) return;
+    cap_blocks = nb;
+    T.alloc(c, (size_t)nb << SEG_SHIFT); U.alloc(c, (size_t)nb << SEG_SHIFT); sym.alloc(c, (size_t)nb << SEG_SHIFT);
+    dn.alloc(c, nb); dcrc.alloc(c, nb); dpidx.alloc(c, nb); dm.alloc(c, nb);
+    dfreq.alloc(c, (size_t)nb * HUFF_MAXSYM); dused.alloc(c, (size_t)nb * 8);
+    dsel.alloc(c, (size_t)nb * SEL_STRIDE); dselmtf.alloc(c, (size_t)nb * SEL_STRIDE);
+    dhb.alloc(c, nb); dbitoff.alloc(c, nb);
+    hn.resize(nb); hm.resize(nb); hp.resize(nb); hhb.resize(nb); hoff.resize(nb);
+  }
+  // append blocks [first, first+count) of `plan` (made over d_in[0,n)); raw_base = offset of d_in in the whole input
+  void encode(const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u64 raw_base) {
+    if (!count) return;
+    // balanced batches: ceil(count / batches) blocks each, so that no tiny tail batch starves the per-block kernels
+    const u32 nbatches = (u32)((count + c.bwt_batch - 1) / c.bwt_batch);
+    const u32 B = (u32)((count + nbatches - 1) / nbatches);
+    reserve((u32)std::min<size_t>(B, count));
+    const size_t done0 = all_crc.size();
+    all_crc.resize(done0 + count);
+    tr.resize(done0 + count);
+    for (size_t k0 = 0; k0 < count; k0 += B) {
+      const u32 nb = (u32)std::min<size_t>(B, count - k0);
+      u32 nmax = 0;
+      for (u32 b = 0; b < nb; b++) { hn[b] = plan.h_blocks[first + k0 + b].n; nmax = std::max(nmax, hn[b]); }
+      {
+        StageScope s(c, ST_RLE1);
+        rle1_materialize(c, d_in, n, plan, first + k0, nb, T, dn, dcrc);
+      }
+      {
+        StageScope s(c, ST_BWT);
+        CUDA_CHECK(cudaMemsetAsync(dpidx, 0, nb * 4, c.stream));
+        bwt_forward_batch(c, T, U, dn, hn.data(), nb, dpidx);
+      }
+      {
+        StageScope s(c, ST_MTF);
+        mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused);
+      }
+      {
+        StageScope s(c, ST_HUFF);
+        huffman_batch(c, sym, dm, dfreq, dused, nb, dsel, dselmtf, dhb);
+      }
+      {
+        StageScope s(c, ST_PACK);
+        k_offsets<<<1, 32, 0, c.stream>>>(dhb, dcrc, nb, state, dbitoff, (u64)cap_words * 32, flag);
+        KLAUNCH(c); KCHECK();
+        pack_batch(c, sym, dsel, dselmtf, dhb, dused, dpidx, dcrc, dbitoff, flag, nb, nmax + 1, reinterpret_cast<u32*>(d_out));
+      }
+      // per-block bookkeeping for the host (trace + CRCs)
+      CUDA_CHECK(cudaMemcpyAsync(hm.data(), dm, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hp.data(), dpidx, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hhb.data(), dhb, nb * sizeof(HuffBlk), cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(hoff.data(), dbitoff, nb * 8, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaMemcpyAsync(all_crc.data() + done0 + k0, dcrc, nb * 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      for (u32 b = 0; b < nb; b++) {
+        b2_block_trace& t = tr[done0 + k0 + b];
+        const BlkInfo& bi = plan.h_blocks[first + k0 + b];
+        t.n = (int32_t)bi.n; t.pidx = (int32_t)hp[b]; t.m = (int32_t)hm[b]; t.alpha = (int32_t)hhb[b].alpha;
+        t.ngroups = (int32_t)hhb[b].ngroups; t.nsel = (int32_t)hhb[b].nsel; t.crc = all_crc[done0 + k0 + b]; t.pad = 0;
+        t.raw_start = raw_base + bi.s; t.raw_len = bi.e - bi.s; t.bit_start = hoff[b]; t.bit_len = hhb[b].body_bits;
+      }
+      c.stats.blocks += nb;
+      if (on_batch) on_batch(hoff[nb - 1] + hhb[nb - 1].body_bits);
+    }
+  }
+  // file trailer (whole files), final size; returns the bit position reached
+  u64 finish(size_t* out_n) {
+    u32 h_flag = 0;
+    u64 h_state[4];
+    if (whole_file) {
+      k_file_trailer<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), state);
+      KLAUNCH(c); KCHECK();
+    }
+    CUDA_CHECK(cudaMemcpyAsync(h_state, state, sizeof h_state, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (h_flag) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
+    // whole files: trailer 48 + 32 bits, zero padded (lib/BitStream.js:68-73)
+    *out_n = whole_file ? (size_t)((h_state[0] + 80 + 7) / 8) : (size_t)((h_state[0] + 7) / 8);
+    c.trace = tr;
+    return h_state[0];
+  }
+};
+
 void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n, size_t first_block,
                            size_t block_count, int bit_phase, bool whole_file, u64* out_bits, std::vector<u32>* crcs_out,
                            size_t* total_blocks, long long spec_first, size_t spec_count, u64* spec_range) {
@@ -343,97 +467,92 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
     owner.keep = true;
     return;
   }
-  if (((size_t)d_out) & 3) throw B2Error{B2_ERR_BAD_ARG, "output buffer must be 4-byte aligned"};
   size_t first = whole_file ? 0 : std::min(first_block, nb_all);
   size_t count = whole_file ? nb_all : std::min(block_count, nb_all - first);
   if (first < plan.first_index) throw B2Error{B2_ERR_BAD_ARG, "block range is not covered by the cached range plan"};
-  const size_t pofs = plan.first_index;  // h_blocks[k] is global block pofs + k
-  const size_t cap_words = out_cap / 4;
-  if (cap_words < 8) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
-  CUDA_CHECK(cudaMemsetAsync(d_out, 0, cap_words * 4, c.stream));
-  DBuf<u64> state(c, 4);
-  DBuf<u32> flag(c, 1);
-  u64 h_state[4] = {whole_file ? 32ull : (u64)bit_phase, 0, 0, 0};
-  CUDA_CHECK(cudaMemcpyAsync(state, h_state, sizeof h_state, cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(flag, 0, 4, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
-  std::vector<u32> all_crc(count);
-  std::vector<b2_block_trace> tr(count);
-  // balanced batches: ceil(count / batches) blocks each, so that no tiny tail batch starves the per-block kernels
-  const u32 nbatches = (u32)((count + c.bwt_batch - 1) / c.bwt_batch);
-  const u32 B = nbatches ? (u32)((count + nbatches - 1) / nbatches) : 1;
-  if (count) {
-    const u32 nbmax = (u32)std::min<size_t>(B, count);
-    DBuf<u8> T(c, (size_t)nbmax << SEG_SHIFT), U(c, (size_t)nbmax << SEG_SHIFT);
-    DBuf<u16> sym(c, (size_t)nbmax << SEG_SHIFT);
-    DBuf<u32> dn(c, nbmax), dcrc(c, nbmax), dpidx(c, nbmax), dm(c, nbmax), dfreq(c, (size_t)nbmax * HUFF_MAXSYM), dused(c, (size_t)nbmax * 8);
-    DBuf<u8> dsel(c, (size_t)nbmax * SEL_STRIDE), dselmtf(c, (size_t)nbmax * SEL_STRIDE);
-    DBuf<HuffBlk> dhb(c, nbmax);
-    DBuf<u64> dbitoff(c, nbmax);
-    std::vector<u32> hn(nbmax), hm(nbmax), hp(nbmax);
-    std::vector<HuffBlk> hhb(nbmax);
-    std::vector<u64> hoff(nbmax);
-    for (size_t k0 = 0; k0 < count; k0 += B) {
-      const u32 nb = (u32)std::min<size_t>(B, count - k0);
-      u32 nmax = 0;
-      for (u32 b = 0; b < nb; b++) { hn[b] = plan.h_blocks[first - pofs + k0 + b].n; nmax = std::max(nmax, hn[b]); }
-      {
-        StageScope s(c, ST_RLE1);
-        rle1_materialize(c, d_in, n, plan, first - pofs + k0, nb, T, dn, dcrc);
-      }
-      {
-        StageScope s(c, ST_BWT);
-        CUDA_CHECK(cudaMemsetAsync(dpidx, 0, nb * 4, c.stream));
-        bwt_forward_batch(c, T, U, dn, hn.data(), nb, dpidx);
-      }
-      {
-        StageScope s(c, ST_MTF);
-        mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused);
-      }
-      {
-        StageScope s(c, ST_HUFF);
-        huffman_batch(c, sym, dm, dfreq, dused, nb, dsel, dselmtf, dhb);
-      }
-      {
-        StageScope s(c, ST_PACK);
-        k_offsets<<<1, 32, 0, c.stream>>>(dhb, dcrc, nb, state, dbitoff, (u64)cap_words * 32, flag);
-        KLAUNCH(c); KCHECK();
-        pack_batch(c, sym, dsel, dselmtf, dhb, dused, dpidx, dcrc, dbitoff, flag, nb, nmax + 1, reinterpret_cast<u32*>(d_out));
-      }
-      // per-block bookkeeping for the host (trace + CRCs)
-      CUDA_CHECK(cudaMemcpyAsync(hm.data(), dm, nb * 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(hp.data(), dpidx, nb * 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(hhb.data(), dhb, nb * sizeof(HuffBlk), cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(hoff.data(), dbitoff, nb * 8, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(all_crc.data() + k0, dcrc, nb * 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaStreamSynchronize(c.stream));
-      for (u32 b = 0; b < nb; b++) {
-        b2_block_trace& t = tr[k0 + b];
-        const BlkInfo& bi = plan.h_blocks[first - pofs + k0 + b];
-        t.n = (int32_t)bi.n; t.pidx = (int32_t)hp[b]; t.m = (int32_t)hm[b]; t.alpha = (int32_t)hhb[b].alpha;
-        t.ngroups = (int32_t)hhb[b].ngroups; t.nsel = (int32_t)hhb[b].nsel; t.crc = all_crc[k0 + b]; t.pad = 0;
-        t.raw_start = bi.s; t.raw_len = bi.e - bi.s; t.bit_start = hoff[b]; t.bit_len = hhb[b].body_bits;
-      }
-      c.stats.blocks += nb;
+  EncSession S(c, level, d_out, out_cap, whole_file, bit_phase);
+  S.encode(d_in, n, plan, first - plan.first_index, count, 0);  // h_blocks[k] is global block first_index + k
+  const u64 bits = S.finish(out_n);
+  if (!whole_file && out_bits) *out_bits = bits - (u64)bit_phase;
+  if (crcs_out) *crcs_out = S.all_crc;
+}
+
+// Bzip2.compressFile with HOST buffers (b2_bzip2_compress).  With a pinned input the upload is cut into chunks
+// on a copy stream; block boundaries only depend on the bytes before them (lib/Bzip2.js:636-667 consumes its
+// input strictly forward), so every block but the last of a plan over the prefix that has arrived is final
+// and is encoded while the rest is still in flight.  Finished words of the output go back on a second copy
+// stream after every batch.  h_out must hold out_cap bytes (pinned).
+void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, u8* d_out, size_t out_cap, u8* h_out, size_t* out_n,
+                         bool pinned_in) {
+  size_t CH = (size_t)64 << 20;
+  if (const char* e = getenv("B2_H2D_CHUNK")) {  // test hook: small chunks exercise the prefix planning on small inputs
+    const long long v = atoll(e);
+    if (v >= 4096) CH = (size_t)v;
+  }
+  const bool trace_host = getenv("B2_TRACE_HOST") != nullptr;  // debug: host-side timeline on stderr
+  const auto t_start = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what, size_t v) {
+    if (trace_host) fprintf(stderr, "[b2 host] %8.2f ms  %s %zu\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what, v);
+  };
+  const size_t nch = (pinned_in && n > CH) ? (n + CH - 1) / CH : (n ? 1 : 0);
+  std::vector<cudaEvent_t> ev(nch);
+  struct Cleanup {
+    std::vector<cudaEvent_t>& ev; Ctx& c;
+    ~Cleanup() {
+      cudaStreamSynchronize(c.h2d_stream); cudaStreamSynchronize(c.d2h_stream);
+      for (auto e : ev) if (e) cudaEventDestroy(e);
     }
+  } cleanup{ev, c};
+  for (auto& e : ev) { e = nullptr; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+  c.copy_begin(c.h2d_stream, 0);
+  for (size_t i = 0; i < nch; i++) {
+    const size_t o = nch == 1 ? 0 : i * CH, len = nch == 1 ? n : std::min(CH, n - o);
+    CUDA_CHECK(cudaMemcpyAsync(d_in + o, h_in + o, len, cudaMemcpyHostToDevice, c.h2d_stream));
+    CUDA_CHECK(cudaEventRecord(ev[i], c.h2d_stream));
   }
-  u32 h_flag = 0;
-  if (whole_file) {
-    k_file_ends<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), level, state, 1);
-    KLAUNCH(c); KCHECK();
+  c.copy_end(c.h2d_stream, 0);
+  mark("uploads queued, chunks", nch);
+  c.trace.clear();
+  EncSession S(c, level, d_out, out_cap, true, 0);
+  mark("session ready", 0);
+  size_t copied = 0;  // bytes of the output already on their way to the host
+  bool d2h_started = false;
+  S.on_batch = [&](u64 bit_end) {
+    const size_t ready = (size_t)(bit_end / 32) * 4;  // whole words below the one still being filled
+    if (ready > copied) {
+      if (!d2h_started) { c.copy_begin(c.d2h_stream, 1); d2h_started = true; }
+      CUDA_CHECK(cudaMemcpyAsync(h_out + copied, d_out + copied, ready - copied, cudaMemcpyDeviceToHost, c.d2h_stream));
+      copied = ready;
+    }
+  };
+  size_t resume = 0, have = 0;  // raw bytes planned so far / chunks known to have arrived
+  while (resume < n) {
+    // block on the next chunk we need, then take every further chunk that has landed meanwhile
+    if (have < nch) { CUDA_CHECK(cudaEventSynchronize(ev[have])); have++; }
+    while (have < nch && cudaEventQuery(ev[have]) == cudaSuccess) have++;
+    const size_t avail = have == nch ? n : have * CH;
+    const bool last = avail == n;
+    mark("chunks arrived", have);
+    Rle1Plan plan;
+    {
+      StageScope s(c, ST_RLE1);
+      rle1_plan(c, d_in + resume, avail - resume, level, plan);
+    }
+    const size_t nfinal = last ? plan.nblocks : (plan.nblocks ? plan.nblocks - 1 : 0);
+    mark("planned, final blocks", nfinal);
+    if (!nfinal) continue;  // the prefix holds less than one full block: wait for more
+    S.encode(d_in + resume, avail - resume, plan, 0, nfinal, resume);
+    mark("encoded", nfinal);
+    resume += plan.h_blocks[nfinal - 1].e;
   }
-  CUDA_CHECK(cudaMemcpyAsync(h_state, state, sizeof h_state, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
-  if (h_flag) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
-  if (whole_file) {
-    *out_n = (size_t)((h_state[0] + 80 + 7) / 8);  // trailer 48 + 32 bits, zero padded (lib/BitStream.js:68-73)
-  } else {
-    *out_n = (size_t)((h_state[0] + 7) / 8);
-    if (out_bits) *out_bits = h_state[0] - (u64)bit_phase;
-  }
-  if (crcs_out) *crcs_out = all_crc;
-  c.trace = tr;
+  S.finish(out_n);
+  if (*out_n > out_cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
+  if (!d2h_started) c.copy_begin(c.d2h_stream, 1);
+  CUDA_CHECK(cudaMemcpyAsync(h_out + copied, d_out + copied, *out_n - copied, cudaMemcpyDeviceToHost, c.d2h_stream));
+  c.copy_end(c.d2h_stream, 1);
+  mark("finished, bytes left to download", *out_n - copied);
+  CUDA_CHECK(cudaStreamSynchronize(c.d2h_stream));
+  mark("download done", *out_n);
 }
 
 // ---- fragment shift for the multi-GPU gather -------------------------------------------------

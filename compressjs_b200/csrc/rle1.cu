@@ -351,10 +351,21 @@ __device__ u64 find_run_end(const u8* in, u64 s, u64 cap, BlocksShared& sh) {
 
 __global__ void __launch_bounds__(RT_THREADS)
 k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ carry, const u64* __restrict__ prefix, u64 ntiles,
-             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks, u64 u_start) {
+             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks, u64 u_start, u32 total) {
   __shared__ BlocksShared sh;
   const u32 tid = threadIdx.x;
   const u64 Wtotal = prefix[ntiles];
+  if (gridDim.x > 1) {
+    // parallel walk: CTA r takes blocks [r*total/P, (r+1)*total/P) of the `total` blocks that W(N) predicts, from
+    // the speculative boundary W = first*BS; the host accepts the result only if every segment ends where the
+    // next one starts (then it IS the sequential walk) and repeats the walk with one CTA otherwise.
+    const u32 P = gridDim.x, r = blockIdx.x;
+    const u32 first = (u32)((u64)r * total / P), next = (u32)((u64)(r + 1) * total / P);
+    u_start = (u64)first * BS;
+    blocks += first;
+    nblocks_out += r;
+    maxblocks = r == P - 1 ? maxblocks - first : next - first;
+  }
   u64 s = 0, Ws = 0;
   bool Ws_valid = true;  // W(0) = 0
   u32 k = 0;
@@ -717,8 +728,33 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     if (maxblocks == 0) return;
   }
   plan.blocks.alloc(c, maxblocks);
+  // exact plans of many blocks: walk P segments in parallel first (see k_rle_blocks)
+  const u32 total = (u32)plan.total_guess;
+  const u32 P = spec_first < 0 ? std::min<u32>(64, total / 8) : 1;
+  if (P > 1 && total < maxblocks) {
+    DBuf<u32> dnb(c, P);
+    k_rle_blocks<<<P, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, 0, total);
+    KLAUNCH(c); KCHECK();
+    std::vector<u32> cut(P);
+    CUDA_CHECK(cudaMemcpyAsync(cut.data(), dnb, 4 * P, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    bool ok = true;
+    for (u32 r = 0; r + 1 < P && ok; r++) ok = cut[r] == (u32)((u64)(r + 1) * total / P) - (u32)((u64)r * total / P);
+    const u32 last_first = (u32)((u64)(P - 1) * total / P);
+    ok = ok && cut[P - 1] > 0;
+    if (ok) {
+      const u32 nb = last_first + cut[P - 1];
+      plan.h_blocks.resize(nb);
+      CUDA_CHECK(cudaMemcpyAsync(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      ok = plan.h_blocks[0].s == 0 && plan.h_blocks[nb - 1].e == n;
+      for (u32 k = 0; k + 1 < nb && ok; k++) ok = plan.h_blocks[k].e == plan.h_blocks[k + 1].s;
+      if (ok) { plan.nblocks = nb; return; }
+      plan.h_blocks.clear();
+    }
+  }
   DBuf<u32> dnb(c, 1);
-  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, u_start);
+  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, u_start, 0);
   KLAUNCH(c); KCHECK();
   u32 nb = 0;
   CUDA_CHECK(cudaMemcpyAsync(&nb, dnb, 4, cudaMemcpyDeviceToHost, c.stream));

@@ -113,3 +113,46 @@ def test_device_entry_with_unaligned_input_pointer(skew):
     rc = L.b2_bzip2_decompress_dev(out.data_ptr(), out_n.value, 0, dec.data_ptr() + skew, len(data), C.byref(dn))
     assert rc == 0 and dn.value == len(data), _native.last_error()
     assert dec[skew:skew + len(data)].cpu().numpy().tobytes() == data
+
+
+@pytest.mark.parametrize("chunk", [4096, 150000, 1 << 20])
+def test_host_entry_pipelined_upload(chunk, monkeypatch):
+    """b2_bzip2_compress with a PINNED input uploads in chunks and encodes the blocks that are final in the
+    prefix that has arrived (block cuts only depend on earlier bytes, lib/Bzip2.js:636-667); the stream must be
+    the one-shot stream whatever the chunking."""
+    import ctypes as C
+    import torch
+    from compressjs_b200 import _native
+    L = _native.lib()
+    monkeypatch.setenv("B2_H2D_CHUNK", str(chunk))
+    data = T.texty(330000, 21) + T.runs(250000, 22) + T.ascii_random(420001, 23) + b"z" * 70000
+    pinned = torch.empty(len(data), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = np.frombuffer(data, dtype=np.uint8)
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = L.b2_bzip2_compress(pinned.data_ptr(), len(data), 1, C.byref(out), C.byref(n))
+    assert rc == 0, _native.last_error()
+    got = bytes(np.ctypeslib.as_array(out, (n.value,)))
+    L.b2_free(out)
+    assert got == O.bzip2_compress(data, 1)
+    tr = _native.last_trace()
+    assert sum(t.raw_len for t in tr) == len(data) and tr[0].raw_start == 0
+    assert all(a.raw_start + a.raw_len == b.raw_start for a, b in zip(tr, tr[1:]))
+
+
+@pytest.mark.parametrize("kind", ["ascii", "text", "slips"])
+def test_many_blocks_parallel_block_walk(kind):
+    """Files of >= 16 blocks cut their blocks with several CTAs from speculated boundaries and accept the cut only
+    if the segments chain up (else one CTA walks again): the stream must equal the sequential reference walk
+    (lib/Bzip2.js:636-667) with and without run-phase slips at block ends."""
+    if kind == "ascii":
+        data = T.ascii_random(2600000, 31)
+    elif kind == "text":
+        data = T.texty(3100000, 32)
+    else:
+        # runs that straddle many block boundaries (blocks filling on a run's 4th byte shift every later boundary)
+        parts = []
+        for i in range(40):
+            parts.append(T.ascii_random(99000 + 37 * i, 100 + i).replace(b"aaaa", b"abab"))
+            parts.append(bytes([65 + i % 26]) * (900 + 13 * i))
+        data = b"".join(parts)
+    _check(data, 1, libbz2=(kind != "slips"))
