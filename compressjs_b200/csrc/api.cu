@@ -51,6 +51,54 @@ void Ctx::collect() {
   }
 }
 
+// ---- small control transfers through mapped pinned memory ----------------------------------
+// During the pipelined host encode the copy engines are busy with 64 MiB uploads and per-batch downloads; an
+// 8-byte cudaMemcpyAsync would wait behind them for milliseconds.  A tiny kernel moves control data through a
+// mapped pinned staging area instead (SM loads/stores over PCIe, no copy engine).
+__global__ void k_stage_copy(void* dst, const void* src, size_t bytes) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  if ((((size_t)dst | (size_t)src | bytes) & 3) == 0) {
+    u32* d = (u32*)dst; const u32* s = (const u32*)src;
+    for (size_t i = i0; i < bytes / 4; i += step) d[i] = s[i];
+  } else {
+    u8* d = (u8*)dst; const u8* s = (const u8*)src;
+    for (size_t i = i0; i < bytes; i += step) d[i] = s[i];
+  }
+}
+size_t Ctx::stage_take(size_t bytes) {
+  if (!stage_h) {
+    CUDA_CHECK(cudaHostAlloc((void**)&stage_h, stage_cap, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer((void**)&stage_d, stage_h, 0));
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (stage_used + need > stage_cap) sync();
+  const size_t off = stage_used;
+  stage_used += need;
+  return off;
+}
+void Ctx::to_device(void* ddst, const void* hsrc, size_t bytes) {
+  if (!bytes) return;
+  if (bytes > stage_cap / 2) { CUDA_CHECK(cudaMemcpyAsync(ddst, hsrc, bytes, cudaMemcpyHostToDevice, stream)); CUDA_CHECK(cudaStreamSynchronize(stream)); return; }
+  const size_t off = stage_take(bytes);
+  memcpy(stage_h + off, hsrc, bytes);
+  k_stage_copy<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256 + 1, 64), 256, 0, stream>>>(ddst, stage_d + off, bytes);
+  CUDA_CHECK(cudaGetLastError());
+}
+void Ctx::to_host(void* hdst, const void* dsrc, size_t bytes) {
+  if (!bytes) return;
+  if (bytes > stage_cap / 2) { CUDA_CHECK(cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, stream)); return; }
+  const size_t off = stage_take(bytes);
+  k_stage_copy<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256 + 1, 64), 256, 0, stream>>>(stage_d + off, dsrc, bytes);
+  CUDA_CHECK(cudaGetLastError());
+  fetches.push_back({hdst, off, bytes});
+}
+void Ctx::sync() {
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  for (auto& f : fetches) memcpy(f.dst, stage_h + f.off, f.bytes);
+  fetches.clear();
+  stage_used = 0;
+}
+
 static int pick_device() {
   const char* e = getenv("B2_DEVICE");
   if (e && *e) return atoi(e);
@@ -159,6 +207,7 @@ void b2_shutdown(void) {
   for (auto& kv : g_pinned_free) cudaFreeHost(kv.second);
   g_pinned_free.clear();
   for (auto& e : g_ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (g_ctx->stage_h) cudaFreeHost(g_ctx->stage_h);
   cudaStreamDestroy(g_ctx->stream);
   cudaStreamDestroy(g_ctx->h2d_stream);
   cudaStreamDestroy(g_ctx->d2h_stream);
@@ -217,12 +266,12 @@ int b2_bwt_cyclic_batch(const uint8_t* T, uint8_t* U, const uint64_t* offs, cons
         CUDA_CHECK(cudaMemcpyAsync(hp.data(), dp, nb * 4, cudaMemcpyDeviceToHost, c.stream));
         for (u32 b = 0; b < nb; b++)
           if (hn[b]) CUDA_CHECK(cudaMemcpyAsync(U + offs[k0 + b], dU.p + ((size_t)b << SEG_SHIFT), hn[b], cudaMemcpyDeviceToHost, c.stream));
-        CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        c.sync();
         for (u32 b = 0; b < nb; b++) pidx[k0 + b] = (int32_t)hp[b];
         c.stats.blocks += nb;
       }
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     c.collect();
     return 0;
   });
@@ -271,7 +320,7 @@ int b2_bzip2_compress_dev(const void* d_in, size_t n, int level, void* d_out, si
       StageScope tot(c, ST_TOTAL);
       bzip2_compress_device(c, (const u8*)d_in, n, level, (u8*)d_out, out_cap, out_n, 0, (size_t)-1, 0, true, nullptr, nullptr, nullptr);
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     c.collect();
     c.stats.raw_bytes = n; c.stats.comp_bytes = *out_n;
     return 0;
@@ -288,7 +337,7 @@ int b2_bzip2_compress(const uint8_t* in, size_t n, int level, uint8_t** out, siz
     try {
       StageScope tot(c, ST_TOTAL);
       DBuf<u8> din(c, n ? n : 1), dout(c, cap);
-      CUDA_CHECK(cudaStreamSynchronize(c.stream));  // the buffers are used from the copy streams as well
+      c.sync();  // the buffers are used from the copy streams as well
       cudaPointerAttributes pa;
       const bool pinned_in = n && cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeHost;
       cudaGetLastError();
@@ -297,7 +346,7 @@ int b2_bzip2_compress(const uint8_t* in, size_t n, int level, uint8_t** out, siz
       pinned_release(host);
       throw;
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     c.collect();
     c.stats.raw_bytes = n; c.stats.comp_bytes = produced;
     *out = (uint8_t*)host; *out_n = produced;
@@ -312,7 +361,7 @@ int b2_bzip2_plan(const void* d_in, size_t n, int level, size_t* total_blocks) {
     c.reset_call();
     size_t dummy = 0;
     bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, total_blocks);
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     return 0;
   });
 }
@@ -326,7 +375,7 @@ int b2_dec_shard_open(const void* d_in, size_t n, int rank, int world, uint64_t*
       StageScope tot(c, ST_TOTAL);
       dec_shard_open(c, (const u8*)d_in, n, rank, world, info);
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     c.collect();
     return 0;
   });
@@ -359,7 +408,7 @@ int b2_bzip2_plan_spec(const void* d_in, size_t n, int level, int rank, int worl
     size_t dummy = 0;
     bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, nullptr, -1,
                           ((size_t)rank << 32) | (size_t)world, info);
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     return 0;
   });
 }
@@ -377,7 +426,7 @@ int b2_bzip2_encode_range_dev(const void* d_in, size_t n, int level, size_t firs
       StageScope tot(c, ST_TOTAL);
       bzip2_compress_device(c, (const u8*)d_in, n, level, (u8*)d_out, out_cap, &bytes, first, count, bit_phase, false, out_bits, &crcs, nullptr);
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     c.collect();
     if (block_crcs) for (size_t i = 0; i < crcs.size(); i++) block_crcs[i] = crcs[i];
     return 0;
@@ -406,10 +455,10 @@ static int decode_common(const uint8_t* in, size_t n, int multistream, bool sing
       StageScope s(c, ST_D2H);
       if (produced) CUDA_CHECK(cudaMemcpyAsync(host, dres, produced, cudaMemcpyDeviceToHost, c.stream));
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     if (dres) c.dfree(dres);
   }
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.sync();
   c.collect();
   c.stats.raw_bytes = produced; c.stats.comp_bytes = n;
   if (rc) return rc;
@@ -447,7 +496,7 @@ int b2_bzip2_decompress_dev(const void* d_in, size_t n, int multistream, void* d
       StageScope tot(c, ST_TOTAL);
       rc = bzip2_decompress_device(c, (const u8*)d_in, n, multistream, (u8*)d_out, out_cap, out_n, false, 0, nullptr, nullptr, nullptr);
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
     c.collect();
     c.stats.raw_bytes = *out_n; c.stats.comp_bytes = n;
     return rc;

@@ -380,8 +380,8 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
     k_text_score<<<1, 256, 0, c.stream>>>(h0, d_n, nblk, sc0);
     KLAUNCH(c); KCHECK();
     float sc = 0.f;
-    CUDA_CHECK(cudaMemcpyAsync(&sc, sc0, 4, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.to_host(&sc, sc0, 4);
+    c.sync();
     c.bwt_wide = sc > 0.5f;
     c.bwt_mode_known = true;
   }
@@ -416,9 +416,9 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   c.stats.bwt_bytes += n_total * (8 + 4 + 4);
   u32 M = 0;
   float score = 0.f;
-  CUDA_CHECK(cudaMemcpyAsync(&M, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaMemcpyAsync(&score, dscore, 4, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.to_host(&M, cnt, 4);
+  c.to_host(&score, dscore, 4);
+  c.sync();
   if (!c.bwt_wide_forced) c.bwt_wide = score > 0.5f;  // next batch of this call
 
   if (M > 0) {
@@ -437,7 +437,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
       k_gather<<<(M + 255) / 256, 256, 0, c.stream>>>(hcur, icur, M, rank, d_n, h, tiebreak, kin64, vin64);
       KLAUNCH(c); KCHECK();
       c.stats.bwt_bytes += (u64)M * (8 + 4 + 12);
-      CUDA_CHECK(cudaMemcpyAsync(dM, &M, 4, cudaMemcpyHostToDevice, c.stream));
+      c.to_device(dM, &M, 4);
       radix_sort<u64>(c, kin64, vin64, kout64, vout64, dM, 1, 31, M, 0, npass, false, M);
       const u32 tiles = (M + RR_TILE - 1) / RR_TILE;
       CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
@@ -448,8 +448,8 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
       KLAUNCH(c); KCHECK();
       c.stats.bwt_bytes += (u64)M * (12 + 4 + 4 + 8);
       u32 Mn = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&Mn, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      c.to_host(&Mn, cnt, 4);
+      c.sync();
       if (tiebreak && Mn != 0) throw B2Error{-200, "internal error: suffix sort did not converge"};
       M = Mn;
       std::swap(hcur, hnext);

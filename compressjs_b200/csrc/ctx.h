@@ -36,6 +36,15 @@ struct Ctx {
   void dfree(void* p) {
     if (p) cudaFreeAsync(p, stream);
   }
+  // Make the stream-ordered pool hold at least `bytes` of physical memory (one big allocation, freed at once; the
+  // pool's release threshold keeps it).  Batches of different sizes then never have to grow the pool mid-call.
+  size_t warmed = 0;
+  void prewarm(size_t bytes) {
+    if (bytes <= warmed) return;
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, bytes, stream) == cudaSuccess) { cudaFreeAsync(p, stream); warmed = bytes; }
+    else cudaGetLastError();  // not fatal: the stages allocate what they need anyway
+  }
   template <typename T>
   T* dalloc_t(size_t count) { return (T*)dalloc(count * sizeof(T)); }
 
@@ -62,12 +71,24 @@ struct Ctx {
   void copy_end(cudaStream_t s, int which) { CUDA_CHECK(cudaEventRecord(copy_ev[which][1], s)); }
   void reset_call() {
     copy_used[0] = copy_used[1] = false;
+    fetches.clear();  // a call that failed half way may have left some behind
+    stage_used = 0;
     ev_used = 0;
     ev_tags.clear();
     bwt_mode_known = false;
     memset(&stats, 0, sizeof stats);
   }
   void collect();  // after the final sync: fold event pairs into stats
+
+  // small control transfers that bypass the copy engines (see api.cu); to_host results are valid after sync()
+  u8* stage_h = nullptr; u8* stage_d = nullptr;
+  size_t stage_cap = (size_t)8 << 20, stage_used = 0;
+  struct Fetch { void* dst; size_t off, bytes; };
+  std::vector<Fetch> fetches;
+  size_t stage_take(size_t bytes);
+  void to_device(void* ddst, const void* hsrc, size_t bytes);
+  void to_host(void* hdst, const void* dsrc, size_t bytes);
+  void sync();
 };
 
 enum Stage {

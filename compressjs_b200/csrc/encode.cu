@@ -330,13 +330,13 @@ struct EncSession {
     state.alloc(c, 4);
     flag.alloc(c, 1);
     u64 h_state[4] = {whole_file ? 32ull : (u64)bit_phase, 0, 0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(state, h_state, sizeof h_state, cudaMemcpyHostToDevice, c.stream));
+    c.to_device(state, h_state, sizeof h_state);
     CUDA_CHECK(cudaMemsetAsync(flag, 0, 4, c.stream));
     if (whole_file) {  // the header goes first: finished words are handed out while later batches are still encoding
       k_file_header<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), level);
       KLAUNCH(c); KCHECK();
     }
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sync();
   }
   void reserve(u32 nb) {
     if (nb <= cap_blocks) return;
@@ -355,6 +355,8 @@ struct EncSession {
     const u32 nbatches = (u32)((count + c.bwt_batch - 1) / c.bwt_batch);
     const u32 B = (u32)((count + nbatches - 1) / nbatches);
     reserve((u32)std::min<size_t>(B, count));
+    // all stage temporaries of one batch come to ~40 bytes per slot; size the pool for the batch class once
+    if (B > 74) c.prewarm((size_t)(B > 148 ? std::max<u32>(B, c.bwt_batch) : 148u) * 40 << SEG_SHIFT);
     const size_t done0 = all_crc.size();
     all_crc.resize(done0 + count);
     tr.resize(done0 + count);
@@ -386,12 +388,12 @@ struct EncSession {
         pack_batch(c, sym, dsel, dselmtf, dhb, dused, dpidx, dcrc, dbitoff, flag, nb, nmax + 1, reinterpret_cast<u32*>(d_out));
       }
       // per-block bookkeeping for the host (trace + CRCs)
-      CUDA_CHECK(cudaMemcpyAsync(hm.data(), dm, nb * 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(hp.data(), dpidx, nb * 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(hhb.data(), dhb, nb * sizeof(HuffBlk), cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(hoff.data(), dbitoff, nb * 8, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaMemcpyAsync(all_crc.data() + done0 + k0, dcrc, nb * 4, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      c.to_host(hm.data(), dm, nb * 4);
+      c.to_host(hp.data(), dpidx, nb * 4);
+      c.to_host(hhb.data(), dhb, nb * sizeof(HuffBlk));
+      c.to_host(hoff.data(), dbitoff, nb * 8);
+      c.to_host(all_crc.data() + done0 + k0, dcrc, nb * 4);
+      c.sync();
       for (u32 b = 0; b < nb; b++) {
         b2_block_trace& t = tr[done0 + k0 + b];
         const BlkInfo& bi = plan.h_blocks[first + k0 + b];
@@ -411,9 +413,9 @@ struct EncSession {
       k_file_trailer<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), state);
       KLAUNCH(c); KCHECK();
     }
-    CUDA_CHECK(cudaMemcpyAsync(h_state, state, sizeof h_state, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.to_host(h_state, state, sizeof h_state);
+    c.to_host(&h_flag, flag, 4);
+    c.sync();
     if (h_flag) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
     // whole files: trailer 48 + 32 bits, zero padded (lib/BitStream.js:68-73)
     *out_n = whole_file ? (size_t)((h_state[0] + 80 + 7) / 8) : (size_t)((h_state[0] + 7) / 8);
@@ -576,5 +578,5 @@ void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst) {
   if (nwords == 0) return;
   k_bitshift<<<(unsigned)((nwords + 255) / 256), 256, 0, c.stream>>>((const u32*)src, nbits, (u32)phase, (u32*)dst, nwords);
   KLAUNCH(c); KCHECK();
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.sync();
 }

@@ -675,8 +675,8 @@ u32 crc32_device(Ctx& c, const u8* d_p, size_t n) {
   DBuf<u64> pb(c, 1);
   DBuf<u32> acc(c, 2), out(c, 1);
   u64 zero = 0;
-  CUDA_CHECK(cudaMemcpyAsync(db, &bi, sizeof bi, cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemcpyAsync(pb, &zero, 8, cudaMemcpyHostToDevice, c.stream));
+  c.to_device(db, &bi, sizeof bi);
+  c.to_device(pb, &zero, 8);
   CUDA_CHECK(cudaMemsetAsync(acc, 0, 8, c.stream));
   const u64 pieces = crc_piece_count(0, n, (u32)((size_t)d_p & (CRC_PIECE - 1)));
   if (pieces) {
@@ -686,8 +686,8 @@ u32 crc32_device(Ctx& c, const u8* d_p, size_t n) {
   k_crc_final<<<1, 32, 0, c.stream>>>(d_p, db, 0, 1, acc, out);
   KLAUNCH(c); KCHECK();
   u32 h = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&h, out, 4, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.to_host(&h, out, 4);
+  c.sync();
   return h;
 }
 
@@ -715,8 +715,8 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     KLAUNCH(c); KCHECK();
   }
   u64 wtotal = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&wtotal, plan.tile_prefix.p + ntiles, 8, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.to_host(&wtotal, plan.tile_prefix.p + ntiles, 8);
+  c.sync();
   plan.total_guess = (size_t)((wtotal + BS - 1) / BS);
   if (tiles_only) return;
   u32 maxblocks = (u32)(n / ((u64)BS * 4 / 5) + 2);
@@ -736,8 +736,8 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     k_rle_blocks<<<P, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, 0, total);
     KLAUNCH(c); KCHECK();
     std::vector<u32> cut(P);
-    CUDA_CHECK(cudaMemcpyAsync(cut.data(), dnb, 4 * P, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.to_host(cut.data(), dnb, 4 * P);
+    c.sync();
     bool ok = true;
     for (u32 r = 0; r + 1 < P && ok; r++) ok = cut[r] == (u32)((u64)(r + 1) * total / P) - (u32)((u64)r * total / P);
     const u32 last_first = (u32)((u64)(P - 1) * total / P);
@@ -745,8 +745,8 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     if (ok) {
       const u32 nb = last_first + cut[P - 1];
       plan.h_blocks.resize(nb);
-      CUDA_CHECK(cudaMemcpyAsync(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb, cudaMemcpyDeviceToHost, c.stream));
-      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      c.to_host(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb);
+      c.sync();
       ok = plan.h_blocks[0].s == 0 && plan.h_blocks[nb - 1].e == n;
       for (u32 k = 0; k + 1 < nb && ok; k++) ok = plan.h_blocks[k].e == plan.h_blocks[k + 1].s;
       if (ok) { plan.nblocks = nb; return; }
@@ -757,12 +757,12 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
   k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, u_start, 0);
   KLAUNCH(c); KCHECK();
   u32 nb = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&nb, dnb, 4, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.to_host(&nb, dnb, 4);
+  c.sync();
   plan.nblocks = nb;
   plan.h_blocks.resize(nb);
-  if (nb) CUDA_CHECK(cudaMemcpyAsync(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb, cudaMemcpyDeviceToHost, c.stream));
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  if (nb) c.to_host(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb);
+  c.sync();
 }
 void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) { rle1_plan_ex(c, d_in, n, level, plan, -1, 0, false); }
 void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc) {
@@ -780,9 +780,9 @@ void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, si
   tbase[count] = tt; pbase[count] = pp;
   DBuf<u64> dtb(c, count + 1), dpb(c, count + 1);
   DBuf<u32> acc(c, 2 * count);
-  CUDA_CHECK(cudaMemcpyAsync(dtb, tbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemcpyAsync(dpb, pbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
-  CUDA_CHECK(cudaMemcpyAsync(d_n, hn.data(), 4 * count, cudaMemcpyHostToDevice, c.stream));
+  c.to_device(dtb, tbase.data(), 8 * (count + 1));
+  c.to_device(dpb, pbase.data(), 8 * (count + 1));
+  c.to_device(d_n, hn.data(), 4 * count);
   CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * count, c.stream));
   k_rle_emit<<<(unsigned)tt, RT_THREADS, 0, c.stream>>>(d_in, n, plan.tile_carry, plan.tile_prefix, plan.blocks, (u32)first, (u32)count, dtb, d_T);
   KLAUNCH(c); KCHECK();
@@ -790,8 +790,6 @@ void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, si
   KLAUNCH(c); KCHECK();
   k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d_in, plan.blocks, (u32)first, (u32)count, acc, d_crc);
   KLAUNCH(c); KCHECK();
-  // tbase/pbase/hn are pageable host vectors: make sure the async copies are done before they die
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
 }
 
 // CRC32 of arbitrary byte ranges [s,e) of one device buffer (decoder: per-block CRC of the output).
@@ -809,7 +807,7 @@ void crc_ranges(Ctx& c, const u8* d_data, const BlkInfo* d_ranges, const std::ve
   pbase[count] = pp;
   DBuf<u64> dpb(c, count + 1);
   DBuf<u32> acc(c, 2 * count);
-  CUDA_CHECK(cudaMemcpyAsync(dpb, pbase.data(), 8 * (count + 1), cudaMemcpyHostToDevice, c.stream));
+  c.to_device(dpb, pbase.data(), 8 * (count + 1));
   CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * count, c.stream));
   if (pp) {
     k_crc_pieces<<<(unsigned)((pp + 255) / 256), 256, 0, c.stream>>>(d_data, d_ranges, 0, (u32)count, dpb, pp, acc);
@@ -817,5 +815,5 @@ void crc_ranges(Ctx& c, const u8* d_data, const BlkInfo* d_ranges, const std::ve
   }
   k_crc_final<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d_data, d_ranges, 0, (u32)count, acc, d_crc_out);
   KLAUNCH(c); KCHECK();
-  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.sync();
 }
