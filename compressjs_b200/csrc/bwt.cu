@@ -315,6 +315,126 @@ k_rerank_init(const u64* __restrict__ rec, const u8* __restrict__ T, u32* __rest
   }
 }
 
+// Sparse-tie path (batches whose 4-byte prefixes rarely collide): one pass over the sorted records emits the
+// BWT column for every position AND compacts the few suffixes that still share their prefix with a neighbour
+// (in sorted order, with their group head) -- no rank array, no SA.  k_resolve_direct then orders each small
+// group by comparing the rotations' next bytes and rewrites the group's slice of the column.
+__global__ void __launch_bounds__(RR_THREADS)
+k_emit_detect(const u64* __restrict__ rec, const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u8* __restrict__ U,
+              u32* __restrict__ pidx, u32* __restrict__ next_head, u32* __restrict__ next_idx, u32* next_count, u32* ticket, u64* st_new,
+              u64* st_cnt, u32 ntiles) {
+  __shared__ u32 sk[RR_TILE + RR_TILE / 32 + 2];
+  __shared__ u32 sg[RR_TILE + RR_TILE / 32 + 2];
+  __shared__ u32 ws[RR_THREADS / 32 + 1];
+  __shared__ u32 s_tile, s_cn, s_cc, s_prev, s_next;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 b = tile / tps, lt = tile - b * tps;
+  const u32 n = seg_n[b];
+  const u32 start = lt * RR_TILE;
+  const u32 cnt = start < n ? min((u32)RR_TILE, n - start) : 0u;
+  const size_t base = ((size_t)b << SEG_SHIFT) + start;
+  const u8* Tb = T + ((size_t)b << SEG_SHIFT);
+  for (u32 j = tid; j < cnt; j += RR_THREADS) {
+    const u64 rv = rec[base + j];
+    sk[RI_PAD(j)] = (u32)(rv >> 32);
+    sg[RI_PAD(j)] = (u32)rv;
+    const u32 i = (u32)rv & SEG_MASK;
+    U[base + j] = Tb[i ? i - 1 : n - 1];
+    if (i == 0) pidx[b] = start + j;
+  }
+  if (tid == 0 && cnt) {
+    s_prev = start ? (u32)(rec[base - 1] >> 32) : 0u;
+    s_next = (start + cnt < n) ? (u32)(rec[base + cnt] >> 32) : 0u;
+  }
+  __syncthreads();
+  u32 vn[RR_ITEMS], nc[RR_ITEMS];
+  u32 mn = 0, cs = 0;
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; j++) {
+    const u32 p = tid * RR_ITEMS + j;
+    vn[j] = 0; nc[j] = 0;
+    if (p < cnt) {
+      const u32 k = sk[RI_PAD(p)];
+      const bool hasprev = p > 0 || start > 0;
+      const u32 kp = p > 0 ? sk[RI_PAD(p - 1)] : s_prev;
+      const bool hasnext = (p + 1 < cnt) || (start + cnt < n);
+      const u32 kn = (p + 1 < cnt) ? sk[RI_PAD(p + 1)] : s_next;
+      const bool nh = !hasprev || kp != k;
+      const bool single = nh && (!hasnext || kn != k);
+      vn[j] = nh ? start + p + 1 : 0u;
+      nc[j] = single ? 0u : 1u;
+      mn = max(mn, vn[j]); cs += nc[j];
+    }
+  }
+  u32 tot_n, tot_c;
+  const u32 ex_n = block_excl_max_u32(mn, ws, &tot_n);
+  const u32 ex_c = block_excl_add<RR_THREADS, u32>(cs, ws, &tot_c);
+  {
+    const u32 w = tid >> 5;
+    if (w == 0 && cnt) { u32 r = lookback_warp(st_new + (size_t)b * tps, lt, tot_n, OpMax()); if (lane_id() == 0) s_cn = r; }
+    else if (w == 1) { u32 r = lookback_warp(st_cnt, tile, tot_c, OpAdd()); if (lane_id() == 0) s_cc = r; }
+  }
+  __syncthreads();
+  if (tile == ntiles - 1 && tid == 0) *next_count = s_cc + tot_c;
+  if (cnt == 0) return;
+  u32 run_n = max(s_cn, ex_n), run_c = s_cc + ex_c;
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; j++) {
+    const u32 p = tid * RR_ITEMS + j;
+    if (p < cnt) {
+      run_n = max(run_n, vn[j]);
+      if (nc[j]) { next_head[run_c] = (b << SEG_SHIFT) | (run_n - 1); next_idx[run_c] = sg[RI_PAD(p)]; }
+      run_c += nc[j];
+    }
+  }
+}
+
+#define RD_MAXGROUP 16  // larger groups and rotations equal over RD_DEPTH more bytes go to the doubling rounds
+#define RD_DEPTH 64
+__global__ void k_resolve_direct(const u32* __restrict__ head, const u32* __restrict__ idx, u32 M, const u8* __restrict__ T,
+                                 const u32* __restrict__ seg_n, u32 h0, u8* __restrict__ U, u32* __restrict__ pidx, u32* fail) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= M) return;
+  const u32 hd = head[q];
+  if (q > 0 && head[q - 1] == hd) return;  // one thread per group: its first member
+  u32 mem[RD_MAXGROUP];
+  u32 cnt = 0;
+  while (q + cnt < M && head[q + cnt] == hd) {
+    if (cnt == RD_MAXGROUP) { atomicOr(fail, 1u); return; }
+    mem[cnt] = idx[q + cnt] & SEG_MASK;
+    cnt++;
+  }
+  const u32 b = hd >> SEG_SHIFT, n = seg_n[b];
+  const u8* Tb = T + ((size_t)b << SEG_SHIFT);
+  // insertion sort; rotations compare by their bytes from h0 on (the first h0 bytes are equal inside a group)
+  for (u32 a = 1; a < cnt; a++) {
+    const u32 x = mem[a];
+    u32 pos = a;
+    while (pos > 0) {
+      const u32 y = mem[pos - 1];
+      int less = -1;  // x < y ?
+      for (u32 d = h0; d < h0 + RD_DEPTH; d += 4) {
+        const u32 wx = word_at(Tb, n, x, d), wy = word_at(Tb, n, y, d);
+        if (wx != wy) { less = wx < wy ? 1 : 0; break; }
+      }
+      if (less < 0) { atomicOr(fail, 1u); return; }
+      if (!less) break;
+      mem[pos] = y;
+      pos--;
+    }
+    mem[pos] = x;
+  }
+  const u32 p0 = hd & SEG_MASK;
+  for (u32 r = 0; r < cnt; r++) {
+    const u32 i = mem[r];
+    U[((size_t)b << SEG_SHIFT) + p0 + r] = Tb[i ? i - 1 : n - 1];
+    if (i == 0) pidx[b] = p0 + r;
+  }
+}
+
 // key64 = head << 20 | rank of the rotation h further on (or n-1-i for the final tie-break).
 __global__ void k_gather(const u32* __restrict__ head, const u32* __restrict__ idx, u32 M, const u32* __restrict__ rank,
                          const u32* __restrict__ seg_n, u32 h, int tiebreak, u64* __restrict__ key_out, u32* __restrict__ val_out) {
@@ -357,7 +477,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   const u32 nslots = nblk << SEG_SHIFT;
   DBuf<u64> recA(c, nslots), recB(c, nslots);
   DBuf<u32> saBuf(c, nslots), rank(c, nslots);
-  DBuf<u32> headA(c, n_total), idxA(c, n_total), cnt(c, 1), ticket(c, 1);
+  DBuf<u32> headA(c, n_total), idxA(c, n_total), cnt(c, 2), ticket(c, 1);
   const u32 rr_tiles_init = (nslots + RR_TILE - 1) / RR_TILE;
   DBuf<u64> st(c, (size_t)3 * rr_tiles_init);
   u64 *kin = recA, *kout = recB;
@@ -401,12 +521,39 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
     radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist.p);
   }
   u32* SA = saBuf;
+  const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;
+  const u32 ri_tiles = ri_tps * nblk;  // <= rr_tiles_init
+  if (!wide) {
+    // sparse-tie path: emit the column straight from the sorted records and order the few tied groups directly
+    CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
+    CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
+    CUDA_CHECK(cudaMemsetAsync(cnt, 0, 8, c.stream));  // cnt[0] = tied suffixes, cnt[1] = "needs the rounds" flag
+    k_emit_detect<<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, d_T, d_n, ri_tps, d_U, d_pidx, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init,
+                                                         ri_tiles);
+    KLAUNCH(c); KCHECK();
+    c.stats.bwt_bytes += n_total * (8 + 2);
+    u32 Mt = 0;
+    float score = 0.f;
+    c.to_host(&Mt, cnt, 4);
+    c.to_host(&score, dscore, 4);
+    c.sync();
+    if (!c.bwt_wide_forced) c.bwt_wide = score > 0.5f;  // next batch of this call
+    u32 failed = 0;
+    if (Mt > n_total / 8) failed = 1;
+    else if (Mt) {
+      k_resolve_direct<<<(Mt + 127) / 128, 128, 0, c.stream>>>(headA, idxA, Mt, d_T, d_n, 4, d_U, d_pidx, cnt.p + 1);
+      KLAUNCH(c); KCHECK();
+      c.stats.bwt_bytes += (u64)Mt * 80;
+      c.to_host(&failed, cnt.p + 1, 4);
+      c.sync();
+    }
+    if (!failed) return;
+    // long repeats after all: fall through to the rank-based rounds (the sorted records are still intact)
+  }
   CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
   CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
   CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4, c.stream));
   {
-    const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;
-    const u32 ri_tiles = ri_tps * nblk;  // <= rr_tiles_init
     if (wide)
       k_rerank_init<true><<<ri_tiles, RR_THREADS, 0, c.stream>>>(kin, d_T, SA, d_n, ri_tps, rank, headA, idxA, cnt, ticket, st.p, st.p + rr_tiles_init, ri_tiles);
     else
