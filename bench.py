@@ -54,7 +54,7 @@ class ClockSampler:
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -63,9 +63,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (perf_counter) -- the sampler is started before the warm-up because
+        nvidia-smi needs about a second to deliver its first line."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -73,6 +75,12 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
+        inside = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for (_, r) in self.rows], "whole run (no sample fell into the timed region)"
+        self.rows = inside
+        self.window = window
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
         mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -83,7 +91,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "window": self.window}
 
 
 def peaks():
@@ -234,11 +242,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident (HBM) arm ----
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
     barrier()
     t0 = time.perf_counter()
     agg = {}
@@ -255,7 +263,7 @@ def main():
     wall = time.perf_counter() - t0
     if world > 1:
         dev_ms = ev0.elapsed_time(ev1)  # includes the NCCL gather and the assembly on rank 0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t0, t0 + wall) if rank == 0 else None
     comp_bytes = state["comp"]
 
     # device time: max over ranks (events on the library's launching stream)

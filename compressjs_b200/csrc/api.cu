@@ -10,13 +10,15 @@
 #include "ctx.h"
 
 // stages implemented in the other translation units
-void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx);
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel = false,
+                       u32* d_sa_out = nullptr);
 u32 crc32_device(Ctx& c, const u8* d_p, size_t n);
 void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n,
                            size_t first_block, size_t block_count, int bit_phase, bool whole_file, u64* out_bits,
                            std::vector<u32>* crcs_out, size_t* total_blocks, long long spec_first = -2, size_t spec_count = 0,
                            u64* spec_range = nullptr);
 void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst);
+void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out);
 void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, u8* d_out, size_t out_cap, u8* h_out, size_t* out_n,
                          bool pinned_in);
 void dec_shard_open(Ctx& c, const u8* d_in, size_t n, int rank, int world, u64* info);
@@ -286,6 +288,69 @@ int32_t b2_bwt_cyclic(const uint8_t* T, uint8_t* U, int32_t n) {
   int32_t pidx = 0;
   int rc = b2_bwt_cyclic_batch(T, U, &off, &n, &pidx, 1);
   return rc < 0 ? rc : pidx;
+}
+
+// suffix array / sentinel BWT of one string (<= 2^20 - 2 bytes, the slot size of the block pipeline)
+static int sentinel_sort(const uint8_t* T, int32_t n, int32_t* SA, uint8_t* U, int32_t* pidx1) {
+  return guarded([&]() {
+    if (n < 2 || (uint32_t)n > SEG_SIZE - 2) throw B2Error{B2_ERR_BAD_ARG, "length out of range (2..1048574)"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    {
+      StageScope tot(c, ST_TOTAL);
+      DBuf<u8> dT(c, SEG_SIZE), dU(c, SEG_SIZE);
+      DBuf<u32> dn(c, 1), dp(c, 1), dsa(c, SEG_SIZE);
+      u32 hn = (u32)n, hp = 0;
+      CUDA_CHECK(cudaMemcpyAsync(dT.p, T, n, cudaMemcpyHostToDevice, c.stream));
+      c.to_device(dn, &hn, 4);
+      CUDA_CHECK(cudaMemsetAsync(dp, 0, 4, c.stream));
+      bwt_forward_batch(c, dT, U ? dU.p : nullptr, dn, &hn, 1, dp, true, SA ? dsa.p : nullptr);
+      c.to_host(&hp, dp, 4);
+      if (SA) CUDA_CHECK(cudaMemcpyAsync(SA, dsa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+      if (U) CUDA_CHECK(cudaMemcpyAsync(U, dU.p, n, cudaMemcpyDeviceToHost, c.stream));
+      c.sync();
+      if (pidx1) *pidx1 = (int32_t)hp;
+    }
+    c.sync();
+    c.collect();
+    return 0;
+  });
+}
+int b2_suffixsort(const uint8_t* T, int32_t* SA, int32_t n) {
+  if (n <= 1) {  // lib/BWT.js:307-310
+    if (n == 1) SA[0] = 0;
+    return 0;
+  }
+  return sentinel_sort(T, n, SA, nullptr, nullptr);
+}
+int32_t b2_bwt_sentinel(const uint8_t* T, uint8_t* U, int32_t n) {
+  if (n <= 1) {  // lib/BWT.js:332-335
+    if (n == 1) U[0] = T[0];
+    return n < 0 ? 0 : n;
+  }
+  int32_t p = 0;
+  int rc = sentinel_sort(T, n, nullptr, U, &p);
+  return rc < 0 ? rc : p;
+}
+int b2_bwt_inverse(const uint8_t* L, uint8_t* out, int32_t n, int32_t pidx) {
+  if (n <= 0) return 0;
+  if (n == 1) { out[0] = L[0]; return 0; }
+  return guarded([&]() {
+    if ((uint32_t)n > SEG_SIZE - 2) throw B2Error{B2_ERR_BAD_ARG, "length out of range (0..1048574)"};
+    if (pidx < 0 || pidx > n) throw B2Error{B2_ERR_BAD_ARG, "primary index out of range"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    {
+      StageScope tot(c, ST_TOTAL);
+      DBuf<u8> dL(c, n), dO(c, n);
+      CUDA_CHECK(cudaMemcpyAsync(dL.p, L, n, cudaMemcpyHostToDevice, c.stream));
+      bwt_inverse_sentinel(c, dL, (u32)n, (u32)pidx, dO);
+      CUDA_CHECK(cudaMemcpyAsync(out, dO.p, n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    c.sync();
+    c.collect();
+    return 0;
+  });
 }
 
 uint32_t b2_crc32_bzip2(const uint8_t* p, size_t n) {

@@ -28,7 +28,7 @@
 #define BK_THREADS 256
 #define BK_ITEMS 16
 __global__ void __launch_bounds__(BK_THREADS)
-k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u64* __restrict__ rec, u32* __restrict__ hist, u32 koff) {
+k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u64* __restrict__ rec, u32* __restrict__ hist, u32 koff, int sentinel) {
   __shared__ u32 h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -42,6 +42,13 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
   for (int k = 0; k < BK_ITEMS; k++) {
     const u32 i = start + k * BK_THREADS + threadIdx.x;
     if (i < n) {
+      if (sentinel) {
+        // suffixes, not rotations (lib/BWT.js:305-321): past the end the key is padded with zeros; a suffix that
+        // ends inside its key ties with longer ones and is placed first by the rounds (its successor ranks 0)
+        const u32 c0 = t[i], c1 = i + 1 < n ? t[i + 1] : 0u, c2 = i + 2 < n ? t[i + 2] : 0u, c3 = i + 3 < n ? t[i + 3] : 0u;
+        ko[i] = ((u64)((c0 << 24) | (c1 << 16) | (c2 << 8) | c3) << 32) | ((b << SEG_SHIFT) | i);
+        continue;
+      }
       u32 i0 = i + koff; if (i0 >= n) i0 %= n;
       u32 i1 = i0 + 1; if (i1 >= n) i1 -= n;
       u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
@@ -437,13 +444,15 @@ __global__ void k_resolve_direct(const u32* __restrict__ head, const u32* __rest
 
 // key64 = head << 20 | rank of the rotation h further on (or n-1-i for the final tie-break).
 __global__ void k_gather(const u32* __restrict__ head, const u32* __restrict__ idx, u32 M, const u32* __restrict__ rank,
-                         const u32* __restrict__ seg_n, u32 h, int tiebreak, u64* __restrict__ key_out, u32* __restrict__ val_out) {
+                         const u32* __restrict__ seg_n, u32 h, int tiebreak, u64* __restrict__ key_out, u32* __restrict__ val_out,
+                         int sentinel) {
   u32 q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= M) return;
   const u32 g = idx[q];
   const u32 b = g >> SEG_SHIFT, i = g & SEG_MASK, n = seg_n[b];
   u32 r2;
   if (tiebreak) r2 = n - 1 - i;
+  else if (sentinel) r2 = i + h < n ? rank[(b << SEG_SHIFT) | (i + h)] + 1 : 0u;  // the empty suffix sorts first
   else r2 = rank[(b << SEG_SHIFT) | ((i + h) % n)];
   key_out[q] = ((u64)head[q] << SEG_SHIFT) | r2;
   val_out[q] = g;
@@ -460,6 +469,29 @@ __global__ void k_emit(const u32* __restrict__ SA, const u8* __restrict__ T, con
   if (i == 0) pidx[b] = p;
 }
 
+// Sentinel mode outputs: the suffix array itself (lib/BWT.js:305-321) and the BWT of lib/BWT.js:328-350:
+// U[0] = T[n-1], then the characters before the suffixes in order with suffix 0 left out; pidx = its rank + 1.
+__global__ void k_emit_sa(const u32* __restrict__ SA, const u32* __restrict__ seg_n, u32 nslots, u32* __restrict__ sa_out, u32* __restrict__ pidx) {
+  u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nslots) return;
+  const u32 b = q >> SEG_SHIFT, p = q & SEG_MASK, n = seg_n[b];
+  if (p >= n) return;
+  const u32 i = SA[q] & SEG_MASK;
+  if (sa_out) sa_out[q] = i;
+  if (i == 0) pidx[b] = p + 1;
+}
+__global__ void k_emit_sentinel(const u32* __restrict__ SA, const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 nslots,
+                                const u32* __restrict__ pidx, u8* __restrict__ U) {
+  u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nslots) return;
+  const u32 b = q >> SEG_SHIFT, p = q & SEG_MASK, n = seg_n[b];
+  if (p >= n) return;
+  const size_t base = (size_t)b << SEG_SHIFT;
+  const u32 i = SA[q] & SEG_MASK, r0 = pidx[b] - 1;
+  if (p == 0) U[base] = T[base + n - 1];
+  if (i != 0) U[base + p + 1 - (p > r0 ? 1u : 0u)] = T[base + i - 1];
+}
+
 // host side: radix_sort<> lives in radix_host.cuh
 static u32 bits_for(u32 maxval) {  // number of bits needed to represent values 0..maxval
   u32 b = 0;
@@ -469,7 +501,7 @@ static u32 bits_for(u32 maxval) {  // number of bits needed to represent values 
 
 // Forward cyclic BWT of `nblk` blocks in the slot layout.  d_T/d_U: u8[nblk << 20];
 // d_n: device u32[nblk]; h_n: host copy; d_pidx: device u32[nblk].
-void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx) {
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel, u32* d_sa_out) {
   if (nblk == 0) return;
   u32 n_max = 0; u64 n_total = 0;
   for (u32 b = 0; b < nblk; b++) { n_max = h_n[b] > n_max ? h_n[b] : n_max; n_total += h_n[b]; }
@@ -490,7 +522,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   // rounds start: bytes 4..7 first, then a stable sort on bytes 0..3 -- two cheap keys-only sorts replace
   // the h=4 round over nearly all suffixes.  The mode of a batch follows the score of the previous batch
   // of the same call (first batch: 4-byte mode unless B2_BWT_PREFIX8=1), so no extra host sync is needed.
-  if (!c.bwt_wide_forced && !c.bwt_mode_known) {
+  if (!sentinel && !c.bwt_wide_forced && !c.bwt_mode_known) {
     // first batch of a call: decide from the byte histogram (one cheap extra pass over the text + one small sync)
     DBuf<u32> h0(c, (size_t)nblk * 256);
     DBuf<float> sc0(c, 1);
@@ -505,15 +537,16 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
     c.bwt_wide = sc > 0.5f;
     c.bwt_mode_known = true;
   }
-  bool wide = c.bwt_wide;
-  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist, wide ? 4u : 0u);
+  const bool wide = sentinel ? false : c.bwt_wide;
+  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist, wide ? 4u : 0u, sentinel ? 1 : 0);
   KLAUNCH(c); KCHECK();
   c.stats.bwt_bytes += n_total * 9;
   DBuf<float> dscore(c, 1);
   k_text_score<<<1, 256, 0, c.stream>>>(bytehist, d_n, nblk, dscore);
   KLAUNCH(c); KCHECK();
   // keys-only sort of the packed records on their upper 32 bits
-  radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist.p);
+  // (sentinel mode: the zero padding breaks the "byte histogram = digit histogram" identity, so the sort counts its own)
+  radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, sentinel ? nullptr : bytehist.p);
   if (wide) {
     k_rekey<<<(nslots + 255) / 256, 256, 0, c.stream>>>(d_T, d_n, nslots, kin);
     KLAUNCH(c); KCHECK();
@@ -523,7 +556,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   u32* SA = saBuf;
   const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;
   const u32 ri_tiles = ri_tps * nblk;  // <= rr_tiles_init
-  if (!wide) {
+  if (!wide && !sentinel) {
     // sparse-tie path: emit the column straight from the sorted records and order the few tied groups directly
     CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)3 * rr_tiles_init * 8, c.stream));
     CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
@@ -581,7 +614,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
       const int tiebreak = h >= n_max ? 1 : 0;
       rounds++;
       u64* kin64 = k64A; u64* kout64 = k64B; u32* vin64 = v64A; u32* vout64 = v64B;
-      k_gather<<<(M + 255) / 256, 256, 0, c.stream>>>(hcur, icur, M, rank, d_n, h, tiebreak, kin64, vin64);
+      k_gather<<<(M + 255) / 256, 256, 0, c.stream>>>(hcur, icur, M, rank, d_n, h, tiebreak, kin64, vin64, sentinel ? 1 : 0);
       KLAUNCH(c); KCHECK();
       c.stats.bwt_bytes += (u64)M * (8 + 4 + 12);
       c.to_device(dM, &M, 4);
@@ -604,6 +637,15 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
       if (h < (1u << 30)) h <<= 1;
     }
     if (rounds > c.stats.bwt_rounds) c.stats.bwt_rounds = rounds;
+  }
+  if (sentinel) {
+    k_emit_sa<<<(nslots + 255) / 256, 256, 0, c.stream>>>(SA, d_n, nslots, d_sa_out, d_pidx);
+    KLAUNCH(c); KCHECK();
+    if (d_U) {
+      k_emit_sentinel<<<(nslots + 255) / 256, 256, 0, c.stream>>>(SA, d_T, d_n, nslots, d_pidx, d_U);
+      KLAUNCH(c); KCHECK();
+    }
+    return;
   }
   k_emit<<<(nslots + 255) / 256, 256, 0, c.stream>>>(SA, d_T, d_n, nslots, d_U, d_pidx);
   KLAUNCH(c); KCHECK();

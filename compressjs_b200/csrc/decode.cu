@@ -127,6 +127,23 @@ struct HdecWarp {
   u32 c_cnt, c_pos, c_flag;
 };
 
+// code longer than the LUT covers: the reference's limit search (lib/Bzip2.js:296-306); returns sym | len << 9,
+// 0 when no code of the table starts with these 20 bits
+__device__ __noinline__ u32 hdec_slow(const HdecWarp& s, u32 g, u32 bits20, int minLen, int maxLen) {
+  int i = minLen;
+  int j = (int)(bits20 >> (20 - i));
+  for (;;) {
+    if (i > maxLen) return 0;                                            // :299
+    if (j <= s.limit[g][i]) break;
+    i++;
+    if (i > 20) return 0;
+    j = (int)(bits20 >> (20 - i));
+  }
+  const int jj = j - s.base[g][i];
+  if (jj >= 0 && jj < HUFF_MAXSYM) return (u32)s.permute[g][jj] | ((u32)i << 9);  // :306
+  return 0;
+}
+
 __global__ void __launch_bounds__(HD_WARPS * 32)
 k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u32 first, u32 count, u32 dbuf_size, u8* __restrict__ sel_buf,
        u16* __restrict__ sym_out, CandRes* __restrict__ res) {
@@ -292,58 +309,51 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
           __syncwarp();
         }
         const u32 shiftbase = (u32)(P & 31);
+        const u32 nk = wlim / 32;  // window steps of this round (warp uniform)
+        u32 j1r[HD_WIN / 32], j2r[HD_WIN / 32];  // this lane's jump targets, kept in registers between the passes
         {
-          // lane l decodes offsets l, l+32, ...: same bit shift every time, one new word per step
+          // lane l decodes offsets l, l+32, ...: same bit shift every time, one new word per step.  Fully unrolled
+          // so that the shared-memory loads of all steps are in flight together.
           const u32 sh = (shiftbase + lane) & 31;
           const u32* wp = s.win + (u32)(w0 - stage_w0) + ((shiftbase + lane) >> 5);
           u32 hiw = wp[0];
-#pragma unroll 4
-          for (u32 k = 0; k < wlim / 32; k++) {
-            const u32 low = wp[k + 1];
-            const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
-            hiw = low;
-            u32 sym = 0, len = 0;
-            const u32 ent = lut[bits20 >> (20 - HD_LUT_BITS)];
-            if (ent) {
-              sym = ent & 511u; len = ent >> 9;
-            } else {
-              int i = minLen;
-              int j = (int)(bits20 >> (20 - i));
-              for (;;) {
-                if (i > maxLen) { i = 0; break; }                        // :299 -> marks "no code here"
-                if (j <= s.limit[g][i]) break;
-                i++;
-                if (i > 20) { i = 0; break; }
-                j = (int)(bits20 >> (20 - i));
-              }
-              if (i) {
-                const int jj = j - s.base[g][i];
-                if (jj >= 0 && jj < HUFF_MAXSYM) { sym = s.permute[g][jj]; len = (u32)i; }  // :306
-              }
+#pragma unroll
+          for (u32 k = 0; k < HD_WIN / 32; k++) {
+            if (k < nk) {
+              const u32 low = wp[k + 1];
+              const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
+              hiw = low;
+              u32 ent = lut[bits20 >> (20 - HD_LUT_BITS)];
+              if (!ent) ent = hdec_slow(s, g, bits20, minLen, maxLen);
+              const u32 o = lane + 32 * k, len = ent >> 9;
+              s.wsym[o] = (u16)(ent & 511u);
+              s.wlen[o] = (u8)len;
+              // J1[o] = o + len[o] (an offset without a code maps to itself, one beyond the window parks there)
+              j1r[k] = min(o + len, wlim + 31u);
+              s.J1[o] = (u16)j1r[k];
             }
-            s.wsym[lane + 32 * k] = (u16)sym;
-            s.wlen[lane + 32 * k] = (u8)len;
           }
         }
-        s.wlen[wlim + lane] = 0;   // everything behind the decoded window parks the chain
-        s.wsym[wlim + lane] = 0;
-        __syncwarp();
-        // jump tables: J1[o] = o + len[o] (an offset without a code, or beyond the window, maps to itself)
-        const u32 jn = (wlim + 32) / 32;
-        for (u32 k = 0; k < jn; k++) {
-          const u32 o = lane + 32 * k;
-          s.J1[o] = (u16)min(o + (u32)s.wlen[o], wlim + 31u);
+        {
+          // everything behind the decoded window parks the chain
+          const u32 o = wlim + lane;
+          s.wlen[o] = 0; s.wsym[o] = 0;
+          s.J1[o] = (u16)o; s.J2[o] = (u16)o; s.J4[o] = (u16)o;
         }
         __syncwarp();
-        for (u32 k = 0; k < jn; k++) {
-          const u32 o = lane + 32 * k;
-          s.J2[o] = s.J1[s.J1[o]];
-        }
+#pragma unroll
+        for (u32 k = 0; k < HD_WIN / 32; k++)
+          if (k < nk) j2r[k] = s.J1[j1r[k]];
+#pragma unroll
+        for (u32 k = 0; k < HD_WIN / 32; k++)
+          if (k < nk) s.J2[lane + 32 * k] = (u16)j2r[k];
         __syncwarp();
-        for (u32 k = 0; k < jn; k++) {
-          const u32 o = lane + 32 * k;
-          s.J4[o] = s.J2[s.J2[o]];
-        }
+#pragma unroll
+        for (u32 k = 0; k < HD_WIN / 32; k++)
+          if (k < nk) j1r[k] = s.J2[j2r[k]];
+#pragma unroll
+        for (u32 k = 0; k < HD_WIN / 32; k++)
+          if (k < nk) s.J4[lane + 32 * k] = (u16)j1r[k];
         __syncwarp();
         if (lane == 0) {
           // the only serial part: 13 dependent shared-memory loads cover 52 symbols
@@ -702,6 +712,64 @@ __global__ void k_ibwt_walk2(const u32* __restrict__ P, const CandRes* __restric
   }
 }
 
+static void dec_attr_once();
+
+// ---- BWT.unbwtransform (lib/BWT.js:352-363): inverse of the sentinel BWT ------------------------------
+// Reference walk: t = 0; for i = n-1..0: U[i] = T[t]; t = LF[t] + C[T[t]]; t += (t < pidx).  LF[t] + C[T[t]] is
+// the rank x of position t in the stable order by byte, i.e. the inverse of the sorted-position vector that one
+// radix pass produces.  P[t] = next(t) << 8 | T[t] feeds the same sampled-row walks as the bzip2 decoder; the
+// spare slot 2^20-1 holds the pseudo start entry (orig) whose successor is row 0.
+__global__ void k_unbwt_pack(const u8* __restrict__ L, const u32* __restrict__ sorted_pos, u32 n, u32 pidx, u32* __restrict__ P) {
+  const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x == 0) P[SEG_SIZE - 1] = 0;
+  if (x >= n) return;
+  const u32 t = sorted_pos[x] & SEG_MASK;
+  P[t] = ((x + (x < pidx ? 1u : 0u)) << 8) | L[t];
+}
+__global__ void k_unbwt_setup(CandRes* r, u32 n) {
+  r->status = 0; r->detail = 0; r->m = 0; r->orig = SEG_SIZE - 1; r->sym_total = 0; r->n = n; r->rawlen = n; r->pad = 0; r->endbit = 0;
+}
+__global__ void k_reverse_bytes(const u8* __restrict__ in, u32 n, u8* __restrict__ out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[n - 1 - i] = in[i];
+}
+static void dec_attr_once() {
+  static bool attr = false;
+  if (attr) return;
+  CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HdecWarp) * HD_WARPS)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_ibwt_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Seg) * IB_SEGS)));
+  attr = true;
+}
+// d_L, d_out: device buffers of n bytes; 2 <= n <= 2^20 - 2; 0 <= pidx <= n
+void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out) {
+  dec_attr_once();
+  DBuf<u32> keyA(c, SEG_SIZE), keyB(c, SEG_SIZE), valA(c, SEG_SIZE), valB(c, SEG_SIZE), dn(c, 1), nvis(c, 1);
+  DBuf<u8> tmp(c, SEG_SIZE);
+  DBuf<CandRes> res(c, 1);
+  DBuf<Seg> segs(c, IB_SEGS);
+  DBuf<Visit> visits(c, IB_VCAP);
+  c.to_device(dn, &n, 4);
+  k_ibwt_keys<<<(SEG_SIZE + 255) / 256, 256, 0, c.stream>>>(d_L, dn, SEG_SIZE, keyA);
+  KLAUNCH(c); KCHECK();
+  u32 *kin = keyA.p, *kout = keyB.p, *vin = valA.p, *vout = valB.p;
+  radix_sort<u32>(c, kin, vin, kout, vout, dn.p, 1, SEG_SHIFT, n, 0, 1, true, n);  // swaps the pairs: vin = sorted positions
+  u32* P = kout;  // the other key buffer is free now
+  CUDA_CHECK(cudaMemsetAsync(P, 0, (size_t)SEG_SIZE * 4, c.stream));  // rows >= n lead back to row 0: the walks stay in bounds
+  k_unbwt_pack<<<(n + 255) / 256, 256, 0, c.stream>>>(d_L, vin, n, pidx, P);
+  KLAUNCH(c); KCHECK();
+  k_unbwt_setup<<<1, 1, 0, c.stream>>>(res, n);
+  KLAUNCH(c); KCHECK();
+  k_ibwt_walk1<<<(IB_SEGS + 127) / 128, 128, 0, c.stream>>>(P, res, 1, segs);
+  KLAUNCH(c); KCHECK();
+  k_ibwt_chain<<<1, 128, sizeof(Seg) * IB_SEGS, c.stream>>>(P, res, 1, segs, visits, nvis);
+  KLAUNCH(c); KCHECK();
+  k_ibwt_walk2<<<(IB_VCAP + 127) / 128, 128, 0, c.stream>>>(P, res, 1, visits, nvis, tmp);
+  KLAUNCH(c); KCHECK();
+  k_reverse_bytes<<<(n + 255) / 256, 256, 0, c.stream>>>(tmp, n, d_out);
+  KLAUNCH(c); KCHECK();
+  c.sync();
+}
+
 // ---- RLE1 decode ------------------------------------------------------------------------------
 #define UR_THREADS 256
 #define UR_ITEMS 8
@@ -925,12 +993,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   // the per-block Huffman stage is one warp per block and latency bound: give it every block at once
   // (about 19 MB of scratch per block; 180 GB of HBM take thousands)
   const u32 DB = std::max(c.bwt_batch, 2048u);
-  static bool attr = false;
-  if (!attr) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HdecWarp) * HD_WARPS)));
-    CUDA_CHECK(cudaFuncSetAttribute(k_ibwt_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Seg) * IB_SEGS)));
-    attr = true;
-  }
+  dec_attr_once();
   if (nb) {
     const u32 nbm = (u32)std::min<size_t>(DB, nb);
     DBuf<u16> sym(c, (size_t)nbm << SEG_SHIFT);

@@ -22,7 +22,8 @@
 #include <vector>
 #include "enc.h"
 
-void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx);
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel = false,
+                       u32* d_sa_out = nullptr);
 
 // ---- bit writers (stream is MSB first; words are stored big-endian) ----------------------
 __device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }

@@ -98,6 +98,46 @@ static napi_value Bwtransform2(napi_env env, napi_callback_info info) {
   return r;
 }
 
+// suffixsort(T, SA /* Int32Array */, n) -> 0        (BWT.suffixsort, lib/BWT.js:305)
+static napi_value Suffixsort(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value argv[3];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* T; size_t tn; int32_t n = 0;
+  napi_typedarray_type ty; size_t len; void* sa; napi_value ab; size_t off;
+  if (!buf_arg(env, argv[0], &T, &tn)) return fail(env, B2_ERR_BAD_ARG);
+  if (napi_get_typedarray_info(env, argv[1], &ty, &len, &sa, &ab, &off) != napi_ok || ty != napi_int32_array) return fail(env, B2_ERR_BAD_ARG);
+  napi_get_value_int32(env, argv[2], &n);
+  if (n < 0 || (size_t)n > tn || (size_t)n > len) return fail(env, B2_ERR_BAD_ARG);
+  int rc = b2_suffixsort(T, (int32_t*)sa, n);
+  if (rc < 0) return fail(env, rc);
+  napi_value r; napi_create_int32(env, 0, &r);
+  return r;
+}
+// bwtransform(T, U, n) -> pidx + 1                   (BWT.bwtransform, lib/BWT.js:328; A is scratch, dropped)
+static napi_value Bwtransform(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value argv[3];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t *T, *U; size_t tn, un; int32_t n = 0;
+  if (!buf_arg(env, argv[0], &T, &tn) || !buf_arg(env, argv[1], &U, &un)) return fail(env, B2_ERR_BAD_ARG);
+  napi_get_value_int32(env, argv[2], &n);
+  int32_t p = b2_bwt_sentinel(T, (uint8_t*)U, n);
+  if (p < 0) return fail(env, p);
+  napi_value r; napi_create_int32(env, p, &r);
+  return r;
+}
+// unbwtransform(T, U, n, pidx)                       (BWT.unbwtransform, lib/BWT.js:352; LF is scratch, dropped)
+static napi_value Unbwtransform(napi_env env, napi_callback_info info) {
+  size_t argc = 4; napi_value argv[4];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t *T, *U; size_t tn, un; int32_t n = 0, pidx = 0;
+  if (!buf_arg(env, argv[0], &T, &tn) || !buf_arg(env, argv[1], &U, &un)) return fail(env, B2_ERR_BAD_ARG);
+  napi_get_value_int32(env, argv[2], &n);
+  napi_get_value_int32(env, argv[3], &pidx);
+  int rc = b2_bwt_inverse(T, (uint8_t*)U, n, pidx);
+  if (rc < 0) return fail(env, rc);
+  return nullptr;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
       {"compressFile", nullptr, CompressFile, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -105,6 +145,9 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"decompressBlock", nullptr, DecompressBlock, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"table", nullptr, Table, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"bwtransform2", nullptr, Bwtransform2, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"suffixsort", nullptr, Suffixsort, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"bwtransform", nullptr, Bwtransform, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"unbwtransform", nullptr, Unbwtransform, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;

@@ -48,5 +48,9 @@ Bzip2.table = function(input, callback, multistream) {
 
 var BWT = Object.create(null);
 BWT.bwtransform2 = function(T, U, n) { return native.bwtransform2(T, U, n); };
+// the sentinel family (lib/BWT.js:305-363); the reference's scratch arrays A / LF are accepted and ignored
+BWT.suffixsort = function(T, SA, n) { return native.suffixsort(T, SA, n); };
+BWT.bwtransform = function(T, U, A, n) { return native.bwtransform(T, U, n); };
+BWT.unbwtransform = function(T, U, LF, n, pidx) { native.unbwtransform(T, U, n, pidx); };
 
 module.exports = Object.freeze({ version: '0.0.1', Bzip2: Bzip2, BWT: BWT });

@@ -59,6 +59,15 @@ int32_t b2_bwt_cyclic(const uint8_t* T, uint8_t* U, int32_t n);
  * block k is T + offs[k], length lens[k] (each <= 900000); U gets the same layout;
  * pidx[k] receives each block's primary index. */
 int b2_bwt_cyclic_batch(const uint8_t* T, uint8_t* U, const uint64_t* offs, const int32_t* lens, int32_t* pidx, size_t nblocks);
+/* The sentinel ("string is terminated by EOF") family used by the reference's BWTC container.  One string of
+ * at most 2^20 - 2 = 1 048 574 bytes per call (the slot size of the block pipeline; BWTC blocks are <= 900 000).
+ * BWT.suffixsort(T, SA, n)                            lib/BWT.js:305-321 ; returns 0 */
+int b2_suffixsort(const uint8_t* T, int32_t* SA, int32_t n);
+/* BWT.bwtransform(T, U, A, n) -> pidx + 1             lib/BWT.js:328-350 (A is scratch in the reference) */
+int32_t b2_bwt_sentinel(const uint8_t* T, uint8_t* U, int32_t n);
+/* BWT.unbwtransform(T, U, LF, n, pidx)                lib/BWT.js:352-363 (L = the transformed string, pidx as
+ * returned by bwtransform; LF is scratch in the reference) */
+int b2_bwt_inverse(const uint8_t* L, uint8_t* out, int32_t n, int32_t pidx);
 /* CRC32 helper object of lib/CRC32.js:72-103 (bzip2 polynomial, MSB first) */
 uint32_t b2_crc32_bzip2(const uint8_t* p, size_t n);
 

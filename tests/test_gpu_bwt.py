@@ -48,3 +48,57 @@ def test_bwt_full_block_and_batch():
 def test_bwt_fixture_sample3():
     data = T.fixture("sample3.ref")  # highly repetitive: many doubling rounds
     assert T.native_bwt(data) == O.bwt_cyclic(data)
+
+
+# ---- the sentinel family: BWT.suffixsort / bwtransform / unbwtransform (lib/BWT.js:305-363) -------------------
+SENT_CASES = [b"ab", b"aa", b"ba", b"aaa", b"aaaa", b"abab", b"abcabcabc", b"mississippi", b"\x00", b"\x00\x00", b"\x00\x00\x00\x00\x00",
+              b"a\x00", b"\x00a\x00\x00", b"ab\x00\x00ab\x00", b"a" * 1000, b"ab" * 777, b"\x00" * 300 + b"\xff" * 300,
+              bytes(range(256)) * 3, b"abc" * 341 + b"abd", b"\x00\x01" * 50 + b"\x00"]
+
+
+def _sentinel_all(data):
+    from compressjs_b200 import BWT
+    n = len(data)
+    sa = np.zeros(n, dtype=np.int32)
+    assert BWT.suffixsort(data, sa, n) == 0
+    u = np.zeros(n, dtype=np.uint8)
+    p1 = BWT.bwtransform(data, u, None, n)
+    back = np.zeros(n, dtype=np.uint8)
+    BWT.unbwtransform(u, back, None, n, p1)
+    return sa, bytes(u), p1, bytes(back)
+
+
+@pytest.mark.parametrize("data", SENT_CASES)
+def test_sentinel_family_small(data):
+    sa, u, p1, back = _sentinel_all(data)
+    assert list(sa) == list(O.suffixsort(data))
+    assert (u, p1) == O.bwt_sentinel(data)
+    assert back == data
+    assert O.unbwt_sentinel(u, p1) == data
+
+
+def test_sentinel_bwtest_kats():
+    # test/bwtest.js:39-79 runs its vectors through bwtransform/unbwtransform as well (round trip) -- same here
+    for i, _, _ in KATS:
+        d = i.encode()
+        sa, u, p1, back = _sentinel_all(d)
+        assert back == d and (u, p1) == O.bwt_sentinel(d)
+
+
+@pytest.mark.parametrize("n,kind", [(1, "ascii"), (1000, "ascii"), (4097, "text"), (70000, "text"), (100000, "runs"), (300000, "ascii"),
+                                    (900000, "text"), (1048574, "ascii")])
+def test_sentinel_family_random(n, kind):
+    data = {"ascii": T.ascii_random, "text": T.texty, "runs": T.runs}[kind](n, seed=n + 17)
+    sa, u, p1, back = _sentinel_all(data)
+    assert back == data
+    assert (u, p1) == O.bwt_sentinel(data)
+    assert np.array_equal(sa, np.asarray(O.suffixsort(data), dtype=np.int32))
+
+
+def test_sentinel_limits():
+    from compressjs_b200 import BWT
+    big = np.zeros(1048575, dtype=np.uint8)
+    with pytest.raises(RuntimeError):
+        BWT.suffixsort(big, np.zeros(big.size, dtype=np.int32), big.size)
+    u = np.zeros(0, dtype=np.uint8)
+    assert BWT.bwtransform(b"", u, None, 0) == 0 and BWT.suffixsort(b"", np.zeros(0, dtype=np.int32), 0) == 0
