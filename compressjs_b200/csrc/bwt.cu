@@ -46,7 +46,7 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
         // suffixes, not rotations (lib/BWT.js:305-321): past the end the key is padded with zeros; a suffix that
         // ends inside its key ties with longer ones and is placed first by the rounds (its successor ranks 0)
         const u32 c0 = t[i], c1 = i + 1 < n ? t[i + 1] : 0u, c2 = i + 2 < n ? t[i + 2] : 0u, c3 = i + 3 < n ? t[i + 3] : 0u;
-        ko[i] = ((u64)((c0 << 24) | (c1 << 16) | (c2 << 8) | c3) << 32) | ((b << SEG_SHIFT) | i);
+        ko[i] = ((u64)((c0 << 24) | (c1 << 16) | (c2 << 8) | c3) << 32) | (((u32)t[i ? i - 1 : n - 1] << SEG_SHIFT) | i);
         continue;
       }
       u32 i0 = i + koff; if (i0 >= n) i0 %= n;
@@ -54,7 +54,9 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
       u32 i2 = i1 + 1; if (i2 >= n) i2 -= n;
       u32 i3 = i2 + 1; if (i3 >= n) i3 -= n;
       const u32 c0 = t[i0];
-      ko[i] = ((u64)((c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3]) << 32) | ((b << SEG_SHIFT) | i);
+      // low word: the byte BEFORE the rotation (its BWT output, so the emit pass needs no gather) and its position;
+      // the block is implied by the slot the record sits in (the sort never moves a record out of its segment)
+      ko[i] = ((u64)((c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3]) << 32) | (((u32)t[i ? i - 1 : n - 1] << SEG_SHIFT) | i);
       atomicAdd(&h[c0], 1u);
     }
   }
@@ -314,7 +316,7 @@ k_rerank_init(const u64* __restrict__ rec, const u8* __restrict__ T, u32* __rest
     if (p < cnt) {
       run_n = max(run_n, vn[j]);
       const u32 lastnew = run_n - 1;  // position (inside the block) of this suffix's group head
-      const u32 g = sg[RI_PAD(p)];
+      const u32 g = (b << SEG_SHIFT) | (sg[RI_PAD(p)] & SEG_MASK);
       rank[g] = lastnew;
       if (nc[j]) { next_head[run_c] = (b << SEG_SHIFT) | lastnew; next_idx[run_c] = g; }
       run_c += nc[j];
@@ -343,14 +345,12 @@ k_emit_detect(const u64* __restrict__ rec, const u8* __restrict__ T, const u32* 
   const u32 start = lt * RR_TILE;
   const u32 cnt = start < n ? min((u32)RR_TILE, n - start) : 0u;
   const size_t base = ((size_t)b << SEG_SHIFT) + start;
-  const u8* Tb = T + ((size_t)b << SEG_SHIFT);
   for (u32 j = tid; j < cnt; j += RR_THREADS) {
     const u64 rv = rec[base + j];
     sk[RI_PAD(j)] = (u32)(rv >> 32);
     sg[RI_PAD(j)] = (u32)rv;
-    const u32 i = (u32)rv & SEG_MASK;
-    U[base + j] = Tb[i ? i - 1 : n - 1];
-    if (i == 0) pidx[b] = start + j;
+    U[base + j] = (u8)((u32)rv >> SEG_SHIFT);  // the byte before the rotation travels in the record
+    if (((u32)rv & SEG_MASK) == 0) pidx[b] = start + j;
   }
   if (tid == 0 && cnt) {
     s_prev = start ? (u32)(rec[base - 1] >> 32) : 0u;
@@ -393,7 +393,7 @@ k_emit_detect(const u64* __restrict__ rec, const u8* __restrict__ T, const u32* 
     const u32 p = tid * RR_ITEMS + j;
     if (p < cnt) {
       run_n = max(run_n, vn[j]);
-      if (nc[j]) { next_head[run_c] = (b << SEG_SHIFT) | (run_n - 1); next_idx[run_c] = sg[RI_PAD(p)]; }
+      if (nc[j]) { next_head[run_c] = (b << SEG_SHIFT) | (run_n - 1); next_idx[run_c] = (b << SEG_SHIFT) | (sg[RI_PAD(p)] & SEG_MASK); }
       run_c += nc[j];
     }
   }

@@ -105,7 +105,7 @@ struct BitReader {
 };
 
 // ---- header + Huffman decode: one warp per candidate ----------------------------------------
-#define HD_WARPS 4
+#define HD_THREADS 128   // one CTA per block: the per-group phases are spread over four warps
 #define HD_LUT_BITS 9   // 6 tables x 512 entries: keeps a warp's state under 19 KB so that 12 blocks fit per SM
 #define HD_WIN 512
 #define HD_STAGE 64
@@ -125,6 +125,7 @@ struct HdecWarp {
   u16 J1[HD_WIN + 32], J2[HD_WIN + 32], J4[HD_WIN + 32];  // chain jump tables: 1, 2 and 4 symbols ahead
   u16 q4[16];
   u32 c_cnt, c_pos, c_flag;
+  u64 P0;
 };
 
 // code longer than the LUT covers: the reference's limit search (lib/Bzip2.js:296-306); returns sym | len << 9,
@@ -144,15 +145,15 @@ __device__ __noinline__ u32 hdec_slow(const HdecWarp& s, u32 g, u32 bits20, int 
   return 0;
 }
 
-__global__ void __launch_bounds__(HD_WARPS * 32)
+// 9 CTAs per SM (56 registers, 19 KB of shared memory each): a 1 GiB file's ~1200 blocks are resident at once
+__global__ void __launch_bounds__(HD_THREADS, 9)
 k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u32 first, u32 count, u32 dbuf_size, u8* __restrict__ sel_buf,
        u16* __restrict__ sym_out, CandRes* __restrict__ res) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  HdecWarp* all = reinterpret_cast<HdecWarp*>(smem_raw);
-  const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u32 ci = blockIdx.x * HD_WARPS + w;
+  HdecWarp& s = *reinterpret_cast<HdecWarp*>(smem_raw);
+  const u32 lane = threadIdx.x;  // 0..HD_THREADS-1: one CTA per candidate block
+  const u32 ci = blockIdx.x;
   if (ci >= count) return;
-  HdecWarp& s = all[w];
   const Cand cd = cands[first + ci];
   CandRes* r = res + ci;
   u8* sel = sel_buf + (size_t)ci * SEL_CAP;
@@ -211,7 +212,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     } while (0);
     r->sym_total = symTotal;
   }
-  __syncwarp();
+  __syncthreads();
   if (s.status != 0) {
     if (lane == 0) r->status = s.status;
     return;
@@ -246,9 +247,9 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     s.limit[g][maxLen] = pp + temp[maxLen] - 1;
     s.base[g][minLen] = 0;
   }
-  __syncwarp();
+  __syncthreads();
   // ---- LUT (HD_LUT_BITS bits) derived from the reference's decode loop (lib/Bzip2.js:296-307) ----
-  for (u32 e = lane; e < gc << HD_LUT_BITS; e += 32) {
+  for (u32 e = lane; e < gc << HD_LUT_BITS; e += HD_THREADS) {
     const u32 g = e >> HD_LUT_BITS, p = e & ((1u << HD_LUT_BITS) - 1);
     const int minLen = s.minlen[g], maxLen = s.maxlen[g];
     u16 ent = 0;  // 0 = needs more than HD_LUT_BITS bits (or fails): take the slow path
@@ -269,26 +270,25 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
     }
     s.lut[g][p] = ent;
   }
-  __syncwarp();
+  __syncthreads();
   // ---- symbol stream (lib/Bzip2.js:288-307).  Per 50-symbol group the table is fixed, so all 32
   // lanes decode the (symbol, length) that WOULD start at every bit offset of a 512-bit window, and
   // lane 0 only follows the chain pos += len[pos] through shared memory; the symbols on the chain are
   // then written out by the whole warp. ----
   {
     const u32 ns = s.nsel, eob = s.symcount - 1;  // symTotal + 1
-    u64 P = 0;
-    if (lane == 0) P = br.tell();
-    P = __shfl_sync(FULL_MASK, P, 0);
+    if (lane == 0) s.P0 = br.tell();
+    __syncthreads();
+    u64 P = s.P0;
     const u32* words = reinterpret_cast<const u32*>(in);
     const u64 nwords = (nbytes + 3) / 4;
     u32 m = 0, selector = 0;
     int status = 0;
     bool done = false;
-    s.wlen[HD_WIN + lane] = 0;
-    s.wsym[HD_WIN + lane] = 0;
+    if (lane < 32) { s.wlen[HD_WIN + lane] = 0; s.wsym[HD_WIN + lane] = 0; }
     u64 stage_w0 = ~0ull;  // index of the stream word held in win[0]
     u32 wlim = HD_WIN;     // bit offsets decoded per window: adapts to the size of the previous group
-    __syncwarp();
+    __syncthreads();
     while (!done) {
       if (selector >= ns) { status = DEC_DATA_ERROR; break; }          // :291
       const u32 g = sel[selector++];
@@ -299,33 +299,31 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
         // (re)stage HD_STAGE + 18 words when the 544-bit window would leave the staged range
         const u64 w0 = P >> 5;
         if (stage_w0 == ~0ull || w0 < stage_w0 || w0 + 18 > stage_w0 + HD_STAGE + 18) {
-          __syncwarp();
-          for (u32 i = lane; i < HD_STAGE + 18; i += 32) {
+          __syncthreads();
+          for (u32 i = lane; i < HD_STAGE + 18; i += HD_THREADS) {
             const u64 wi = w0 + i;
             const u32 wv = wi < nwords ? words[wi] : 0u;
             s.win[i] = __byte_perm(wv, 0, 0x0123);
           }
           stage_w0 = w0;
-          __syncwarp();
+          __syncthreads();
         }
         const u32 shiftbase = (u32)(P & 31);
-        const u32 nk = wlim / 32;  // window steps of this round (warp uniform)
-        u32 j1r[HD_WIN / 32], j2r[HD_WIN / 32];  // this lane's jump targets, kept in registers between the passes
+        u32 j1r[HD_WIN / HD_THREADS], j2r[HD_WIN / HD_THREADS];  // this thread's jump targets, kept in registers between the passes
         {
-          // lane l decodes offsets l, l+32, ...: same bit shift every time, one new word per step.  Fully unrolled
-          // so that the shared-memory loads of all steps are in flight together.
+          // thread t decodes offsets t, t+128, ...: same bit shift every time
           const u32 sh = (shiftbase + lane) & 31;
           const u32* wp = s.win + (u32)(w0 - stage_w0) + ((shiftbase + lane) >> 5);
-          u32 hiw = wp[0];
 #pragma unroll
-          for (u32 k = 0; k < HD_WIN / 32; k++) {
-            if (k < nk) {
-              const u32 low = wp[k + 1];
+          for (u32 k = 0; k < HD_WIN / HD_THREADS; k++) {
+            const u32 o = lane + HD_THREADS * k;
+            j1r[k] = o;
+            if (o < wlim) {
+              const u32 hiw = wp[(HD_THREADS / 32) * k], low = wp[(HD_THREADS / 32) * k + 1];
               const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
-              hiw = low;
               u32 ent = lut[bits20 >> (20 - HD_LUT_BITS)];
               if (!ent) ent = hdec_slow(s, g, bits20, minLen, maxLen);
-              const u32 o = lane + 32 * k, len = ent >> 9;
+              const u32 len = ent >> 9;
               s.wsym[o] = (u16)(ent & 511u);
               s.wlen[o] = (u8)len;
               // J1[o] = o + len[o] (an offset without a code maps to itself, one beyond the window parks there)
@@ -334,41 +332,41 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
             }
           }
         }
-        {
+        if (lane < 32) {
           // everything behind the decoded window parks the chain
           const u32 o = wlim + lane;
           s.wlen[o] = 0; s.wsym[o] = 0;
           s.J1[o] = (u16)o; s.J2[o] = (u16)o; s.J4[o] = (u16)o;
         }
-        __syncwarp();
+        __syncthreads();
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / 32; k++)
-          if (k < nk) j2r[k] = s.J1[j1r[k]];
+        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
+          if (lane + HD_THREADS * k < wlim) j2r[k] = s.J1[j1r[k]];
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / 32; k++)
-          if (k < nk) s.J2[lane + 32 * k] = (u16)j2r[k];
-        __syncwarp();
+        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
+          if (lane + HD_THREADS * k < wlim) s.J2[lane + HD_THREADS * k] = (u16)j2r[k];
+        __syncthreads();
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / 32; k++)
-          if (k < nk) j1r[k] = s.J2[j2r[k]];
+        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
+          if (lane + HD_THREADS * k < wlim) j1r[k] = s.J2[j2r[k]];
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / 32; k++)
-          if (k < nk) s.J4[lane + 32 * k] = (u16)j1r[k];
-        __syncwarp();
+        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
+          if (lane + HD_THREADS * k < wlim) s.J4[lane + HD_THREADS * k] = (u16)j1r[k];
+        __syncthreads();
         if (lane == 0) {
           // the only serial part: 13 dependent shared-memory loads cover 52 symbols
           u32 pos = 0;
 #pragma unroll
           for (u32 i = 0; i < 13; i++) { s.q4[i] = (u16)pos; pos = s.J4[pos]; }
         }
-        __syncwarp();
+        __syncthreads();
         if (lane < 13) {
           const u32 p0 = s.q4[lane], p1 = s.J1[p0], p2 = s.J1[p1], p3 = s.J1[p2];
           s.spos[4 * lane] = (u16)p0; s.spos[4 * lane + 1] = (u16)p1; s.spos[4 * lane + 2] = (u16)p2; s.spos[4 * lane + 3] = (u16)p3;
         }
-        __syncwarp();
-        {
-          // whole warp: where does the group stop inside this window?
+        __syncthreads();
+        if (lane < 32) {
+          // first warp: where does the group stop inside this window?
           const u32 lim = remaining;  // <= 50
           u32 first_stop = 0xffffffffu, first_eob = 0xffffffffu;
           for (u32 i = lane; i < lim; i += 32) {
@@ -384,10 +382,10 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
           else if (first_stop < lim) { cntw = first_stop; flag = (s.spos[first_stop] < wlim) ? 2u : 0u; }  // :299/:306 vs. window exhausted
           if (lane == 0) { s.c_cnt = cntw; s.c_pos = s.spos[cntw]; s.c_flag = flag; }
         }
-        __syncwarp();
+        __syncthreads();
         const u32 cnt = s.c_cnt, flag = s.c_flag;
         if (m + cnt >= SEG_SIZE) { status = DEC_DATA_ERROR; done = true; break; }
-        for (u32 i = lane; i < cnt; i += 32) so[m + i] = s.wsym[s.spos[i]];
+        if (lane < cnt) so[m + lane] = s.wsym[s.spos[lane]];  // cnt <= 50
         m += cnt;
         remaining -= cnt;
         P += s.c_pos;
@@ -398,7 +396,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
         }
         if (flag == 2) { status = DEC_DATA_ERROR; done = true; }
         else if (flag == 1) done = true;
-        __syncwarp();
+        __syncthreads();
       }
     }
     if (lane == 0) {
@@ -736,7 +734,7 @@ __global__ void k_reverse_bytes(const u8* __restrict__ in, u32 n, u8* __restrict
 static void dec_attr_once() {
   static bool attr = false;
   if (attr) return;
-  CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HdecWarp) * HD_WARPS)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HdecWarp)));
   CUDA_CHECK(cudaFuncSetAttribute(k_ibwt_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Seg) * IB_SEGS)));
   attr = true;
 }
@@ -1013,7 +1011,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
       CandRes* rb = dres.p + k0;
       {
         StageScope ss(c, ST_HDEC);
-        k_hdec<<<(cnt + HD_WARPS - 1) / HD_WARPS, HD_WARPS * 32, sizeof(HdecWarp) * HD_WARPS, c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size,
+        k_hdec<<<cnt, HD_THREADS, sizeof(HdecWarp), c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size,
                                                                                                        selbuf, sym, rb);
         KLAUNCH(c); KCHECK();
       }
