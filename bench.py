@@ -231,8 +231,11 @@ def main():
         out = SH.compress_file_sharded(d, LEVEL)
         nn = 0
         if out is not None:
-            hostout = out.cpu()                      # D2H of the step's result
-            nn = hostout.numel()
+            nn = out.numel()
+            if state.get("pinned_out") is None or state["pinned_out"].numel() < nn:
+                state["pinned_out"] = torch.empty(nn + (nn >> 3), dtype=torch.uint8, pin_memory=True)
+            state["pinned_out"][:nn].copy_(out, non_blocking=True)   # D2H of the step's result into pinned memory
+            torch.cuda.current_stream().synchronize()
         return _native.stats(), nn
 
     def barrier():

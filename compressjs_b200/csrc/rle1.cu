@@ -18,6 +18,7 @@
 //   CRC k_crc_pieces : 256-byte pieces, pure polynomial remainders shifted by x^(8*bytes after)
 //                      and XOR-combined per block (CRC is linear), then the init/final XOR.
 #include <algorithm>
+#include <cstdlib>
 #include "enc.h"
 
 #define RT_THREADS 256
@@ -307,6 +308,132 @@ k_rle_scan(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u32* __restrict_
   if (tid == 0) prefix[ntiles] = grand;
 }
 
+// Multi-CTA version of the same scan for inputs of many tiles (one CTA per RG_TILES tiles, five small launches):
+//   g1: per group, the aggregate run state                    g2: exclusive scan of the group aggregates (one CTA)
+//   g3: per tile carry + output size S (in prefix[]), group sums   g4: exclusive scan of the group sums (one CTA)
+//   g5: prefix[t] = group base + exclusive scan of S inside the group
+#define RG_THREADS 256
+#define RG_PER 8
+#define RG_TILES (RG_THREADS * RG_PER)
+__device__ __forceinline__ u64 rg_tile_state(const TileSum& s, u64 t, u64 N) {
+  const u64 tl = min((u64)RLE_TILE, N - t * RLE_TILE);
+  return rs_make(s.allsame, s.fc, s.lc, s.trail % 255, (u32)(tl % 255));
+}
+// exclusive scan over the CTA's threads with the (non commutative) state operator; *total = combination of all
+__device__ __forceinline__ u64 rg_block_excl_state(u64 v, u64* sa, u64* sb, u64* total) {
+  const u32 tid = threadIdx.x;
+  sa[tid] = v;
+  __syncthreads();
+  u64* src = sa; u64* dst = sb;
+  for (u32 o = 1; o < RG_THREADS; o <<= 1) {
+    u64 x = src[tid];
+    if (tid >= o) x = rs_combine(src[tid - o], x);
+    dst[tid] = x;
+    __syncthreads();
+    u64* tmp = src; src = dst; dst = tmp;
+  }
+  const u64 ex = tid ? src[tid - 1] : 0;
+  *total = src[RG_THREADS - 1];
+  __syncthreads();
+  return ex;
+}
+__global__ void __launch_bounds__(RG_THREADS)
+k_rle_scan_g1(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u64* __restrict__ group_agg) {
+  __shared__ u64 sa[RG_THREADS], sb[RG_THREADS];
+  const u64 t0 = (u64)blockIdx.x * RG_TILES + (u64)threadIdx.x * RG_PER;
+  u64 agg = 0;
+  for (u32 j = 0; j < RG_PER; j++) {
+    const u64 t = t0 + j;
+    if (t < ntiles) agg = rs_combine(agg, rg_tile_state(sums[t], t, N));
+  }
+  u64 total;
+  rg_block_excl_state(agg, sa, sb, &total);
+  if (threadIdx.x == 0) group_agg[blockIdx.x] = total;
+}
+// one CTA: exclusive scan of ngroups values (state operator when STATE, plain addition otherwise); out[ngroups] = total
+template <bool STATE>
+__global__ void __launch_bounds__(RS_THREADS)
+k_rle_scan_groups(const u64* __restrict__ in, u32 ngroups, u64* __restrict__ out) {
+  __shared__ u64 sa[RS_THREADS], sb[RS_THREADS];
+  const u32 tid = threadIdx.x;
+  const u32 per = (ngroups + RS_THREADS - 1) / RS_THREADS;
+  const u32 g0 = tid * per, g1 = min(ngroups, g0 + per);
+  u64 agg = 0;
+  for (u32 g = g0; g < g1; g++) agg = STATE ? rs_combine(agg, in[g]) : agg + in[g];
+  sa[tid] = agg;
+  __syncthreads();
+  u64* src = sa; u64* dst = sb;
+  for (u32 o = 1; o < RS_THREADS; o <<= 1) {
+    u64 x = src[tid];
+    if (tid >= o) x = STATE ? rs_combine(src[tid - o], x) : src[tid - o] + x;
+    dst[tid] = x;
+    __syncthreads();
+    u64* tmp = src; src = dst; dst = tmp;
+  }
+  u64 run = tid ? src[tid - 1] : 0;
+  for (u32 g = g0; g < g1; g++) {
+    const u64 v = in[g];
+    out[g] = run;
+    run = STATE ? rs_combine(run, v) : run + v;
+  }
+  if (tid == RS_THREADS - 1) out[ngroups] = src[RS_THREADS - 1];
+}
+__global__ void __launch_bounds__(RG_THREADS)
+k_rle_scan_g3(const TileSum* __restrict__ sums, u64 ntiles, u64 N, const u64* __restrict__ group_start, u32* __restrict__ carry,
+              u64* __restrict__ prefix, u64* __restrict__ group_sum) {
+  __shared__ u64 sa[RG_THREADS], sb[RG_THREADS];
+  __shared__ u32 ws[RG_THREADS / 32 + 1];
+  const u64 t0 = (u64)blockIdx.x * RG_TILES + (u64)threadIdx.x * RG_PER;
+  TileSum ts[RG_PER];
+  u64 agg = 0;
+#pragma unroll
+  for (u32 j = 0; j < RG_PER; j++) {
+    const u64 t = t0 + j;
+    if (t < ntiles) { ts[j] = sums[t]; agg = rs_combine(agg, rg_tile_state(ts[j], t, N)); }
+  }
+  u64 total;
+  u64 st = rs_combine(group_start[blockIdx.x], rg_block_excl_state(agg, sa, sb, &total));
+  u32 mysum = 0;  // <= 2048 tiles x 5120 bytes per group: fits 32 bits
+#pragma unroll
+  for (u32 j = 0; j < RG_PER; j++) {
+    const u64 t = t0 + j;
+    if (t < ntiles) {
+      const TileSum& s = ts[j];
+      u32 c = 0;
+      if ((st >> 63) && ((st >> 16) & 255) == s.fc) c = (st >> 8) & 255;
+      carry[t] = c;
+      const u64 S = outfresh((u64)c + s.lead) - outfresh(c) + s.rest;
+      prefix[t] = S;
+      mysum += (u32)S;
+      st = rs_combine(st, rg_tile_state(s, t, N));
+    }
+  }
+  u32 tot;
+  block_excl_add<RG_THREADS, u32>(mysum, ws, &tot);
+  if (threadIdx.x == 0) group_sum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(RG_THREADS)
+k_rle_scan_g5(u64 ntiles, const u64* __restrict__ group_base, u32 ngroups, u64* __restrict__ prefix) {
+  __shared__ u32 ws[RG_THREADS / 32 + 1];
+  const u64 t0 = (u64)blockIdx.x * RG_TILES + (u64)threadIdx.x * RG_PER;
+  u32 S[RG_PER];
+  u32 mysum = 0;
+#pragma unroll
+  for (u32 j = 0; j < RG_PER; j++) {
+    const u64 t = t0 + j;
+    S[j] = t < ntiles ? (u32)prefix[t] : 0u;
+    mysum += S[j];
+  }
+  u32 tot;
+  u64 run = group_base[blockIdx.x] + block_excl_add<RG_THREADS, u32>(mysum, ws, &tot);
+#pragma unroll
+  for (u32 j = 0; j < RG_PER; j++) {
+    const u64 t = t0 + j;
+    if (t < ntiles) { prefix[t] = run; run += S[j]; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) prefix[ntiles] = group_base[ngroups];
+}
+
 // ---- C ---------------------------------------------------------------------------------
 struct BlocksShared {
   TileScratch sc;
@@ -351,20 +478,21 @@ __device__ u64 find_run_end(const u8* in, u64 s, u64 cap, BlocksShared& sh) {
 
 __global__ void __launch_bounds__(RT_THREADS)
 k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ carry, const u64* __restrict__ prefix, u64 ntiles,
-             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks, u64 u_start, u32 total) {
+             BlkInfo* __restrict__ blocks, u32* nblocks_out, u32 maxblocks, u64 u_start, u32 range_first, u32 range_count, int open_end) {
   __shared__ BlocksShared sh;
   const u32 tid = threadIdx.x;
   const u64 Wtotal = prefix[ntiles];
   if (gridDim.x > 1) {
-    // parallel walk: CTA r takes blocks [r*total/P, (r+1)*total/P) of the `total` blocks that W(N) predicts, from
-    // the speculative boundary W = first*BS; the host accepts the result only if every segment ends where the
-    // next one starts (then it IS the sequential walk) and repeats the walk with one CTA otherwise.
+    // parallel walk: CTA r takes its share of the blocks [range_first, range_first + range_count) that W predicts,
+    // from the speculative boundary W = first*BS; the host accepts the result only if every segment ends where
+    // the next one starts (then it IS the sequential walk) and repeats the walk with one CTA otherwise.
+    // blocks[0] is block range_first; open_end: the last CTA goes on to the end of the input.
     const u32 P = gridDim.x, r = blockIdx.x;
-    const u32 first = (u32)((u64)r * total / P), next = (u32)((u64)(r + 1) * total / P);
+    const u32 first = range_first + (u32)((u64)r * range_count / P), next = range_first + (u32)((u64)(r + 1) * range_count / P);
     u_start = (u64)first * BS;
-    blocks += first;
+    blocks += first - range_first;
     nblocks_out += r;
-    maxblocks = r == P - 1 ? maxblocks - first : next - first;
+    maxblocks = (r == P - 1 && open_end) ? maxblocks - (first - range_first) : next - first;
   }
   u64 s = 0, Ws = 0;
   bool Ws_valid = true;  // W(0) = 0
@@ -711,8 +839,24 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     plan.tile_prefix.alloc(c, ntiles + 1);
     k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums);
     KLAUNCH(c); KCHECK();
-    k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix);
-    KLAUNCH(c); KCHECK();
+    static const bool force_groups = getenv("B2_RLE_SCAN_GROUPS") != nullptr;  // test hook: multi-CTA scan on small inputs too
+    if (ntiles <= 4 * RG_TILES && !force_groups) {
+      k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix);
+      KLAUNCH(c); KCHECK();
+    } else {
+      const u32 ng = (u32)((ntiles + RG_TILES - 1) / RG_TILES);
+      DBuf<u64> gagg(c, ng), gstart(c, ng + 1), gsum(c, ng), gbase(c, ng + 1);
+      k_rle_scan_g1<<<ng, RG_THREADS, 0, c.stream>>>(sums, ntiles, n, gagg);
+      KLAUNCH(c); KCHECK();
+      k_rle_scan_groups<true><<<1, RS_THREADS, 0, c.stream>>>(gagg, ng, gstart);
+      KLAUNCH(c); KCHECK();
+      k_rle_scan_g3<<<ng, RG_THREADS, 0, c.stream>>>(sums, ntiles, n, gstart, plan.tile_carry, plan.tile_prefix, gsum);
+      KLAUNCH(c); KCHECK();
+      k_rle_scan_groups<false><<<1, RS_THREADS, 0, c.stream>>>(gsum, ng, gbase);
+      KLAUNCH(c); KCHECK();
+      k_rle_scan_g5<<<ng, RG_THREADS, 0, c.stream>>>(ntiles, gbase, ng, plan.tile_prefix);
+      KLAUNCH(c); KCHECK();
+    }
   }
   u64 wtotal = 0;
   c.to_host(&wtotal, plan.tile_prefix.p + ntiles, 8);
@@ -728,33 +872,37 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     if (maxblocks == 0) return;
   }
   plan.blocks.alloc(c, maxblocks);
-  // exact plans of many blocks: walk P segments in parallel first (see k_rle_blocks)
+  // many blocks: walk P segments in parallel first (see k_rle_blocks)
   const u32 total = (u32)plan.total_guess;
-  const u32 P = spec_first < 0 ? std::min<u32>(64, total / 8) : 1;
-  if (P > 1 && total < maxblocks) {
+  const bool exact = spec_first < 0;
+  const u32 rfirst = exact ? 0u : (u32)spec_first, rcount = exact ? total : maxblocks;
+  const u32 P = std::min<u32>(64, rcount / 8);
+  if (P > 1 && (!exact || total < maxblocks)) {
     DBuf<u32> dnb(c, P);
-    k_rle_blocks<<<P, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, 0, total);
+    k_rle_blocks<<<P, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, 0, rfirst, rcount,
+                                                exact ? 1 : 0);
     KLAUNCH(c); KCHECK();
     std::vector<u32> cut(P);
     c.to_host(cut.data(), dnb, 4 * P);
     c.sync();
     bool ok = true;
-    for (u32 r = 0; r + 1 < P && ok; r++) ok = cut[r] == (u32)((u64)(r + 1) * total / P) - (u32)((u64)r * total / P);
-    const u32 last_first = (u32)((u64)(P - 1) * total / P);
+    for (u32 r = 0; r + 1 < P && ok; r++) ok = cut[r] == (u32)((u64)(r + 1) * rcount / P) - (u32)((u64)r * rcount / P);
+    const u32 last_first = (u32)((u64)(P - 1) * rcount / P);
     ok = ok && cut[P - 1] > 0;
     if (ok) {
       const u32 nb = last_first + cut[P - 1];
       plan.h_blocks.resize(nb);
       c.to_host(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb);
       c.sync();
-      ok = plan.h_blocks[0].s == 0 && plan.h_blocks[nb - 1].e == n;
+      // exact plans must cover the input; range plans are checked against their neighbours by the caller
+      ok = !exact || (plan.h_blocks[0].s == 0 && plan.h_blocks[nb - 1].e == n);
       for (u32 k = 0; k + 1 < nb && ok; k++) ok = plan.h_blocks[k].e == plan.h_blocks[k + 1].s;
       if (ok) { plan.nblocks = nb; return; }
       plan.h_blocks.clear();
     }
   }
   DBuf<u32> dnb(c, 1);
-  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, u_start, 0);
+  k_rle_blocks<<<1, RT_THREADS, 0, c.stream>>>(d_in, n, BS, plan.tile_carry, plan.tile_prefix, ntiles, plan.blocks, dnb, maxblocks, u_start, 0, 0, 0);
   KLAUNCH(c); KCHECK();
   u32 nb = 0;
   c.to_host(&nb, dnb, 4);
