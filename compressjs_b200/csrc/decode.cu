@@ -5,16 +5,20 @@
 //
 //   k_scan_magic   : every bit offset is tested for the 48-bit block / end-of-stream magics
 //                    (blocks start at arbitrary bit positions and a .bz2 has no index)
-//   k_hdec         : one warp per candidate block: header parse (symbol map, selectors, code length
-//                    tables -- lib/Bzip2.js:137-275), canonical decode tables exactly as the
-//                    reference builds them (limit/base/permute) plus a 10-bit LUT derived from them,
-//                    then the Huffman symbol stream (lib/Bzip2.js:288-307)
-//   k_unmtf_a/scan/b: RUNA/RUNB expansion and inverse move-to-front (lib/Bzip2.js:312-361), chunk
-//                    parallel: per chunk the composite MTF permutation, a per-block scan over the
-//                    chunks, then every chunk replays from its true start list
+//   k_hdec         : one CTA (4 warps) per candidate block: header parse (symbol map, selectors, code
+//                    length tables -- lib/Bzip2.js:137-275), canonical decode tables exactly as the
+//                    reference builds them (limit/base/permute) plus a 9-bit LUT derived from them,
+//                    then the Huffman symbol stream (lib/Bzip2.js:288-307): per 50-symbol group the
+//                    (symbol, length) that would start at EVERY bit offset of a window, jump tables
+//                    1/2/4 symbols ahead, and one thread following 13 jumps
+//   k_unmtf_a/scan/map: RUNA/RUNB expansion and inverse move-to-front (lib/Bzip2.js:312-361), chunk
+//                    parallel: one serial list pass per chunk that records start-list POSITIONS and
+//                    the chunk's composite permutation, a per-block scan over the chunks, then a
+//                    lane-parallel pass that maps positions to bytes and expands the runs
 //   inverse BWT    : T-vector by one onesweep radix pass on the L column (lib/Bzip2.js:370-381),
-//                    then the n-step pointer chase (lib/Bzip2.js:418-423) is broken into ~440
+//                    then the n-step pointer chase (lib/Bzip2.js:418-423) is broken into ~7000
 //                    independent walks per block between sampled rows (walk, chain, walk+emit)
+//   bwt_inverse_sentinel: BWT.unbwtransform (lib/BWT.js:352-363) on the same walk kernels
 //   k_unrle_*      : RLE1 decode (lib/Bzip2.js:424-436): count bytes are identified from local
 //                    synchronisation points, output offsets by chained scan, CRC32 per block
 //   host           : walks the block chain (a block must start exactly where the previous one
@@ -104,7 +108,7 @@ struct BitReader {
   __device__ __forceinline__ u64 tell() const { return widx * 32 - avail; }
 };
 
-// ---- header + Huffman decode: one warp per candidate ----------------------------------------
+// ---- header + Huffman decode: one CTA per candidate ------------------------------------------
 #define HD_THREADS 128   // one CTA per block: the per-group phases are spread over four warps
 #define HD_LUT_BITS 9   // 6 tables x 512 entries: keeps a warp's state under 19 KB so that 12 blocks fit per SM
 #define HD_WIN 512
@@ -624,7 +628,7 @@ __global__ void k_ibwt_pack(const u8* __restrict__ tt, const u32* __restrict__ t
 struct Seg { u32 len, next; };
 struct Visit { u32 row, off, len; };
 
-// walk from every sampled row (multiples of 2^11 and the start row) to the next sampled row
+// walk from every sampled row (multiples of 2^IB_SHIFT and the start row) to the next sampled row
 __global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, Seg* __restrict__ segs) {
   const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 ci = gid / IB_SEGS, sid = gid % IB_SEGS;
@@ -988,7 +992,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   const u32 ur_tps = UR_TPS;
 
   // ---- 2. decode the own share of the candidate blocks, in batches ----
-  // the per-block Huffman stage is one warp per block and latency bound: give it every block at once
+  // the per-block Huffman stage is one CTA per block and latency bound: give it every block at once
   // (about 19 MB of scratch per block; 180 GB of HBM take thousands)
   const u32 DB = std::max(c.bwt_batch, 2048u);
   dec_attr_once();

@@ -8,9 +8,11 @@
 //   k_mtf_prefix  : per block, running max over the chunks -> last occurrence BEFORE each chunk;
 //                   the MTF list at a chunk start is "bytes by most recent occurrence, then the
 //                   not-yet-seen used bytes in ascending order" (the initial list M)
-//   k_mtf_ranks   : one warp per chunk keeps the 256-entry list in registers (8 entries per
-//                   lane), finds a byte with byte-wise SIMD compares + ballot and rotates the
-//                   prefix with shuffles -> MTF rank per byte
+//   k_mtf_ranks   : one warp per chunk, 32 bytes per step: every byte value carries a recency key
+//                   (255 - rank at the chunk start, or 256 + position of its last occurrence inside
+//                   the chunk); the rank of a byte is the number of live keys above its own, counted
+//                   through a bucketed live-key bitmap with suffix sums, and the bytes of one step
+//                   that precede each other are settled with SWAR pair compares
 //   k_rle2        : zero ranks form runs -> bijective base-2 RUNA/RUNB digits; chained scans
 //                   (run starts, output offsets) across tiles; symbols u16 + histogram + EOB
 #include "enc.h"
