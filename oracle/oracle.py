@@ -15,7 +15,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("bz2_oracle.c", "bwtc_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("bz2_oracle.c",)]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
     return so
@@ -58,10 +58,6 @@ def lib():
         L.orc_compress_block_stages.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.POINTER(u8p), szp]
         L.orc_free.argtypes = [C.c_void_p]
-        for name in ("orc_bwtc_compress", "orc_bwtc_decompress"):
-            if hasattr(L, name):
-                getattr(L, name).argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(u8p), szp] \
-                    if name.endswith("_compress") else [C.c_void_p, C.c_size_t, C.POINTER(u8p), szp]
         _LIB = L
     return _LIB
 
