@@ -15,7 +15,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("bz2_oracle.c",)]
+    srcs = [os.path.join(_HERE, f) for f in ("bz2_oracle.c", "bwtc_oracle.c")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
     return so
@@ -58,6 +58,8 @@ def lib():
         L.orc_compress_block_stages.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.POINTER(u8p), szp]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_bwtc_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(u8p), szp]
+        L.orc_bwtc_decompress.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(u8p), szp]
         _LIB = L
     return _LIB
 
@@ -204,3 +206,25 @@ def compress_block_stages(block, legacy_sort=False):
     bits = _take(L, out, nb)
     return dict(trace=tr, sym=sym[:tr.m].copy(), sel=sel[:tr.nsel].copy(),
                 lens=lens.reshape(6, 258)[:tr.ngroups, :tr.alpha + 2].copy(), bits=bits, nbits=nbits.value)
+
+
+def bwtc_compress(data, level=9):
+    """BWTC.compressFile (lib/BWTC.js:12-139), levels 6..9."""
+    L = lib()
+    a, p = _buf(data)
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = L.orc_bwtc_compress(p, a.size, level, C.byref(out), C.byref(n))
+    if rc:
+        raise OracleError(rc, "bwtc compress failed")
+    return _take(L, out, n)
+
+
+def bwtc_decompress(data):
+    """BWTC.decompressFile (lib/BWTC.js:141-231)."""
+    L = lib()
+    a, p = _buf(data)
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = L.orc_bwtc_decompress(p, a.size, C.byref(out), C.byref(n))
+    if rc:
+        raise OracleError(rc, "Bad magic" if rc == -2 else "bwtc decompress failed")
+    return _take(L, out, n)

@@ -131,3 +131,39 @@ def test_rle1_quirk_uncounted_run_of_four():
     data = T.ascii_random(99977, 3).replace(b"aaaa", b"abab") + b"a" * 20 + b"tail"
     z = O.bzip2_compress(data, 1)
     assert O.bzip2_decompress(z) == data
+
+
+# ---- BWTC container (lib/BWTC.js) -- oracle only, no CUDA path yet ----------------
+BWTC9 = {  # size and SHA-256 of BWTC.compressFile(sample, null, 9)
+    "sample1": (32903, "982488a6bb9282e93e848ff7e9eed798a580f2b3f3e963677573c9ad9fda9fcb"),
+    "sample2": (74536, "b6109e3e2e40d0b143a2a72cf8f2302b67618a373f198a8530ba28b3c5d35088"),
+    "sample3": (201, "0e06e8045a87124f2b0692c02b4a0ce0544b47655a2a54a09db6c04643ba970d"),
+    "sample4": (335422, "9f5c636794242b9a24040e8c75fdc58044c861ded15a2f711e21812c5492738c"),
+    "sample5": (272997, "01d8d0a0490c39ef86808be3a449a1f57c864c11ea1cf5b2057ba56a241c23ca"),  # = README.md:41
+}
+
+
+def test_bwtc_sample0_whole_file():
+    z = O.bwtc_compress(T.fixture("sample0.ref"), 9)
+    assert z.hex() == "627774639009625e4eff9d2a362e8184ba3a3eef321c245ae8adbbb300001c"
+    assert O.bwtc_decompress(z) == T.fixture("sample0.ref")
+
+
+@pytest.mark.parametrize("name", sorted(BWTC9))
+def test_bwtc_level9_vectors(name):
+    d = T.fixture(name + ".ref")
+    z = O.bwtc_compress(d, 9)
+    assert (len(z), hashlib.sha256(z).hexdigest()) == BWTC9[name]
+    assert O.bwtc_decompress(z) == d
+
+
+def test_bwtc_level6_and_edges():
+    d = T.fixture("sample5.ref")
+    z = O.bwtc_compress(d, 6)
+    assert (len(z), hashlib.sha256(z).hexdigest()) == (279678, "29206d8d51e293ddee9e5fafb27552502bba5adc9730e27cefb56e962bb7c1b6")
+    assert O.bwtc_decompress(z) == d
+    for data in (b"", b"a", b"\x00" * 5000, bytes(range(256)) * 9, T.ascii_random(600000, 3) + T.runs(100001, 4)):
+        for level in (6, 9):
+            assert O.bwtc_decompress(O.bwtc_compress(data, level)) == data   # 700001 bytes at -6: one full + one short block
+    with pytest.raises(O.OracleError):
+        O.bwtc_decompress(b"bzzt" + b"\x81\x00\x00\x00\x00\x00")
