@@ -7,10 +7,11 @@
  * checker, and as the CPU yardstick for BASELINE config 4.
  *
  * Restates, citing file:line under /root/reference:
- *   lib/BWTC.js:12-139   compressFile (levels 6..9: FenwickModel; levels 1..5 use DefSumModel -- not restated)
+ *   lib/BWTC.js:12-139   compressFile (levels 6..9: FenwickModel; levels 1..5: DefSumModel)
  *   lib/BWTC.js:141-231  decompressFile
  *   lib/RangeCoder.js:27-232
  *   lib/FenwickModel.js:15-165
+ *   lib/DefSumModel.js:11-131
  *   lib/LogDistanceModel.js:8-49 over lib/NoModel.js:8-30 (raw bits through the range coder)
  *   lib/Util.js:105-220  magic + self-delimiting size + suppressed final byte
  *
@@ -258,13 +259,79 @@ static uint32_t fen_decode(fen_t* f) {  /* :115-122 */
   return s;
 }
 
+/* ---- DefSumModel (DefSumModel.js): deferred-sum model of the "fast" levels 1..5 ------------------------------ */
+#define DS_LOG_TOTAL 8
+#define DS_TOTAL 256u
+#define DS_MAX_ESCAPE 40
+typedef struct { uint32_t numSyms, updateCount, updateThresh; uint16_t prob[262], escape[262], update[262]; rc_t* rc; } dsm_t;
+
+static void dsm_init(dsm_t* m, rc_t* rc, uint32_t size) {  /* :11-35 */
+  memset(m, 0, sizeof *m);
+  m->rc = rc; m->numSyms = size;
+  m->prob[size + 1] = DS_TOTAL;                        /* everything escapes at first */
+  for (uint32_t i = 0; i <= size; i++) m->escape[i] = (uint16_t)i;
+  m->updateCount = 0;
+  m->updateThresh = DS_TOTAL - DS_TOTAL / 2;
+}
+static void dsm_update(dsm_t* m, uint32_t symbol) {  /* :39-93 (the decoder's lookup tables are searched instead) */
+  if (symbol == m->numSyms) {
+    if (m->update[symbol] >= DS_MAX_ESCAPE) return;
+    if (m->updateCount >= m->updateThresh - 1) return;   /* an escape never triggers the table rebuild */
+  }
+  m->update[symbol]++;
+  m->updateCount++;
+  if (m->updateCount < m->updateThresh) return;
+  uint32_t cumProb = 0, cumEscProb = 0, odd = 0, i;
+  m->escape[0] = 0; m->prob[0] = 0;
+  for (i = 0; i < m->numSyms + 1; i++) {
+    const uint32_t newProb = ((uint32_t)(m->prob[i + 1] - m->prob[i]) >> 1) + m->update[i];
+    m->prob[i] = (uint16_t)cumProb;
+    m->escape[i] = (uint16_t)cumEscProb;
+    if (newProb) { cumProb += newProb; if (newProb & 1) odd++; }
+    else cumEscProb++;
+  }
+  m->prob[i] = (uint16_t)cumProb;
+  m->updateThresh = DS_TOTAL - (cumProb - odd) / 2;
+  for (i = 0; i < m->numSyms + 1; i++) m->update[i] = 0;
+  m->update[m->numSyms] = 1;
+  m->updateCount = 1;
+}
+static void dsm_encode(dsm_t* m, uint32_t symbol) {  /* :94-111 */
+  uint32_t lt_f = m->prob[symbol], sy_f = m->prob[symbol + 1] - lt_f;
+  if (sy_f) { enc_shift(m->rc, sy_f, lt_f, DS_LOG_TOTAL); dsm_update(m, symbol); return; }
+  dsm_encode(m, m->numSyms);                            /* escape, then the symbol among the escaping ones */
+  lt_f = m->escape[symbol];
+  sy_f = m->escape[symbol + 1] - lt_f;
+  enc_freq(m->rc, sy_f, lt_f, m->escape[m->numSyms]);
+  dsm_update(m, symbol);
+}
+static uint32_t dsm_decode(dsm_t* m) {  /* :112-131 */
+  uint32_t prob = dec_culshift(m->rc, DS_LOG_TOTAL), symbol = 0;
+  while (symbol < m->numSyms && !(m->prob[symbol] <= prob && prob < m->prob[symbol + 1])) symbol++;   /* probToSym */
+  uint32_t lt_f = m->prob[symbol], sy_f = m->prob[symbol + 1] - lt_f;
+  dec_update(m->rc, sy_f, lt_f, DS_TOTAL);
+  dsm_update(m, symbol);
+  if (symbol != m->numSyms) return symbol;
+  const uint32_t tot_f = m->escape[m->numSyms];
+  if (tot_f == 0) return 0xffffffffu;
+  prob = dec_culfreq(m->rc, tot_f);
+  symbol = 0;
+  while (symbol + 1 < m->numSyms && !(m->escape[symbol] <= prob && prob < m->escape[symbol + 1])) symbol++;   /* escProbToSym */
+  lt_f = m->escape[symbol];
+  sy_f = m->escape[symbol + 1] - lt_f;
+  dec_update(m->rc, sy_f, lt_f, tot_f);
+  dsm_update(m, symbol);
+  return symbol;
+}
+
 /* ---- container ---------------------------------------------------------------------------------- */
 #define F_PROB_MAX 0xFF00u   /* BWTC.js:7 */
 #define F_PROB_INCR 0x0100u  /* BWTC.js:8 */
 
 /* BWTC.compressFile(input, output, level) for a buffer input of known size (Util.js:105-141: the size is written). */
 ORC_EXPORT int orc_bwtc_compress(const uint8_t* in, size_t n, int level, uint8_t** out, size_t* out_n) {
-  if (level < 6 || level > 9) return -100;   /* 1..5 switch to DefSumModel (BWTC.js:22,103): not restated */
+  if (level < 1 || level > 9) level = 9;      /* BWTC.js:16-19: anything else means 9 */
+  const int fast = level <= 5;                /* :22 */
   sink_t o = {0, 0, 0, 0};
   put(&o, 'b'); put(&o, 'w'); put(&o, 't'); put(&o, 'c');                      /* BWTC.js:11 */
   /* Util.js:194-209 writeUnsignedNumber(fileSize + 1), big endian 7-bit groups, last group flagged; the final byte
@@ -280,7 +347,8 @@ ORC_EXPORT int orc_bwtc_compress(const uint8_t* in, size_t n, int level, uint8_t
   const uint32_t blockSize = (uint32_t)level * 100000u;                           /* :23 */
   uint8_t* U = (uint8_t*)malloc(blockSize ? blockSize : 1);
   fen_t* model = (fen_t*)malloc(sizeof(fen_t));
-  if (!U || !model) { free(U); free(model); free(o.p); return -6; }
+  dsm_t* dmodel = (dsm_t*)malloc(sizeof(dsm_t));
+  if (!U || !model || !dmodel) { free(U); free(model); free(dmodel); free(o.p); return -6; }
   logdist_t lenModel;
   logdist_init(&lenModel, blockSize);                                             /* :40-42 */
   size_t pos = 0;
@@ -316,22 +384,25 @@ ORC_EXPORT int orc_bwtc_compress(const uint8_t* in, size_t n, int level, uint8_t
       for (; j > 0; j--) M[j] = M[j - 1];
       M[0] = c;
     }
-    fen_init(model, &rc, alphabetSize + 1, F_PROB_MAX, F_PROB_INCR);               /* :109-110 */
+    if (fast) dsm_init(dmodel, &rc, alphabetSize + 1);                             /* :111 */
+    else fen_init(model, &rc, alphabetSize + 1, F_PROB_MAX, F_PROB_INCR);          /* :109-110 */
+#define MODEL_ENCODE(sym) do { if (fast) dsm_encode(dmodel, (sym)); else fen_encode(model, (sym)); } while (0)
     uint32_t runLength = 0;
     for (uint32_t i = 0; i <= length; i++) {                                       /* :112-137; i == length flushes */
       const uint32_t c = i < length ? U[i] : 1u;
       if (i < length && c == 0) { runLength++; continue; }
       while (runLength) {                                                          /* emitLastRun :113-124 */
-        if (runLength & 1) { fen_encode(model, 0); runLength -= 1; }
-        else { fen_encode(model, 1); runLength -= 2; }
+        if (runLength & 1) { MODEL_ENCODE(0); runLength -= 1; }
+        else { MODEL_ENCODE(1); runLength -= 2; }
         runLength >>= 1;
       }
-      if (i < length) fen_encode(model, c + 1);
+      if (i < length) MODEL_ENCODE(c + 1);
     }
+#undef MODEL_ENCODE
   } while (length == blockSize);                                                   /* :139 */
   enc_freq(&rc, 1, 2, 3);                                                           /* :141 */
   enc_finish(&rc);
-  free(U); free(model);
+  free(U); free(model); free(dmodel);
   if (o.oom) { free(o.p); return -6; }
   *out = o.p; *out_n = o.n;
   return 0;
@@ -353,13 +424,15 @@ ORC_EXPORT int orc_bwtc_decompress(const uint8_t* in, size_t n, uint8_t** out, s
   rc_t rc;
   dec_start_skipping_initial_read(&rc, &s);                                        /* BWTC.js:143 */
   const uint32_t level = dec_byte(&rc);                                            /* :144 */
-  if (level < 6 || level > 9) return level >= 1 && level <= 5 ? -100 : -5;
+  if (level < 1 || level > 9) return -5;                                           /* :145 asserts */
+  const int fast = level <= 5;
   const uint32_t blockSize = level * 100000u;
   sink_t o = {0, 0, 0, 0};
   uint8_t* block = (uint8_t*)malloc(blockSize + 2);
   uint8_t* U = (uint8_t*)malloc(blockSize);
   fen_t* model = (fen_t*)malloc(sizeof(fen_t));
-  if (!block || !U || !model) { free(block); free(U); free(model); return -6; }
+  dsm_t* dmodel = (dsm_t*)malloc(sizeof(dsm_t));
+  if (!block || !U || !model || !dmodel) { free(block); free(U); free(model); free(dmodel); return -6; }
   logdist_t lenModel;
   logdist_init(&lenModel, blockSize);
   int rcode = 0;
@@ -386,11 +459,12 @@ ORC_EXPORT int orc_bwtc_decompress(const uint8_t* in, size_t n, uint8_t** out, s
     uint32_t alphabetSize = 0;
     for (uint32_t i = 0; i < 256; i++) if (useTree[256 + i]) M[alphabetSize++] = (uint8_t)i;
     if (alphabetSize == 0) { rcode = -5; break; }
-    fen_init(model, &rc, alphabetSize + 1, F_PROB_MAX, F_PROB_INCR);               /* :196-197 */
+    if (fast) dsm_init(dmodel, &rc, alphabetSize + 1);                             /* :198 */
+    else fen_init(model, &rc, alphabetSize + 1, F_PROB_MAX, F_PROB_INCR);          /* :196-197 */
     uint64_t val = 1;
     uint32_t i = 0;
     while (i < length) {                                                           /* :200-212 */
-      const uint32_t c = fen_decode(model);
+      const uint32_t c = fast ? dsm_decode(dmodel) : fen_decode(model);
       if (c == 0xffffffffu || c > alphabetSize) { rcode = -5; break; }
       if (c == 0 || c == 1) {
         const uint64_t cnt = val * (c + 1);
@@ -413,7 +487,7 @@ ORC_EXPORT int orc_bwtc_decompress(const uint8_t* in, size_t n, uint8_t** out, s
     orc_unbwt_sentinel(block, U, (int32_t)length, (int32_t)pidx);                   /* :224 */
     for (i = 0; i < length; i++) put(&o, U[i]);
   }
-  free(block); free(U); free(model);
+  free(block); free(U); free(model); free(dmodel);
   if (!rcode && fs != 0 && o.n != fs - 1) rcode = -5;   /* Util.js:69-71: "outputsize does not match decoded input" */
   if (rcode || o.oom) { free(o.p); return rcode ? rcode : -6; }
   if (!o.p) o.p = (uint8_t*)malloc(1);

@@ -209,7 +209,7 @@ def compress_block_stages(block, legacy_sort=False):
 
 
 def bwtc_compress(data, level=9):
-    """BWTC.compressFile (lib/BWTC.js:12-139), levels 6..9."""
+    """BWTC.compressFile (lib/BWTC.js:12-139)."""
     L = lib()
     a, p = _buf(data)
     out, n = C.POINTER(C.c_uint8)(), C.c_size_t()

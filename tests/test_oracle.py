@@ -157,13 +157,15 @@ def test_bwtc_level9_vectors(name):
     assert O.bwtc_decompress(z) == d
 
 
-def test_bwtc_level6_and_edges():
+def test_bwtc_other_levels_and_edges():
     d = T.fixture("sample5.ref")
+    z = O.bwtc_compress(d, 1)   # levels 1..5 switch to the deferred-sum model (lib/BWTC.js:22,111)
+    assert len(z) == 345764 and O.bwtc_decompress(z) == d   # README.md:46
     z = O.bwtc_compress(d, 6)
     assert (len(z), hashlib.sha256(z).hexdigest()) == (279678, "29206d8d51e293ddee9e5fafb27552502bba5adc9730e27cefb56e962bb7c1b6")
     assert O.bwtc_decompress(z) == d
     for data in (b"", b"a", b"\x00" * 5000, bytes(range(256)) * 9, T.ascii_random(600000, 3) + T.runs(100001, 4)):
-        for level in (6, 9):
-            assert O.bwtc_decompress(O.bwtc_compress(data, level)) == data   # 700001 bytes at -6: one full + one short block
+        for level in (1, 5, 6, 9):
+            assert O.bwtc_decompress(O.bwtc_compress(data, level)) == data   # 700001 bytes: full + short blocks at -1, -5, -6
     with pytest.raises(O.OracleError):
         O.bwtc_decompress(b"bzzt" + b"\x81\x00\x00\x00\x00\x00")
