@@ -13,7 +13,7 @@ _LIB = None
 EXPORTS = [
     "b2_init", "b2_shutdown", "b2_last_error", "b2_free",
     "b2_bzip2_compress", "b2_bzip2_decompress", "b2_bzip2_decompress_block", "b2_bzip2_table",
-    "b2_bwt_cyclic", "b2_bwt_cyclic_batch", "b2_suffixsort", "b2_bwt_sentinel", "b2_bwt_inverse", "b2_crc32_bzip2",
+    "b2_bwt_cyclic", "b2_bwt_cyclic_batch", "b2_suffixsort", "b2_bwt_sentinel", "b2_bwt_inverse", "b2_bwtc_compress", "b2_bwtc_decompress", "b2_crc32_bzip2",
     "b2_bzip2_bound", "b2_bzip2_compress_dev", "b2_bzip2_decompress_dev",
     "b2_bzip2_plan", "b2_bzip2_plan_spec", "b2_bitshift_dev", "b2_dec_shard_open", "b2_dec_shard_export", "b2_dec_shard_finish", "b2_bzip2_encode_range_dev", "b2_get_stats", "b2_last_trace",
 ]
@@ -63,6 +63,8 @@ def lib():
     L.b2_bwt_sentinel.restype = C.c_int32
     L.b2_bwt_sentinel.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.b2_bwt_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    L.b2_bwtc_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, u8pp, szp]
+    L.b2_bwtc_decompress.argtypes = [C.c_void_p, C.c_size_t, u8pp, szp]
     L.b2_crc32_bzip2.restype = C.c_uint32
     L.b2_crc32_bzip2.argtypes = [C.c_void_p, C.c_size_t]
     L.b2_bzip2_bound.restype = C.c_size_t

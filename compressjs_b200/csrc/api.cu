@@ -19,6 +19,9 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
                            u64* spec_range = nullptr);
 void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst);
 void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out);
+size_t bwtc_bound(size_t n);
+void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n);
+void bwtc_decompress_device(Ctx& c, const u8* d_in, size_t n, const u8* h_head, size_t head_n, u8* d_out, size_t out_cap, size_t* out_n);
 void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, u8* d_out, size_t out_cap, u8* h_out, size_t* out_n,
                          bool pinned_in);
 void dec_shard_open(Ctx& c, const u8* d_in, size_t n, int rank, int world, u64* info);
@@ -349,6 +352,62 @@ int b2_bwt_inverse(const uint8_t* L, uint8_t* out, int32_t n, int32_t pidx) {
     }
     c.sync();
     c.collect();
+    return 0;
+  });
+}
+
+// ---- BWTC container (experimental, see bwtc.cu) ----------------------------------------------
+int b2_bwtc_compress(const uint8_t* in, size_t n, int level, uint8_t** out, size_t* out_n) {
+  return guarded([&]() {
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    const size_t cap = bwtc_bound(n);
+    size_t produced = 0;
+    void* host = nullptr;
+    {
+      StageScope tot(c, ST_TOTAL);
+      DBuf<u8> din(c, n ? n : 1), dout(c, cap);
+      if (n) CUDA_CHECK(cudaMemcpyAsync(din.p, in, n, cudaMemcpyHostToDevice, c.stream));
+      bwtc_compress_device(c, din, n, level, dout, cap, &produced);
+      host = pinned_alloc(produced);
+      CUDA_CHECK(cudaMemcpyAsync(host, dout.p, produced, cudaMemcpyDeviceToHost, c.stream));
+    }
+    c.sync();
+    c.collect();
+    c.stats.raw_bytes = n; c.stats.comp_bytes = produced;
+    *out = (uint8_t*)host; *out_n = produced;
+    return 0;
+  });
+}
+int b2_bwtc_decompress(const uint8_t* in, size_t n, uint8_t** out, size_t* out_n) {
+  return guarded([&]() {
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    size_t produced = 0;
+    void* host = nullptr;
+    {
+      StageScope tot(c, ST_TOTAL);
+      // the decoded size is in the header: parse it before any device work
+      size_t pos = 4; uint64_t fs = 0;
+      if (n < 5 || memcmp(in, "bwtc", 4)) throw B2Error{B2_ERR_BAD_MAGIC, "Bad magic"};
+      for (;;) {
+        if (pos >= n || pos > 14) throw B2Error{B2_ERR_DATA_ERROR, "truncated BWTC header"};
+        const uint32_t ch = in[pos++];
+        if (ch & 0x80) { fs += ch & 0x7F; break; }
+        fs = (fs + ch) * 128;
+      }
+      if (fs == 0) throw B2Error{B2_ERR_BAD_ARG, "BWTC streams of unknown size are not supported"};
+      const size_t size = (size_t)(fs - 1);
+      DBuf<u8> din(c, n), dout(c, size ? size : 1);
+      CUDA_CHECK(cudaMemcpyAsync(din.p, in, n, cudaMemcpyHostToDevice, c.stream));
+      bwtc_decompress_device(c, din, n, in, std::min<size_t>(n, 16), dout, size, &produced);
+      host = pinned_alloc(produced);
+      if (produced) CUDA_CHECK(cudaMemcpyAsync(host, dout.p, produced, cudaMemcpyDeviceToHost, c.stream));
+    }
+    c.sync();
+    c.collect();
+    c.stats.raw_bytes = produced; c.stats.comp_bytes = n;
+    *out = (uint8_t*)host; *out_n = produced;
     return 0;
   });
 }

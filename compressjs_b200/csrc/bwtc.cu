@@ -1,0 +1,222 @@
+// bwtc.cu -- compressjs' BWTC container (lib/BWTC.js:12-231) on the GPU.
+//
+// STATUS: experimental.  The serial model / range-coder code (bwtc_core.cuh) is verified on the host build against
+// the oracle (tests/test_host_api.py::test_bwtc_core_matches_oracle); the kernels and the orchestration below have
+// not run on a B200 yet (the round's GPU budget ended first) -- tests/test_gpu_bwtc.py is opt-in (B2_TEST_BWTC=1)
+// until they have.
+//
+// Per block the container needs: sentinel BWT (lib/BWT.js:328-350), MTF over the used bytes, zero runs as
+// RUNA/RUNB digits, an adaptive model (Fenwick tree, or the deferred-sum model below level 6) that turns every
+// symbol into a (sy_f, lt_f, tot_f) triple, and ONE range coder that runs over the whole file.  The first three are
+// the block-parallel kernels of the bzip2 path (bwt.cu in sentinel mode, mtf.cu: the symbol values are identical,
+// bzip2 merely appends an end-of-block symbol).  The model is a serial chain per block (k_bwtc_model: one thread per
+// block, blocks in parallel), the coder a serial chain per file (k_bwtc_code: one thread; its `range` recurrence
+// needs an integer division per symbol and nothing shortens it).  Decode cannot even split model and coder:
+// k_bwtc_decode is one thread for the whole stream, followed by the inverse sentinel BWT per block (decode.cu).
+#include <algorithm>
+#include <vector>
+#include "enc.h"
+#include "bwtc_core.cuh"
+
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel, u32* d_sa_out);
+void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out);
+
+struct BwtcState {
+  bc_enc rc;
+  u32 overflow;  // a block's triples did not fit its buffer
+  u32 pad;
+};
+
+__global__ void k_bwtc_start(BwtcState* st, u8* out, u64 cap, u32 finalByte, u32 level) {
+  if (threadIdx.x || blockIdx.x) return;
+  bc_enc_start(&st->rc, out, cap, finalByte);                 // lib/BWTC.js:13-14
+  bc_enc_code(&st->rc, bc_triple(1, level, 256));             // encoder.encodeByte(blockSize), :21
+  st->overflow = 0;
+}
+
+// one thread per block (lane 0 of its warp): header + model -> triples
+__global__ void __launch_bounds__(32)
+k_bwtc_model(const u16* __restrict__ sym, const u32* __restrict__ d_m, const u32* __restrict__ d_n, const u32* __restrict__ d_pidx1,
+             const u32* __restrict__ d_used, u32 blockSize, int fast, u64* __restrict__ triples, u32 tcap, u32* __restrict__ tcount) {
+  if (threadIdx.x) return;
+  const u32 b = blockIdx.x;
+  bc_model model;
+  bc_emit e;
+  e.t = triples + (size_t)b * tcap; e.n = 0; e.cap = tcap;
+  const u32 m = d_m[b];
+  bc_block_triples(&e, &model, blockSize, d_n[b], d_pidx1[b], d_used + (size_t)b * 8, sym + ((size_t)b << SEG_SHIFT), m ? m - 1 : 0, fast);
+  tcount[b] = e.n;
+}
+
+// one thread: the blocks of a batch through the file's range coder
+__global__ void k_bwtc_code(BwtcState* st, const u64* __restrict__ triples, const u32* __restrict__ tcount, u32 nblk, u32 tcap) {
+  if (threadIdx.x || blockIdx.x) return;
+  bc_enc rc = st->rc;
+  u32 overflow = st->overflow;
+  for (u32 b = 0; b < nblk; b++) {
+    const u32 n = tcount[b];
+    if (n > tcap) { overflow = 1; break; }
+    const u64* t = triples + (size_t)b * tcap;
+    for (u32 k = 0; k < n; k++) bc_enc_code(&rc, t[k]);
+  }
+  st->rc = rc;
+  st->overflow = overflow;
+}
+
+__global__ void k_bwtc_finish(BwtcState* st) {
+  if (threadIdx.x || blockIdx.x) return;
+  bc_enc_code(&st->rc, bc_triple(1, 2, 3));                   // "no more blocks", lib/BWTC.js:141
+  bc_enc_finish(&st->rc);
+}
+
+size_t bwtc_bound(size_t n) { return n + n / 8 + (n / 100000 + 2) * 1024 + 64; }
+
+// BWTC.compressFile on device buffers; the size of the input is written into the header (Util.js:118-134: a buffer
+// input has a known size).  out_cap >= bwtc_bound(n).
+void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n) {
+  if (level < 1 || level > 9) level = 9;                      // lib/BWTC.js:16-19
+  const u32 blockSize = (u32)level * 100000u;
+  const int fast = level <= 5;                                // :22
+  if (out_cap < 32) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
+  u8 hdr[24];
+  u32 finalByte = 0;
+  const u32 hlen = bc_file_header(hdr, n, &finalByte);
+  c.to_device(d_out, hdr, hlen);
+  DBuf<BwtcState> st(c, 1);
+  k_bwtc_start<<<1, 1, 0, c.stream>>>(st, d_out + hlen, out_cap - hlen, finalByte, (u32)level);
+  KLAUNCH(c); KCHECK();
+  const size_t nblocks = (n + blockSize - 1) / blockSize;
+  if (nblocks) {
+    const u32 B = (u32)std::min<size_t>(c.bwt_batch, nblocks);
+    const u32 tcap = 2 * (blockSize + 1) + 1024;              // every symbol can cost an escape and a literal
+    DBuf<u8> T(c, (size_t)B << SEG_SHIFT), U(c, (size_t)B << SEG_SHIFT);
+    DBuf<u16> sym(c, (size_t)B << SEG_SHIFT);
+    DBuf<u32> dn(c, B), dpidx(c, B), dm(c, B), dfreq(c, (size_t)B * HUFF_MAXSYM), dused(c, (size_t)B * 8), tcount(c, B);
+    DBuf<u64> triples(c, (size_t)B * tcap);
+    std::vector<u32> hn(B);
+    for (size_t k0 = 0; k0 < nblocks; k0 += B) {
+      const u32 nb = (u32)std::min<size_t>(B, nblocks - k0);
+      for (u32 b = 0; b < nb; b++) hn[b] = (u32)std::min<size_t>(blockSize, n - (k0 + b) * blockSize);
+      const u32 full = hn[nb - 1] == blockSize ? nb : nb - 1;   // only the last block of the file can be short
+      if (full)
+        CUDA_CHECK(cudaMemcpy2DAsync(T.p, SEG_SIZE, d_in + k0 * blockSize, blockSize, blockSize, full, cudaMemcpyDeviceToDevice, c.stream));
+      if (full < nb)
+        CUDA_CHECK(cudaMemcpyAsync(T.p + ((size_t)full << SEG_SHIFT), d_in + (k0 + full) * blockSize, hn[full], cudaMemcpyDeviceToDevice, c.stream));
+      c.to_device(dn, hn.data(), 4 * nb);
+      CUDA_CHECK(cudaMemsetAsync(dpidx, 0, 4 * nb, c.stream));
+      {
+        StageScope s(c, ST_BWT);
+        bwt_forward_batch(c, T, U, dn, hn.data(), nb, dpidx, true, nullptr);   // U = sentinel BWT, dpidx = pidx + 1
+      }
+      {
+        StageScope s(c, ST_MTF);
+        mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused);
+      }
+      {
+        StageScope s(c, ST_HUFF);   // the model + coder stage takes the slot of the Huffman stage in the statistics
+        k_bwtc_model<<<nb, 32, 0, c.stream>>>(sym, dm, dn, dpidx, dused, blockSize, fast, triples, tcap, tcount);
+        KLAUNCH(c); KCHECK();
+        k_bwtc_code<<<1, 1, 0, c.stream>>>(st, triples, tcount, nb, tcap);
+        KLAUNCH(c); KCHECK();
+      }
+      c.stats.blocks += nb;
+    }
+  }
+  k_bwtc_finish<<<1, 1, 0, c.stream>>>(st);
+  KLAUNCH(c); KCHECK();
+  BwtcState h;
+  c.to_host(&h, st, sizeof h);
+  c.sync();
+  if (h.overflow) throw B2Error{B2_ERR_CUDA, "internal error: BWTC triple buffer overflow"};
+  if (h.rc.n > h.rc.cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
+  *out_n = hlen + (size_t)h.rc.n;
+}
+
+// ---- decode ---------------------------------------------------------------------------------------------------
+struct BwtcDecResult {
+  int status;       // 0 ok, negative: the stream is nonsense
+  u32 nblocks;
+  u32 level;
+  u32 pad;
+};
+
+// one thread: the whole stream down to the L columns (inverse MTF folded in), block b at slot b << 20
+__global__ void k_bwtc_decode(const u8* __restrict__ in, u64 n, u64 pos, u32 maxblocks, u8* __restrict__ L, u32* __restrict__ lengths,
+                              u32* __restrict__ pidx1, BwtcDecResult* res) {
+  if (threadIdx.x || blockIdx.x) return;
+  bc_dec rc;
+  bc_dec_start(&rc, in, n, pos);                                // lib/BWTC.js:142-143
+  const u32 level = bc_dec_cul(&rc, 256);                       // decoder.decodeByte(), :144
+  bc_dec_update(&rc, 1, level, 256);
+  res->level = level;
+  res->nblocks = 0;
+  if (level < 1 || level > 9) { res->status = B2_ERR_DATA_ERROR; return; }
+  bc_model model;
+  u32 nb = 0;
+  int r = 0;
+  for (;;) {
+    if (nb >= maxblocks) {
+      // only "no more blocks" may follow
+      const u32 ind = bc_dec_cul(&rc, 3);
+      r = ind == 2 ? 1 : B2_ERR_DATA_ERROR;
+      break;
+    }
+    u32 len = 0, p1 = 0;
+    r = bc_decode_block(&rc, &model, level * 100000u, level <= 5, L + ((size_t)nb << SEG_SHIFT), &len, &p1);
+    if (r) break;
+    lengths[nb] = len; pidx1[nb] = p1;
+    nb++;
+  }
+  res->nblocks = nb;
+  res->status = r == 1 ? 0 : B2_ERR_DATA_ERROR;
+}
+
+// BWTC.decompressFile on device buffers.  h_head = the first bytes of the stream on the host (>= 16 or all of it).
+void bwtc_decompress_device(Ctx& c, const u8* d_in, size_t n, const u8* h_head, size_t head_n, u8* d_out, size_t out_cap, size_t* out_n) {
+  if (head_n < 5 || h_head[0] != 'b' || h_head[1] != 'w' || h_head[2] != 't' || h_head[3] != 'c')
+    throw B2Error{B2_ERR_BAD_MAGIC, "Bad magic"};             // lib/Util.js:151-153
+  size_t pos = 4;
+  u64 fs = 0;
+  for (;;) {                                                   // lib/Util.js:211-220 readUnsignedNumber
+    if (pos >= head_n || pos > 14) throw B2Error{B2_ERR_DATA_ERROR, "truncated BWTC header"};
+    const u32 ch = h_head[pos++];
+    if (ch & 0x80) { fs += ch & 0x7F; break; }
+    fs = (fs + ch) * 128;
+  }
+  if (fs == 0) throw B2Error{B2_ERR_BAD_ARG, "BWTC streams of unknown size are not supported"};
+  const u64 size = fs - 1;
+  *out_n = (size_t)size;
+  if (size > out_cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
+  // the level is inside the coded stream: size the buffers for the smallest block size
+  const u32 maxblocks = (u32)(size / 100000u + 2);
+  DBuf<u8> L(c, (size_t)maxblocks << SEG_SHIFT);
+  DBuf<u32> lengths(c, maxblocks), pidx1(c, maxblocks);
+  DBuf<BwtcDecResult> res(c, 1);
+  {
+    StageScope s(c, ST_HDEC);
+    k_bwtc_decode<<<1, 1, 0, c.stream>>>(d_in, n, pos, maxblocks, L, lengths, pidx1, res);
+    KLAUNCH(c); KCHECK();
+  }
+  BwtcDecResult h;
+  c.to_host(&h, res, sizeof h);
+  c.sync();
+  if (h.status) throw B2Error{B2_ERR_DATA_ERROR, "Data error: BWTC stream is corrupt"};
+  std::vector<u32> hl(h.nblocks), hp(h.nblocks);
+  if (h.nblocks) {
+    c.to_host(hl.data(), lengths, 4 * h.nblocks);
+    c.to_host(hp.data(), pidx1, 4 * h.nblocks);
+    c.sync();
+  }
+  u64 total = 0;
+  for (u32 b = 0; b < h.nblocks; b++) total += hl[b];
+  if (total != size) throw B2Error{B2_ERR_DATA_ERROR, "outputsize does not match decoded input"};   // lib/Util.js:69-71
+  u64 off = 0;
+  StageScope s(c, ST_IBWT);
+  for (u32 b = 0; b < h.nblocks; b++) {                         // BWT.unbwtransform per block, lib/BWTC.js:224
+    const u8* Lb = L.p + ((size_t)b << SEG_SHIFT);
+    if (hl[b] == 1) CUDA_CHECK(cudaMemcpyAsync(d_out + off, Lb, 1, cudaMemcpyDeviceToDevice, c.stream));
+    else bwt_inverse_sentinel(c, Lb, hl[b], hp[b], d_out + off);
+    off += hl[b];
+  }
+  c.stats.blocks += h.nblocks;
+}

@@ -32,6 +32,7 @@ extern "C" {
 #define B2_ERR_OBSOLETE_INPUT (-7) /* lib/Bzip2.js:71 */
 #define B2_ERR_BAD_LEVEL (-100)   /* lib/Bzip2.js:888-890 "Invalid block size multiplier" */
 #define B2_ERR_BAD_ARG (-101)
+#define B2_ERR_BAD_MAGIC (-102)   /* lib/Util.js:151-153 Error("Bad magic") of the BWTC container */
 #define B2_ERR_CUDA (-200)        /* CUDA runtime failure or no device: never falls back to CPU */
 
 /* Select the CUDA device (ordinal) used by this process and create the context.
@@ -68,6 +69,11 @@ int32_t b2_bwt_sentinel(const uint8_t* T, uint8_t* U, int32_t n);
 /* BWT.unbwtransform(T, U, LF, n, pidx)                lib/BWT.js:352-363 (L = the transformed string, pidx as
  * returned by bwtransform; LF is scratch in the reference) */
 int b2_bwt_inverse(const uint8_t* L, uint8_t* out, int32_t n, int32_t pidx);
+/* ---- compressjs.BWTC (lib/BWTC.js) -- EXPERIMENTAL: see compressjs_b200/csrc/bwtc.cu ---------------------------
+ * BWTC.compressFile(input, output, level)             lib/BWTC.js:12-139 (level outside 1..9 means 9, as there) */
+int b2_bwtc_compress(const uint8_t* in, size_t n, int level, uint8_t** out, size_t* out_n);
+/* BWTC.decompressFile(input, output)                  lib/BWTC.js:141-231 (streams that carry their size) */
+int b2_bwtc_decompress(const uint8_t* in, size_t n, uint8_t** out, size_t* out_n);
 /* CRC32 helper object of lib/CRC32.js:72-103 (bzip2 polynomial, MSB first) */
 uint32_t b2_crc32_bzip2(const uint8_t* p, size_t n);
 

@@ -1,0 +1,44 @@
+"""GPU parity of the experimental BWTC container path (compressjs_b200/csrc/bwtc.cu; lib/BWTC.js:12-231) against
+the oracle.  OPT-IN (B2_TEST_BWTC=1) until the kernels have been run on a B200 once: the round that wrote them ended
+its GPU budget first, and the serial code they execute is checked on the host by
+tests/test_host_api.py::test_bwtc_core_matches_oracle."""
+import os
+
+import pytest
+
+from oracle import oracle as O
+from tests import util as T
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B2_TEST_BWTC") != "1", reason="experimental BWTC path: set B2_TEST_BWTC=1")]
+
+
+@pytest.mark.parametrize("level", [1, 5, 6, 9])
+@pytest.mark.parametrize("name", ["sample0", "sample1", "sample2", "sample3"])
+def test_bwtc_samples(name, level):
+    from compressjs_b200 import BWTC
+    d = T.fixture(name + ".ref")
+    z = BWTC.compressFile(d, None, level)
+    assert z == O.bwtc_compress(d, level)
+    assert BWTC.decompressFile(z) == d
+
+
+@pytest.mark.parametrize("data", [b"", b"a", b"ab", b"\x00" * 5000, bytes(range(256)) * 9])
+def test_bwtc_edges(data):
+    from compressjs_b200 import BWTC
+    for level in (1, 9):
+        z = BWTC.compressFile(data, None, level)
+        assert z == O.bwtc_compress(data, level)
+        assert BWTC.decompressFile(z) == data
+
+
+def test_bwtc_multi_block_and_errors():
+    from compressjs_b200 import BWTC
+    d = T.ascii_random(250001, 3) + T.runs(60000, 4) + T.texty(120000, 5)
+    for level in (1, 2, 6):   # 430001 bytes: full and short blocks
+        z = BWTC.compressFile(d, None, level)
+        assert z == O.bwtc_compress(d, level)
+        assert BWTC.decompressFile(z) == d
+    assert BWTC.compressFile(d, None, 12) == O.bwtc_compress(d, 9)   # lib/BWTC.js:16-19
+    with pytest.raises(ValueError):
+        BWTC.decompressFile(b"bzzt" + b"\x81\x00\x00\x00")

@@ -111,3 +111,53 @@ def test_device_allocator_port_matches_kats():
         n = int(g.integers(3, 259))
         fr = np.sort(g.integers(0, 900000, size=n)).astype(np.int32)
         assert f(fr, 20) == O.huffman_code_lengths(fr.tolist(), 20)
+
+
+def test_bwtc_core_matches_oracle():
+    """compressjs_b200/csrc/bwtc_core.cuh (the serial model + range coder that bwtc.cu runs on the GPU) built for the
+    host: container bytes and decoded L columns must equal the oracle's for every level family."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    from oracle import oracle as O
+    so = os.path.join(tempfile.gettempdir(), "libbwtc_host_test.so")
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-x", "c", os.path.join(ROOT, "tests", "host", "bwtc_host.c"), "-o", so])
+    L = C.CDLL(so)
+    L.host_bwtc_encode.restype = C.c_size_t
+    L.host_bwtc_encode.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
+    L.host_bwtc_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+
+    def enc(data, level):
+        bs = level * 100000
+        blocks = [data[i:i + bs] for i in range(0, len(data), bs)]
+        pairs = [O.bwt_sentinel(b) for b in blocks]
+        lens = np.array([len(b) for b in blocks], dtype=np.uint32)
+        pp = np.array([p for _, p in pairs], dtype=np.uint32)
+        U = np.frombuffer(b"".join(u for u, _ in pairs) or b"\0", dtype=np.uint8).copy()
+        cap = len(data) * 2 + 4096
+        out = np.zeros(cap, dtype=np.uint8)
+        n = L.host_bwtc_encode(level, len(blocks), lens.ctypes.data, pp.ctypes.data, U.ctypes.data, len(data), out.ctypes.data, cap)
+        return bytes(out[:n])
+
+    def dec(z, n):
+        Lout = np.zeros(max(n, 1), dtype=np.uint8)
+        lens = np.zeros(64, dtype=np.uint32)
+        pp = np.zeros(64, dtype=np.uint32)
+        fs = C.c_uint64()
+        a = np.frombuffer(z, dtype=np.uint8).copy()
+        nb = L.host_bwtc_decode(a.ctypes.data, a.size, Lout.ctypes.data, Lout.size, lens.ctypes.data, pp.ctypes.data, 64, C.byref(fs))
+        assert nb >= 0 and fs.value == n + 1
+        out, off = b"", 0
+        for k in range(nb):
+            ln = int(lens[k])
+            out += O.unbwt_sentinel(bytes(Lout[off:off + ln]), int(pp[k]))
+            off += ln
+        return out
+
+    cases = [T.fixture("sample0.ref"), T.fixture("sample2.ref"), T.fixture("sample5.ref")[:450001], b"", b"a", b"\x00" * 5000,
+             T.ascii_random(250001, 3) + T.runs(60000, 4)]
+    for d in cases:
+        for level in (1, 2, 5, 6, 9):
+            ref = O.bwtc_compress(d, level)
+            assert enc(d, level) == ref
+            assert dec(ref, len(d)) == d
