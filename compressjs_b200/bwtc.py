@@ -1,7 +1,6 @@
 """compressjs.BWTC on the GPU (lib/BWTC.js:10-231): same two entry points and the same container bytes.
 
-EXPERIMENTAL: the kernels of csrc/bwtc.cu have not yet run on a B200 (see its header); the serial model and
-range-coder code they execute is verified on its host build.  The block stages (sentinel BWT, MTF, zero runs) are
+New in round 1 (see the header of csrc/bwtc.cu for what has been verified where).  The block stages (sentinel BWT, MTF, zero runs) are
 the block-parallel kernels of the bzip2 path; the range coder is one serial chain over the file, so this path is
 bound by a single GPU thread."""
 import ctypes as C

@@ -69,7 +69,7 @@ int32_t b2_bwt_sentinel(const uint8_t* T, uint8_t* U, int32_t n);
 /* BWT.unbwtransform(T, U, LF, n, pidx)                lib/BWT.js:352-363 (L = the transformed string, pidx as
  * returned by bwtransform; LF is scratch in the reference) */
 int b2_bwt_inverse(const uint8_t* L, uint8_t* out, int32_t n, int32_t pidx);
-/* ---- compressjs.BWTC (lib/BWTC.js) -- EXPERIMENTAL: see compressjs_b200/csrc/bwtc.cu ---------------------------
+/* ---- compressjs.BWTC (lib/BWTC.js) -- new, bound by one serial coder thread: see compressjs_b200/csrc/bwtc.cu -----
  * BWTC.compressFile(input, output, level)             lib/BWTC.js:12-139 (level outside 1..9 means 9, as there) */
 int b2_bwtc_compress(const uint8_t* in, size_t n, int level, uint8_t** out, size_t* out_n);
 /* BWTC.decompressFile(input, output)                  lib/BWTC.js:141-231 (streams that carry their size) */

@@ -1,16 +1,12 @@
-"""GPU parity of the experimental BWTC container path (compressjs_b200/csrc/bwtc.cu; lib/BWTC.js:12-231) against
-the oracle.  OPT-IN (B2_TEST_BWTC=1) until the kernels have been run on a B200 once: the round that wrote them ended
-its GPU budget first, and the serial code they execute is checked on the host by
-tests/test_host_api.py::test_bwtc_core_matches_oracle."""
-import os
-
+"""GPU parity of the BWTC container path (compressjs_b200/csrc/bwtc.cu; lib/BWTC.js:12-231) against the oracle.
+The file sorts last on purpose: the path is the newest one (first B200 run: profiles/r1e_bwtc_try.txt, 12 cases bit
+exact); the serial code it executes is also checked on the host by tests/test_host_api.py::test_bwtc_core_matches_oracle."""
 import pytest
 
 from oracle import oracle as O
 from tests import util as T
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B2_TEST_BWTC") != "1", reason="experimental BWTC path: set B2_TEST_BWTC=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("level", [1, 5, 6, 9])
