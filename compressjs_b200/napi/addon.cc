@@ -98,6 +98,32 @@ static napi_value Bwtransform2(napi_env env, napi_callback_info info) {
   return r;
 }
 
+// bwtcCompressFile(buffer, level) -> Buffer        (BWTC.compressFile, lib/BWTC.js:12)
+static napi_value BwtcCompressFile(napi_env env, napi_callback_info info) {
+  size_t argc = 2; napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* in; size_t n; int32_t level = 9;
+  if (!buf_arg(env, argv[0], &in, &n)) return fail(env, B2_ERR_BAD_ARG);
+  if (argc > 1) napi_get_value_int32(env, argv[1], &level);
+  uint8_t* out; size_t out_n;
+  int rc = b2_bwtc_compress(in, n, level, &out, &out_n);
+  if (rc) return fail(env, rc);
+  napi_value buf; napi_create_external_buffer(env, out_n, out, fin, nullptr, &buf);
+  return buf;
+}
+// bwtcDecompressFile(buffer) -> Buffer              (BWTC.decompressFile, lib/BWTC.js:141)
+static napi_value BwtcDecompressFile(napi_env env, napi_callback_info info) {
+  size_t argc = 1; napi_value argv[1];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t* in; size_t n;
+  if (!buf_arg(env, argv[0], &in, &n)) return fail(env, B2_ERR_BAD_ARG);
+  uint8_t* out; size_t out_n;
+  int rc = b2_bwtc_decompress(in, n, &out, &out_n);
+  if (rc == B2_ERR_BAD_MAGIC) { napi_throw_error(env, nullptr, "Bad magic"); return nullptr; }   // lib/Util.js:151-153
+  if (rc) return fail(env, rc);
+  napi_value buf; napi_create_external_buffer(env, out_n, out, fin, nullptr, &buf);
+  return buf;
+}
 // suffixsort(T, SA /* Int32Array */, n) -> 0        (BWT.suffixsort, lib/BWT.js:305)
 static napi_value Suffixsort(napi_env env, napi_callback_info info) {
   size_t argc = 3; napi_value argv[3];
@@ -148,6 +174,8 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"suffixsort", nullptr, Suffixsort, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"bwtransform", nullptr, Bwtransform, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"unbwtransform", nullptr, Unbwtransform, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"bwtcCompressFile", nullptr, BwtcCompressFile, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"bwtcDecompressFile", nullptr, BwtcDecompressFile, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;

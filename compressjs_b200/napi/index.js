@@ -53,4 +53,14 @@ BWT.suffixsort = function(T, SA, n) { return native.suffixsort(T, SA, n); };
 BWT.bwtransform = function(T, U, A, n) { return native.bwtransform(T, U, n); };
 BWT.unbwtransform = function(T, U, LF, n, pidx) { native.unbwtransform(T, U, n, pidx); };
 
-module.exports = Object.freeze({ version: '0.0.1', Bzip2: Bzip2, BWT: BWT });
+var BWTC = Object.create(null);   // lib/BWTC.js:10-231
+BWTC.MAGIC = 'bwtc';
+BWTC.compressFile = function(inStream, outStream, props) {
+  var level = (typeof props === 'number' && props >= 1 && props <= 9) ? props : 9;   // :16-19
+  return deliver(outStream, native.bwtcCompressFile(drain(inStream), level));
+};
+BWTC.decompressFile = function(input, output) {
+  return deliver(output, native.bwtcDecompressFile(drain(input)));
+};
+
+module.exports = Object.freeze({ version: '0.0.1', Bzip2: Bzip2, BWT: BWT, BWTC: BWTC });
