@@ -24,6 +24,9 @@ for k in range(6):
             "size": len(z), "sha256": hashlib.sha256(z).hexdigest(),
             "blocks": [{"n": t.n, "pidx": t.pidx, "m": t.m, "alpha": t.alpha, "ngroups": t.ngroups, "nsel": t.nsel,
                         "crc": t.crc, "bit_start": t.bit_start, "bit_len": t.bit_len} for t in tr]}
+    for lv in (1, 6, 9):   # BWTC container (oracle/bwtc_oracle.c); -9 and sample5 -1 equal SURVEY.md section 8c / README.md:41,46
+        z = O.bwtc_compress(data, lv)
+        out["bwtc_%s_-%d" % (name, lv)] = {"size": len(z), "sha256": hashlib.sha256(z).hexdigest()}
 for lv in (1, 9):
     z = O.bzip2_compress(open(os.path.join(REF, "sample5.ref"), "rb").read(), lv, legacy_sort=True)
     out["bzip2_sample5_-%d_legacy_v8_sort" % lv] = {"size": len(z), "sha256": hashlib.sha256(z).hexdigest()}

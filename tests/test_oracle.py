@@ -169,3 +169,12 @@ def test_bwtc_other_levels_and_edges():
             assert O.bwtc_decompress(O.bwtc_compress(data, level)) == data   # 700001 bytes: full + short blocks at -1, -5, -6
     with pytest.raises(O.OracleError):
         O.bwtc_decompress(b"bzzt" + b"\x81\x00\x00\x00\x00\x00")
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_bwtc_committed_golden(k):
+    d = T.fixture("sample%d.ref" % k)
+    for level in (1, 6, 9):
+        z = O.bwtc_compress(d, level)
+        g = T.golden()["bwtc_sample%d_-%d" % (k, level)]
+        assert (len(z), hashlib.sha256(z).hexdigest()) == (g["size"], g["sha256"])
