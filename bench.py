@@ -351,6 +351,14 @@ def main():
             line["cpu_baseline"] = {"value": sample.size / dtc / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
                                     "sample": "first 8 x 900k blocks (%d bytes) of the same workload, oracle/bz2_oracle.c, 1 thread" % sample.size,
                                     "compressed_bytes": len(zc)}
+            # yardsticks SURVEY.md section 8(d) asks for next to the port: libbz2 1.0.8 on one core (a different, much
+            # cheaper table search: NOT bit-compatible) and the reference's own published single-thread figure
+            import bz2
+            tl = time.perf_counter()
+            zl = bz2.compress(sample.tobytes(), LEVEL)
+            line["cpu_baseline"]["libbz2_1thread_MBps"] = sample.size / (time.perf_counter() - tl) / 1e6
+            line["cpu_baseline"]["libbz2_compressed_bytes"] = len(zl)
+            line["cpu_baseline"]["reference_js_published_MBps"] = 0.0936   # README.md:70 of the reference (enwik8, node 0.8, 2013 laptop)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
