@@ -25,7 +25,8 @@ class Stats(C.Structure):
                  "ms_scan", "ms_hdec", "ms_unmtf", "ms_ibwt", "ms_unrle", "ms_radix")] + \
                [(n, C.c_uint64) for n in
                 ("radix_launches", "radix_bytes", "bwt_bytes", "bwt_rounds", "kernel_launches", "blocks",
-                 "raw_bytes", "comp_bytes")]
+                 "raw_bytes", "comp_bytes", "msd_launches", "msd_scatter_bytes", "msd_bucket_bytes")] + \
+               [(n, C.c_float) for n in ("ms_msd_scatter", "ms_msd_bucket")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

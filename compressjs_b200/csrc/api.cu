@@ -49,6 +49,7 @@ void Ctx::collect() {
   stats.ms_huff = acc[ST_HUFF]; stats.ms_pack = acc[ST_PACK]; stats.ms_scan = acc[ST_SCAN];
   stats.ms_hdec = acc[ST_HDEC]; stats.ms_unmtf = acc[ST_UNMTF]; stats.ms_ibwt = acc[ST_IBWT];
   stats.ms_unrle = acc[ST_UNRLE]; stats.ms_radix = acc[ST_RADIX];
+  stats.ms_msd_scatter = acc[ST_MSD_SCATTER]; stats.ms_msd_bucket = acc[ST_MSD_BUCKET];
   // overlapped copies of the pipelined host path: span from the first to the last copy on their stream
   for (int w = 0; w < 2; w++) {
     float ms = 0.f;
@@ -137,6 +138,8 @@ static Ctx& ctx_locked() {
     CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     const char* b = getenv("B2_BWT_BATCH");
     if (b && atoi(b) > 0) c->bwt_batch = (u32)atoi(b);
+    const char* msd = getenv("B2_BWT_MSD");
+    if (msd && *msd) c->bwt_msd = atoi(msd) != 0;
     const char* w8 = getenv("B2_BWT_PREFIX8");
     if (w8 && *w8) { c->bwt_wide_forced = true; c->bwt_wide = atoi(w8) != 0; }
     g_ctx = c;

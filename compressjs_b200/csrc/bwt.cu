@@ -20,6 +20,7 @@
 #include "ctx.h"
 #include "radix.cuh"
 #include "radix_host.cuh"
+#include "bwt_msd.h"
 
 // ---------------------------------------------------------------------------------------
 // key32 = first four bytes of every rotation; hist[b][256] = byte histogram of block b (which is the
@@ -57,11 +58,11 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
       // low word: the byte BEFORE the rotation (its BWT output, so the emit pass needs no gather) and its position;
       // the block is implied by the slot the record sits in (the sort never moves a record out of its segment)
       ko[i] = ((u64)((c0 << 24) | ((u32)t[i1] << 16) | ((u32)t[i2] << 8) | (u32)t[i3]) << 32) | (((u32)t[i ? i - 1 : n - 1] << SEG_SHIFT) | i);
-      atomicAdd(&h[c0], 1u);
+      if (hist) atomicAdd(&h[c0], 1u);
     }
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
+  if (hist && h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(BK_THREADS) k_byte_hist(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ hist) {
@@ -509,41 +510,65 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   const u32 nslots = nblk << SEG_SHIFT;
   DBuf<u64> recA(c, nslots), recB(c, nslots);
   DBuf<u32> saBuf(c, nslots), rank(c, nslots);
-  DBuf<u32> headA(c, n_total), idxA(c, n_total), cnt(c, 2), ticket(c, 1);
+  DBuf<u32> headA(c, n_total), idxA(c, n_total), cnt(c, 4), ticket(c, 1);
   const u32 rr_tiles_init = (nslots + RR_TILE - 1) / RR_TILE;
   DBuf<u64> st(c, (size_t)3 * rr_tiles_init);
   u64 *kin = recA, *kout = recB;
   u32 *vin = nullptr, *vout = nullptr;
 
   DBuf<u32> bytehist(c, (size_t)nblk * 256);
+  DBuf<float> dscore(c, 1);
   CUDA_CHECK(cudaMemsetAsync(bytehist, 0, (size_t)nblk * 256 * 4, c.stream));
   const u32 bk_tps = (n_max + BK_THREADS * BK_ITEMS - 1) / (BK_THREADS * BK_ITEMS);
+  // The block byte histograms come first: they are the digit histogram of every pass of the 4-byte-prefix sort, the
+  // bucket sizes of the MSD path and the input of the text-likeness score that picks the mode of the batch.
+  if (!sentinel) {
+    k_byte_hist<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, bytehist);
+    KLAUNCH(c); KCHECK();
+    c.stats.bwt_bytes += n_total;
+  }
+  k_text_score<<<1, 256, 0, c.stream>>>(bytehist, d_n, nblk, dscore);  // sentinel mode: zero histogram, score 0
+  KLAUNCH(c); KCHECK();
   // Text-like batches (many 4-byte-prefix collisions) sort on the first EIGHT bytes before the doubling
   // rounds start: bytes 4..7 first, then a stable sort on bytes 0..3 -- two cheap keys-only sorts replace
-  // the h=4 round over nearly all suffixes.  The mode of a batch follows the score of the previous batch
-  // of the same call (first batch: 4-byte mode unless B2_BWT_PREFIX8=1), so no extra host sync is needed.
+  // the h=4 round over nearly all suffixes.  The first batch of a call reads its own score (one small sync);
+  // later batches follow the score of the batch before them (B2_BWT_PREFIX8 forces the mode).
   if (!sentinel && !c.bwt_wide_forced && !c.bwt_mode_known) {
-    // first batch of a call: decide from the byte histogram (one cheap extra pass over the text + one small sync)
-    DBuf<u32> h0(c, (size_t)nblk * 256);
-    DBuf<float> sc0(c, 1);
-    CUDA_CHECK(cudaMemsetAsync(h0, 0, (size_t)nblk * 256 * 4, c.stream));
-    k_byte_hist<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, h0);
-    KLAUNCH(c); KCHECK();
-    k_text_score<<<1, 256, 0, c.stream>>>(h0, d_n, nblk, sc0);
-    KLAUNCH(c); KCHECK();
     float sc = 0.f;
-    c.to_host(&sc, sc0, 4);
+    c.to_host(&sc, dscore, 4);
     c.sync();
     c.bwt_wide = sc > 0.5f;
     c.bwt_mode_known = true;
   }
   const bool wide = sentinel ? false : c.bwt_wide;
-  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, bytehist, wide ? 4u : 0u, sentinel ? 1 : 0);
+  if (!wide && !sentinel && c.bwt_msd) {
+    // sparse-tie batches: one MSD pass + shared-memory bucket sorts (bwt_msd.cu); ties on 5 bytes are ordered directly
+    CUDA_CHECK(cudaMemsetAsync(cnt, 0, 16, c.stream));
+    bwt_msd_launch(c, d_T, d_U, d_n, nblk, n_max, n_total, bytehist, recA, d_pidx, headA, idxA, cnt);
+    u32 h_ctl[4] = {0, 0, 0, 0};
+    float score = 0.f;
+    c.to_host(h_ctl, cnt, 16);
+    c.to_host(&score, dscore, 4);
+    c.sync();
+    if (!c.bwt_wide_forced) c.bwt_wide = score > 0.5f;  // next batch of this call
+    if (!h_ctl[2]) {
+      const u32 Mt = h_ctl[0];
+      u32 failed = 0;
+      if (Mt > n_total / 8) failed = 1;
+      else if (Mt) {
+        k_resolve_direct<<<(Mt + 127) / 128, 128, 0, c.stream>>>(headA, idxA, Mt, d_T, d_n, 5, d_U, d_pidx, cnt.p + 1);
+        KLAUNCH(c); KCHECK();
+        c.stats.bwt_bytes += (u64)Mt * 80;
+        c.to_host(&failed, cnt.p + 1, 4);
+        c.sync();
+      }
+      if (!failed) return;
+    }
+    // an oversized bucket or long repeats after all: the LSD path below redoes the batch
+  }
+  k_build_keys<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, kin, nullptr, wide ? 4u : 0u, sentinel ? 1 : 0);
   KLAUNCH(c); KCHECK();
   c.stats.bwt_bytes += n_total * 9;
-  DBuf<float> dscore(c, 1);
-  k_text_score<<<1, 256, 0, c.stream>>>(bytehist, d_n, nblk, dscore);
-  KLAUNCH(c); KCHECK();
   // keys-only sort of the packed records on their upper 32 bits
   // (sentinel mode: the zero padding breaks the "byte histogram = digit histogram" identity, so the sort counts its own)
   radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, sentinel ? nullptr : bytehist.p);

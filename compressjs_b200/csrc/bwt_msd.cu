@@ -1,0 +1,335 @@
+// bwt_msd.cu -- forward cyclic BWT for batches whose short prefixes rarely collide (near-uniform data such as
+// BASELINE config 2): ONE most-significant-digit pass over HBM + a shared-memory sort of every (block, first byte)
+// bucket, instead of four least-significant-digit passes (radix.cuh).
+//
+//   k_byte_hist (bwt.cu)   block byte histograms = bucket sizes
+//   k_msd_prep             bucket offsets, dense symbol ranks, the scale that spreads 4-symbol keys over 32 bits
+//   k_msd_scatter          text tile -> records (key32 = symbols 1..4 of the rotation as a scaled mixed-radix number,
+//                          byte before the rotation, position) scattered into their first-byte bucket.  An MSD pass
+//                          may be unstable, so ranks come from shared-memory atomics and bucket space from one global
+//                          atomic per (tile, digit): no look-back chain, no warp match.  The tile arrives by bulk copy.
+//   k_msd_bucket           persistent CTAs: the next bucket streams into shared memory by bulk copy (mbarrier) while
+//                          the current one is sorted: interpolation cells (key >> 18) counted with shared-memory atomics,
+//                          scanned, scattered in place, then every record ranks itself inside its cell.  The sorted
+//                          order is only used to write the BWT column (the byte travels in the record) and pidx; equal
+//                          keys (rotations that share 5 bytes) go to the tie list for k_resolve_direct (bwt.cu).
+//
+// Contract: lib/BWT.js:372-417 (bwtransform2), same result as the LSD path.  Algorithmic HBM bytes per text byte:
+// 1 (histogram) + 1 + 8 (scatter) + 8 + 1 (bucket sort) = 19.
+#include "ctx.h"
+#include "tma.cuh"
+#include "bwt_msd.h"
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_msd_prep(const u32* __restrict__ hist, u32* __restrict__ bstart, u32* __restrict__ cursor, u8* __restrict__ lut, MsdBlk* __restrict__ blk,
+           uint4* __restrict__ work, u32* ctl) {
+  __shared__ u32 ws[9];
+  __shared__ u32 s_base;
+  const u32 b = blockIdx.x, d = threadIdx.x;
+  const u32 h = hist[b * 256 + d];
+  u32 tot;
+  const u32 ex = block_excl_add<256, u32>(h, ws, &tot);
+  bstart[b * 256 + d] = ex;
+  cursor[b * 256 + d] = ex;
+  const u32 r = block_excl_add<256, u32>(h ? 1u : 0u, ws, &tot);  // tot = symbols in use
+  lut[b * 256 + d] = (u8)r;
+  if (h > MB_CAP) atomicOr(&ctl[2], 1u);  // a bucket that does not fit the shared-memory sort: LSD path for this batch
+  if (d == 0) {
+    const u64 a = tot, a4 = a * a * a * a;
+    MsdBlk m;
+    m.a = (u32)a;
+    m.a2 = (u32)(a * a);
+    // key * S >> 32 is strictly increasing in key as long as S >= 2^32 (a <= 255); 256 symbols: the key is the 4 raw bytes
+    m.S = a4 >= (1ull << 32) ? (1ull << 32) : (a4 ? 0xffffffffffffffffull / a4 : 0ull);
+    blk[b] = m;
+    s_base = atomicAdd(&ctl[3], (u32)a);  // the block's non-empty buckets take consecutive entries of the work list
+  }
+  __syncthreads();
+  if (h) work[s_base + r] = make_uint4(b * 256 + d, ex, h, 0u);  // (bucket id, first row inside the block, records)
+}
+
+// ---------------------------------------------------------------------------------------
+struct MsdScatterSmem {
+  __align__(16) u8 raw[16 + MSD_TILE + 16];  // raw[15] = byte before the tile, raw[16..] the tile, then 4 bytes of look-ahead
+  __align__(16) u8 rk[MSD_TILE + 16];        // dense symbol ranks of raw[16..]
+  __align__(16) u64 rec[MSD_TILE];
+  u8 dig[MSD_TILE];
+  u32 cnt[256];
+  int gdst[256];
+  u8 lut[256];
+  u32 ws[9];
+  __align__(8) u64 bar;
+};
+
+__device__ __forceinline__ u32 lut4(const u8* lut, u32 w) {
+  return (u32)lut[w & 0xff] | ((u32)lut[(w >> 8) & 0xff] << 8) | ((u32)lut[(w >> 16) & 0xff] << 16) | ((u32)lut[w >> 24] << 24);
+}
+
+__global__ void __launch_bounds__(MSD_THREADS, 4)
+k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, const u8* __restrict__ lut, const MsdBlk* __restrict__ blk,
+              u32* __restrict__ cursor, u64* __restrict__ rec_out, const u32* __restrict__ ctl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MsdScatterSmem& s = *reinterpret_cast<MsdScatterSmem*>(smem_raw);
+  if (ctl[2]) return;
+  const u32 b = blockIdx.x / tps, lt = blockIdx.x - b * tps;
+  const u32 n = seg_n[b];
+  const u32 start = lt * MSD_TILE;
+  if (start >= n) return;
+  const u32 count = min((u32)MSD_TILE, n - start);
+  const u8* Tb = T + ((size_t)b << SEG_SHIFT);
+  const u32 tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&s.bar, 1); mbar_fence_init(); }
+  s.lut[tid] = lut[b * 256 + tid];
+  s.cnt[tid] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    // the whole tile in one bulk copy (a short last tile reads on into the unused rest of the 1 MiB slot)
+    mbar_expect_tx(&s.bar, MSD_TILE);
+    bulk_g2s(s.raw + 16, Tb + start, MSD_TILE, &s.bar);
+  }
+  if (tid == 32) s.raw[15] = start ? Tb[start - 1] : Tb[n - 1];
+  mbar_wait(&s.bar, 0);
+  // look-ahead of the last rotations of the tile: the next text bytes, cyclically
+  if (tid < 4) s.raw[16 + count + tid] = Tb[(start + count + tid) % n];
+  __syncthreads();
+  // ---- dense ranks of the own 16 bytes ----
+  const uint4 rv = *reinterpret_cast<const uint4*>(s.raw + 16 + tid * 16);
+  {
+    uint4 kv;
+    kv.x = lut4(s.lut, rv.x); kv.y = lut4(s.lut, rv.y); kv.z = lut4(s.lut, rv.z); kv.w = lut4(s.lut, rv.w);
+    *reinterpret_cast<uint4*>(s.rk + tid * 16) = kv;
+    if (tid < 4) s.rk[count + tid] = s.lut[s.raw[16 + count + tid]];  // look-ahead ranks (same value as the owner's store, if any)
+  }
+  __syncthreads();
+  const MsdBlk mb = blk[b];
+  const u32 a = mb.a, a2 = mb.a2, S_lo = (u32)mb.S, S_hi = (u32)(mb.S >> 32);
+  u32 key[MSD_ITEMS], slot[MSD_ITEMS / 2];
+  {
+    const uint4 k0 = *reinterpret_cast<const uint4*>(s.rk + tid * 16);
+    const u32 k1 = *reinterpret_cast<const u32*>(s.rk + tid * 16 + 16);
+    const u32 kw[5] = {k0.x, k0.y, k0.z, k0.w, k1};
+    u32 rr[20];
+#pragma unroll
+    for (int j = 0; j < 20; j++) rr[j] = (kw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+    u32 v2[19];  // two symbols starting at j
+#pragma unroll
+    for (int j = 1; j < 19; j++) v2[j] = rr[j] * a + rr[j + 1];
+    const u32 rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+    for (int j = 0; j < MSD_ITEMS; j++) {
+      const u32 k = v2[j + 1] * a2 + v2[j + 3];          // symbols j+1 .. j+4 as a base-a number
+      key[j] = k * S_hi + __umulhi(k, S_lo);             // spread over 32 bits (order preserving, injective)
+      const u32 d = (rw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+      u32 sl = 0;
+      if (tid * MSD_ITEMS + j < count) sl = atomicAdd(&s.cnt[d], 1u);
+      if (j & 1) slot[j >> 1] |= sl << 16; else slot[j >> 1] = sl;
+    }
+  }
+  __syncthreads();
+  // ---- per digit: space in the block's bucket (any order: the bucket is sorted afterwards) ----
+  {
+    const u32 c = s.cnt[tid];
+    u32 tot;
+    const u32 ex = block_excl_add<MSD_THREADS, u32>(c, s.ws, &tot);
+    const u32 g = c ? atomicAdd(&cursor[b * 256 + tid], c) : 0u;
+    s.gdst[tid] = (int)g - (int)ex;
+    s.cnt[tid] = ex;
+  }
+  __syncthreads();
+  // ---- stage the tile in digit order ----
+  {
+    const u32 rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    u32 prev = s.raw[15 + tid * 16];
+#pragma unroll
+    for (int j = 0; j < MSD_ITEMS; j++) {
+      const u32 d = (rw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+      if (tid * MSD_ITEMS + j < count) {
+        const u32 sl = (j & 1) ? (slot[j >> 1] >> 16) : (slot[j >> 1] & 0xffffu);
+        const u32 p = s.cnt[d] + sl;
+        s.rec[p] = ((u64)key[j] << 32) | (u64)((prev << SEG_SHIFT) | (start + tid * MSD_ITEMS + j));
+        s.dig[p] = (u8)d;
+      }
+      prev = d;
+    }
+  }
+  __syncthreads();
+  u64* out = rec_out + ((size_t)b << SEG_SHIFT);
+#pragma unroll
+  for (int k = 0; k < MSD_ITEMS; k++) {
+    const u32 p = k * MSD_THREADS + tid;
+    if (p < count) out[(int)p + s.gdst[s.dig[p]]] = s.rec[p];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct MsdBucketSmem {
+  __align__(16) u64 buf[2][MB_BUF];
+  __align__(16) u32 cnt[MB_CELLS / 2];  // two 16-bit cell counters per word
+  u32 ws[MB_THREADS / 32 + 1];
+  __align__(8) u64 bar[2];
+  u32 w[2], M[2], off[2], st[2];
+};
+
+__device__ __forceinline__ u32 cell_of(u32 key) { return key >> (32 - MB_CELL_BITS); }
+
+__global__ void __launch_bounds__(MB_THREADS, 1)
+k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __restrict__ U, u32* __restrict__ pidx,
+             u32* __restrict__ tie_head, u32* __restrict__ tie_idx, u32* ctl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MsdBucketSmem& s = *reinterpret_cast<MsdBucketSmem*>(smem_raw);
+  if (ctl[2]) return;
+  const u32 tid = threadIdx.x;
+  const u32 nw = ctl[3];
+  // Thread 0 is the producer.  Work descriptors are fetched one round ahead of their use, so that the only global
+  // latency on its path is already covered when the bulk copy of the next bucket is issued.
+  auto issue = [&](u32 i, uint4 d) {
+    const u32 w = d.x, st = d.y, M = d.z, off = st & 1u;
+    s.w[i] = w; s.M[i] = M; s.off[i] = off; s.st[i] = st;
+    if (!M) return;  // end of this CTA's list
+    const u32 recs = (M + off + 1u) & ~1u;  // 16-byte granules: at most one foreign record on each side
+    mbar_expect_tx(&s.bar[i], recs * 8u);
+    bulk_g2s(s.buf[i], rec + (((size_t)(w >> 8)) << SEG_SHIFT) + (st - off), recs * 8u, &s.bar[i]);
+  };
+  uint4 dnext = make_uint4(0, 0, 0, 0);
+  u32 inext = blockIdx.x + gridDim.x;
+  if (tid == 0) {
+    mbar_init(&s.bar[0], 1); mbar_init(&s.bar[1], 1); mbar_fence_init();
+    issue(0, blockIdx.x < nw ? work[blockIdx.x] : dnext);
+    if (inext < nw) dnext = work[inext];
+  }
+  __syncthreads();
+  for (u32 it = 0;; it++) {
+    const u32 i = it & 1u;
+    if (s.M[i] == 0) break;
+    const u32 w = s.w[i];
+    if (tid == 0) {  // the other buffer was released by the barrier that ended the last round
+      issue(i ^ 1u, dnext);
+      inext += gridDim.x;
+      dnext = inext < nw ? work[inext] : make_uint4(0, 0, 0, 0);
+    }
+    const u32 M = s.M[i], off = s.off[i], ust = s.st[i], blockb = w >> 8;
+    u64* buf = s.buf[i];
+    {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      uint4* c4 = reinterpret_cast<uint4*>(s.cnt);
+#pragma unroll
+      for (u32 k = 0; k < MB_CELLS / 8 / MB_THREADS; k++) c4[tid + k * MB_THREADS] = z;
+    }
+    mbar_wait(&s.bar[i], (it >> 1) & 1u);
+    u64 r[MB_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MB_ITEMS; k++) {
+      const u32 p = tid + k * MB_THREADS;
+      r[k] = p < M ? buf[off + p] : 0ull;
+    }
+    __syncthreads();
+    // ---- cell histogram ----
+#pragma unroll
+    for (int k = 0; k < MB_ITEMS; k++) {
+      const u32 p = tid + k * MB_THREADS;
+      if (p < M) {
+        const u32 c = cell_of((u32)(r[k] >> 32));
+        atomicAdd(&s.cnt[c >> 1], 1u << ((c & 1u) * 16u));
+      }
+    }
+    __syncthreads();
+    // ---- exclusive scan of the cell counts (each thread owns 8 words = 16 cells) ----
+    {
+      uint4* c4 = reinterpret_cast<uint4*>(s.cnt) + tid * 2;
+      uint4 x0 = c4[0], x1 = c4[1];
+      u32 wv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      u32 sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += (wv[k] & 0xffffu) + (wv[k] >> 16);
+      u32 tot;
+      u32 run = block_excl_add<MB_THREADS, u32>(sum, s.ws, &tot);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const u32 lo = wv[k] & 0xffffu, hi = wv[k] >> 16;
+        wv[k] = run | ((run + lo) << 16);
+        run += lo + hi;
+      }
+      c4[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      c4[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+    }
+    __syncthreads();
+    // ---- scatter in place (every record of the bucket sits in a register by now) ----
+#pragma unroll
+    for (int k = 0; k < MB_ITEMS; k++) {
+      const u32 p = tid + k * MB_THREADS;
+      if (p < M) {
+        const u32 c = cell_of((u32)(r[k] >> 32));
+        const u32 sh = (c & 1u) * 16u;
+        const u32 old = atomicAdd(&s.cnt[c >> 1], 1u << sh);
+        buf[(old >> sh) & 0xffffu] = r[k];
+      }
+    }
+    __syncthreads();
+    // ---- every record ranks itself inside its cell; emit the column ----
+    const u16* cend = reinterpret_cast<const u16*>(s.cnt);  // after the scatter: end of every cell
+    u8* Ub = U + ((size_t)blockb << SEG_SHIFT) + ust;
+#pragma unroll 2
+    for (int k = 0; k < MB_ITEMS; k++) {
+      const u32 p = tid + k * MB_THREADS;
+      if (p < M) {
+        const u64 rv = buf[p];
+        const u32 key = (u32)(rv >> 32), lw = (u32)rv;
+        const u32 c = cell_of(key);
+        const u32 lo = c ? cend[c - 1] : 0u, hi = cend[c];
+        u32 less = 0, eq_before = 0, eq = 0;
+        for (u32 q = lo; q < hi; q++) {
+          const u32 kq = (u32)(buf[q] >> 32);
+          less += kq < key ? 1u : 0u;
+          if (kq == key) { eq++; eq_before += q < p ? 1u : 0u; }
+        }
+        const u32 f = lo + less + eq_before;
+        Ub[f] = (u8)(lw >> SEG_SHIFT);
+        if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + f;
+        if (eq > 1 && eq_before == 0) {
+          // first member of a group of rotations that share their first 5 bytes: hand the group to the resolver
+          u32 t = atomicAdd(&ctl[0], eq);
+          const u32 head = (blockb << SEG_SHIFT) | (ust + lo + less);
+          for (u32 q = lo; q < hi; q++) {
+            const u64 rq = buf[q];
+            if ((u32)(rq >> 32) == key) { tie_head[t] = head; tie_idx[t] = (blockb << SEG_SHIFT) | ((u32)rq & SEG_MASK); t++; }
+          }
+        }
+      }
+    }
+    fence_async_smem();  // the generic-proxy writes to this buffer are ordered before the bulk copy that refills it
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+void bwt_msd_launch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, u32 nblk, u32 n_max, u64 n_total, const u32* d_hist, u64* d_rec,
+                    u32* d_pidx, u32* d_tie_head, u32* d_tie_idx, u32* d_ctl) {
+  static int sms = 0;
+  if (!sms) {
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+    CUDA_CHECK(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdScatterSmem)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_msd_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdBucketSmem)));
+  }
+  DBuf<u32> bstart(c, (size_t)nblk * 256), cursor(c, (size_t)nblk * 256);
+  DBuf<u8> lut(c, (size_t)nblk * 256);
+  DBuf<MsdBlk> blk(c, nblk);
+  DBuf<uint4> work(c, (size_t)nblk * 256);
+  k_msd_prep<<<nblk, 256, 0, c.stream>>>(d_hist, bstart, cursor, lut, blk, work, d_ctl);
+  KLAUNCH(c); KCHECK();
+  const u32 tps = (n_max + MSD_TILE - 1) / MSD_TILE;
+  {
+    size_t ev = c.begin(ST_MSD_SCATTER);
+    k_msd_scatter<<<tps * nblk, MSD_THREADS, sizeof(MsdScatterSmem), c.stream>>>(d_T, d_n, tps, lut, blk, cursor, d_rec, d_ctl);
+    c.end(ev);
+    KLAUNCH(c); KCHECK();
+    ev = c.begin(ST_MSD_BUCKET);
+    k_msd_bucket<<<(unsigned)sms, MB_THREADS, sizeof(MsdBucketSmem), c.stream>>>(d_rec, work, d_U, d_pidx, d_tie_head, d_tie_idx, d_ctl);
+    c.end(ev);
+    KLAUNCH(c); KCHECK();
+  }
+  c.stats.msd_launches++;
+  c.stats.msd_scatter_bytes += n_total * 9;  // text in, records out
+  c.stats.msd_bucket_bytes += n_total * 9;   // records in, column out
+  c.stats.bwt_bytes += n_total * 18;
+}

@@ -23,6 +23,7 @@ struct Ctx {
   std::vector<b2_block_trace> trace;
   u32 bwt_batch = 296;  // bzip2 blocks processed together in one batch (2 CTAs x 148 SMs for the per-block kernels)
   bool timing = true;
+  bool bwt_msd = true;  // MSD + shared-memory bucket sort for sparse-tie batches (bwt_msd.cu); B2_BWT_MSD=0 disables it
   bool bwt_wide = false, bwt_wide_forced = false, bwt_mode_known = false;  // 8-byte initial sort for text-like batches (see bwt.cu)
   // plan handed from b2_bzip2_plan to the next b2_bzip2_encode_range_dev on the same (unchanged) buffer
   void* plan_cache = nullptr; const void* plan_ptr = nullptr; size_t plan_n = 0; int plan_level = 0;
@@ -93,7 +94,7 @@ struct Ctx {
 
 enum Stage {
   ST_TOTAL = 0, ST_H2D, ST_D2H, ST_RLE1, ST_BWT, ST_MTF, ST_HUFF, ST_PACK,
-  ST_SCAN, ST_HDEC, ST_UNMTF, ST_IBWT, ST_UNRLE, ST_RADIX, ST_COUNT
+  ST_SCAN, ST_HDEC, ST_UNMTF, ST_IBWT, ST_UNRLE, ST_RADIX, ST_MSD_SCATTER, ST_MSD_BUCKET, ST_COUNT
 };
 
 struct StageScope {

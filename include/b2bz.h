@@ -132,6 +132,11 @@ typedef struct b2_stats {
   uint64_t kernel_launches;  /* all kernels launched by the last call */
   uint64_t blocks;           /* bzip2 blocks processed */
   uint64_t raw_bytes, comp_bytes;
+  /* MSD path of the forward BWT (bwt_msd.cu): one scatter pass + one shared-memory bucket sort per batch */
+  uint64_t msd_launches;       /* batches that took the path (one launch of each of the two kernels) */
+  uint64_t msd_scatter_bytes;  /* algorithmic bytes of k_msd_scatter (text in, records out) */
+  uint64_t msd_bucket_bytes;   /* algorithmic bytes of k_msd_bucket (records in, column out) */
+  float ms_msd_scatter, ms_msd_bucket;
 } b2_stats;
 void b2_get_stats(b2_stats* s);
 
