@@ -8,11 +8,16 @@ A step = one bzip2 -9 encode of the workload (BASELINE configs[1]: 1 GiB synthet
 numpy PCG64 seed 20260923, 94 printable bytes + newline).  `value` = whole-job MB/s (10^6 raw bytes
 per second) with the input resident in HBM; `e2e` = the same through the host-buffer C ABI call
 (b2_bzip2_compress: H2D + all kernels + D2H inside the timed region).  The roofline entry is for the
-dominant kernel (k_radix_pass, the onesweep pass of the BWT suffix sort): algorithmic bytes per launch
-over its CUDA-event time, against the measured HBM copy bandwidth.
+dominant kernel of the forward BWT (k_msd_bucket, the shared-memory bucket sort that follows the MSD
+scatter pass): algorithmic bytes per launch over its CUDA-event time, against the measured HBM copy
+bandwidth; `roofline.bwt_stage` is the whole forward BWT.  Further objects on the same line:
+`parity` (oracle vs the first blocks of the benchmarked stream), `decode` (resident + end to end +
+roofline), `config3` (100 MB enwik-shaped text, encode + decode), `bwtc` (BASELINE configs[3]),
+`cpu_baseline`.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +33,7 @@ import numpy as np  # noqa: E402
 SEED = 20260923
 LEVEL = 9
 METRIC = "bzip2_-9_encode_MBps"
+BS9 = LEVEL * 100000 - 19
 
 
 def gen_ascii(nbytes, seed):
@@ -105,7 +111,8 @@ def peaks():
 
 
 def traffic_from_profiles():
-    p = os.path.join(ROOT, "profiles", "radix_pass_traffic.json")
+    """DRAM bytes per record of the BWT kernels from the committed `ncu --set full` captures."""
+    p = os.path.join(ROOT, "profiles", "bwt_kernel_traffic.json")
     if os.path.exists(p):
         try:
             return json.load(open(p))
@@ -114,35 +121,40 @@ def traffic_from_profiles():
     return None
 
 
-def cpu_sample_blocks(data, nblocks):
-    bs = LEVEL * 100000 - 19
-    return data[: min(len(data), nblocks * bs)]
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
     """The reference's own CPU implementation of the path (its JavaScript cannot run here: no node in the
-    image; this is the C restatement in oracle/, all host threads), on a bounded sample per step."""
+    image; this is the C restatement in oracle/, all host threads), on a bounded sample per step.  Encode is the
+    line's metric; a decode leg of the same sample follows (`decode`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
     O.build()
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count() or 1
-    cores = max(1, min(cores, 32))  # one 900k block (~60 MB of working set) per thread; more threads only thrash the host caches
-    per_step_blocks = max(2, cores)  # one 900k block per core and step keeps the run in minutes
-    mb = int(os.environ.get("B2_BENCH_MB", "1024"))
-    data = gen_ascii(min(mb << 20, per_step_blocks * 900000 + 1000), SEED)
-    sample = np.ascontiguousarray(cpu_sample_blocks(data, per_step_blocks))
+    cores = max(1, min(host_cores(), 32))  # one 900k block (~60 MB of working set) per thread; more threads only thrash the host caches
+    per_step_blocks = max(2, cores)        # one 900k block per core and step keeps the run in minutes
+    data = gen_ascii(min(args.mb << 20, per_step_blocks * 900000 + 1000), SEED)
+    sample = np.ascontiguousarray(data[: min(len(data), per_step_blocks * BS9)])
     for _ in range(args.warmup):
         O.bzip2_compress(sample[: 2 * 900000], LEVEL, threads=cores)
     t0 = time.perf_counter()
+    z = None
     for _ in range(args.steps):
-        O.bzip2_compress(sample, LEVEL, threads=cores)
+        z = O.bzip2_compress(sample, LEVEL, threads=cores)
     dt = time.perf_counter() - t0
     val = sample.size * args.steps / dt / 1e6
+    # decode leg: the reference's decoder is single threaded per stream (lib/Bzip2.js:454-481)
+    dsteps = max(1, min(args.steps, 2))
+    td = time.perf_counter()
+    for _ in range(dsteps):
+        back = O.bzip2_decompress(z)
+    ddt = time.perf_counter() - td
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -152,9 +164,164 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "MB/s", "cores": cores, "kind": "port",
                          "sample": "%d x 900k blocks per step, %d threads (oracle/bz2_oracle.c, one block per thread)" % (per_step_blocks, cores)},
         "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "decode": {"metric": "bzip2_-9_decode_MBps", "value": sample.size * dsteps / ddt / 1e6, "unit": "MB/s", "cores": 1, "steps": dsteps,
+                   "roundtrip_ok": bool(back == sample.tobytes()), "sample": "the stream of the encode sample, oracle decoder, 1 thread"},
         "note": "reference JS cannot execute in this image (no node); C restatement of its algorithm timed instead",
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def _check(rc, what, _native):
+    if rc:
+        raise SystemExit("%s failed: %s" % (what, _native.last_error()))
+
+
+def prefix_parity(L, _native, host, d_out, comp_bytes, trace, nblocks_check, threads):
+    """Oracle (CPU restatement of the reference) on the first blocks of the workload against the benchmarked
+    stream: the bits in front of block K must be identical."""
+    import torch
+    from oracle import oracle as O
+    O.build()
+    K = min(nblocks_check, len(trace) - 1)
+    if K < 1:
+        return {"blocks": 0, "ok": None, "note": "stream has fewer than two blocks"}
+    raw_end = int(trace[K].raw_start)  # first raw byte of block K
+    sample = np.ascontiguousarray(host[: min(len(host), raw_end + BS9 // 2)])
+    t0 = time.perf_counter()
+    z = O.bzip2_compress(sample, LEVEL, threads=threads)
+    dt = time.perf_counter() - t0
+    bits = int(trace[K].bit_start)
+    nbytes, rem = bits // 8, bits % 8
+    got = d_out[: nbytes + 1].cpu().numpy()
+    exp = np.frombuffer(z, dtype=np.uint8)[: nbytes + 1]
+    ok = bool(np.array_equal(got[:nbytes], exp[:nbytes]))
+    if rem and ok:
+        mask = (0xFF << (8 - rem)) & 0xFF
+        ok = (int(got[nbytes]) & mask) == (int(exp[nbytes]) & mask)
+    return {"blocks": K, "bits": bits, "ok": ok, "oracle_s": round(dt, 2), "oracle_threads": threads,
+            "what": "oracle/bz2_oracle.c output on the first %d raw bytes vs the first %d bits of the benchmarked stream" % (sample.size, bits)}
+
+
+def decode_arm(L, _native, torch, d_comp, comp, d_ref, nbytes, steps, pinned_comp=None):
+    """Decode of a stream: resident (b2_bzip2_decompress_dev) and end to end (b2_bzip2_decompress, pinned host in,
+    library-pinned out), round trip checked against d_ref."""
+    d_dec = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dn = C.c_size_t()
+    _check(L.b2_bzip2_decompress_dev(d_comp.data_ptr(), comp, 0, d_dec.data_ptr(), nbytes, C.byref(dn)), "decompress_dev", _native)
+    dms, dst = 0.0, None
+    for _ in range(steps):
+        _check(L.b2_bzip2_decompress_dev(d_comp.data_ptr(), comp, 0, d_dec.data_ptr(), nbytes, C.byref(dn)), "decompress_dev", _native)
+        dst = _native.stats()
+        dms += dst["ms_total"]
+    ok = dn.value == nbytes and bool(torch.equal(d_dec[: dn.value], d_ref))
+    res = {"metric": "bzip2_-9_decode_MBps", "value": nbytes * steps / (dms / 1e3) / 1e6, "unit": "MB/s", "steps": steps,
+           "roundtrip_ok": ok, "ms_per_step": dms / steps,
+           "stages_ms": {k: dst[k] for k in ("ms_scan", "ms_hdec", "ms_unmtf", "ms_ibwt", "ms_unrle")}}
+    # SURVEY.md 8(d): c + 4n (dbuf) + 8n (T-vector build) + 4n (chase) + N_raw out
+    alg = comp + 16 * nbytes + nbytes
+    peak, _ = peaks()
+    dom = max(res["stages_ms"].items(), key=lambda kv: kv[1])
+    res["roofline"] = {"bound": "hbm", "achieved": alg / 1e9 / (dms / steps / 1e3), "peak": peak, "unit": "GB/s",
+                       "frac": alg / 1e9 / (dms / steps / 1e3) / peak, "algorithmic_bytes": alg, "dominant_stage": dom[0],
+                       "dominant_stage_ms": dom[1], "note": "whole decode, algorithmic bytes of SURVEY.md 8(d): c + 16 n + N"}
+    if pinned_comp is not None:
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        _check(L.b2_bzip2_decompress(pinned_comp.data_ptr(), comp, 0, C.byref(out), C.byref(n)), "decompress", _native)
+        L.b2_free(out)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _check(L.b2_bzip2_decompress(pinned_comp.data_ptr(), comp, 0, C.byref(out), C.byref(n)), "decompress", _native)
+            if n.value != nbytes:
+                raise SystemExit("e2e decode returned %d bytes" % n.value)
+            L.b2_free(out)
+        dt = time.perf_counter() - t0
+        res["e2e"] = {"value": nbytes * steps / dt / 1e6, "unit": "MB/s", "h2d_bytes_per_step": comp, "d2h_bytes_per_step": nbytes,
+                      "api": "b2_bzip2_decompress (host pinned in, library-pinned out)"}
+    return res
+
+
+def config3_leg(L, _native, torch, steps):
+    """BASELINE configs[2]: 100 MB enwik-shaped text, bzip2 -9 encode + decode on this GPU."""
+    from tools.workloads import enwik_like
+    t0 = time.perf_counter()
+    data = enwik_like(100000000)
+    gen_s = time.perf_counter() - t0
+    n = data.size
+    pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = data
+    d_in = pinned.cuda()
+    cap = L.b2_bzip2_bound(n)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    out_n = C.c_size_t()
+    for _ in range(2):
+        _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), n, LEVEL, d_out.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
+    ems, st, agg = 0.0, None, {}
+    for _ in range(steps):
+        _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), n, LEVEL, d_out.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
+        st = _native.stats()
+        ems += st["ms_total"]
+        for k, v in st.items():
+            agg[k] = agg.get(k, 0) + v
+    comp = out_n.value
+    # end to end encode
+    out, nn = C.POINTER(C.c_uint8)(), C.c_size_t()
+    _check(L.b2_bzip2_compress(pinned.data_ptr(), n, LEVEL, C.byref(out), C.byref(nn)), "compress", _native)
+    pinned_comp = torch.empty(nn.value, dtype=torch.uint8, pin_memory=True)
+    pinned_comp.numpy()[:] = np.ctypeslib.as_array(out, (nn.value,))
+    L.b2_free(out)
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        _check(L.b2_bzip2_compress(pinned.data_ptr(), n, LEVEL, C.byref(out), C.byref(nn)), "compress", _native)
+        L.b2_free(out)
+    e2e_s = (time.perf_counter() - t1) / steps
+    dec = decode_arm(L, _native, torch, d_out, comp, d_in, n, steps, pinned_comp)
+    peak, _ = peaks()
+    bwt_gbs = (agg["bwt_bytes"] / 1e9) / (agg["ms_bwt"] / 1e3) if agg.get("ms_bwt") else 0.0
+    enc_ms, dec_ms = ems / steps, dec["ms_per_step"]
+    return {"workload": "100 000 000 B enwik-shaped text (order-3 chain trained on the reference's test/sample5.ref + 1 % long repeats, seed %d), bzip2 -9" % SEED,
+            "encode_MBps": n / (enc_ms / 1e3) / 1e6, "decode_MBps": dec["value"], "encode_plus_decode_MBps": n / ((enc_ms + dec_ms) / 1e3) / 1e6,
+            "encode_e2e_MBps": n / e2e_s / 1e6, "decode_e2e_MBps": (dec.get("e2e") or {}).get("value"),
+            "encode_ms": enc_ms, "decode_ms": dec_ms, "compressed_bytes": comp, "blocks": int(agg["blocks"] // steps), "roundtrip_ok": dec["roundtrip_ok"],
+            "bwt_stage": {"achieved": bwt_gbs, "frac": bwt_gbs / peak, "rounds": int(st["bwt_rounds"]), "ms_per_step": agg["ms_bwt"] / steps,
+                          "path": "LSD radix passes + prefix doubling (text mode)"},
+            "encode_stages_ms": {k: agg[k] / steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack")},
+            "decode_stages_ms": dec["stages_ms"], "generator_s": round(gen_s, 1)}
+
+
+def bwtc_leg(L, _native, torch, host, mb, check_blocks):
+    """BASELINE configs[3]: BWTC -9 (range-coder back end) on the config-2 buffer, one GPU."""
+    n = min(len(host), mb << 20)
+    src = np.ascontiguousarray(host[:n])
+    out, nn = C.POINTER(C.c_uint8)(), C.c_size_t()
+    t0 = time.perf_counter()
+    _check(L.b2_bwtc_compress(src.ctypes.data, n, 9, C.byref(out), C.byref(nn)), "bwtc_compress", _native)
+    dt = time.perf_counter() - t0
+    st = _native.stats()
+    z = bytes(np.ctypeslib.as_array(out, (nn.value,)))
+    L.b2_free(out)
+    res = {"workload": "BWTC -9 on the first %d MiB of the config-2 buffer (b2_bwtc_compress, host buffers)" % (n >> 20), "bytes": n,
+           "encode_MBps": n / dt / 1e6, "wall_s": round(dt, 3), "compressed_bytes": nn.value, "ms_total_gpu": st["ms_total"],
+           "stages_ms": {"bwt": st["ms_bwt"], "mtf": st["ms_mtf"], "model": st["ms_huff"], "coder": st["ms_pack"]},
+           "note": "model = one thread per block (parallel over blocks); coder = ONE thread per file (the range recurrence is serial): stages_ms.coder bounds the path"}
+    if check_blocks:
+        from oracle import oracle as O
+        k = min(n, check_blocks * 900000)
+        exp = O.bwtc_compress(src[:k].tobytes(), 9)
+        o2, n2 = C.POINTER(C.c_uint8)(), C.c_size_t()
+        _check(L.b2_bwtc_compress(src.ctypes.data, k, 9, C.byref(o2), C.byref(n2)), "bwtc_compress", _native)
+        res["parity_blocks"] = check_blocks
+        res["parity_ok"] = bytes(np.ctypeslib.as_array(o2, (n2.value,))) == exp
+        L.b2_free(o2)
+    # decode back (serial range decoder)
+    t1 = time.perf_counter()
+    arr = np.frombuffer(z, dtype=np.uint8)
+    _check(L.b2_bwtc_decompress(arr.ctypes.data, arr.size, C.byref(out), C.byref(nn)), "bwtc_decompress", _native)
+    res["decode_MBps"] = n / (time.perf_counter() - t1) / 1e6
+    res["roundtrip_ok"] = bool(nn.value == n and np.array_equal(np.ctypeslib.as_array(out, (nn.value,)), src))
+    L.b2_free(out)
+    return res
 
 
 def main():
@@ -164,7 +331,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mb", type=int, default=int(os.environ.get("B2_BENCH_MB", "1024")), help="MiB of input per GPU and step")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip every leg that runs the CPU oracle (cpu_baseline, parity)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config3 and bwtc legs")
+    ap.add_argument("--bwtc-mb", type=int, default=int(os.environ.get("B2_BENCH_BWTC_MB", "64")), help="MiB of the config-2 buffer for the BWTC leg (config 4 = 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -198,27 +367,24 @@ def main():
     d_out = torch.empty(cap, dtype=torch.uint8, device="cuda") if world == 1 else None
     out_n = C.c_size_t()
     from compressjs_b200 import sharded as SH
-    state = {"comp": 0}
+    state = {"comp": 0, "out": None}
 
     def step_resident():
         if world == 1:
-            rc = L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n))
-            if rc:
-                raise SystemExit("compress_dev failed: " + _native.last_error())
+            _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
             state["comp"] = out_n.value
             return _native.stats()
         out = SH.compress_file_sharded(d_in, LEVEL)
         st = _native.stats()
         if out is not None:
             state["comp"] = out.numel()
+            state["out"] = out
         return st
 
     def step_e2e(check=False):
         if world == 1:
             out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
-            rc = L.b2_bzip2_compress(pinned.data_ptr(), nbytes, LEVEL, C.byref(out), C.byref(n))
-            if rc:
-                raise SystemExit("compress failed: " + _native.last_error())
+            _check(L.b2_bzip2_compress(pinned.data_ptr(), nbytes, LEVEL, C.byref(out), C.byref(n)), "compress", _native)
             st = _native.stats()
             if check:  # untimed warm-up call: the host-buffer path must produce the resident path's stream
                 got = torch.from_numpy(np.ctypeslib.as_array(out, (n.value,))).cuda()
@@ -268,12 +434,27 @@ def main():
         dev_ms = ev0.elapsed_time(ev1)  # includes the NCCL gather and the assembly on rank 0
     clocks = sampler.stop(t0, t0 + wall) if rank == 0 else None
     comp_bytes = state["comp"]
+    trace = _native.last_trace() if world == 1 else []
 
     # device time: max over ranks (events on the library's launching stream)
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = t.tolist()
+
+    # ---- multi-rank parity: the stream assembled from the ranks' fragments == the one-GPU stream of the same input ----
+    sharded_parity = None
+    if world > 1 and rank == 0:
+        one = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, one.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
+        same = out_n.value == state["out"].numel() and bool(torch.equal(one[: out_n.value], state["out"]))
+        sharded_parity = {"ok": same, "bytes": int(out_n.value),
+                          "sha256_16": hashlib.sha256(state["out"].cpu().numpy().tobytes()).hexdigest()[:16],
+                          "what": "%d-rank NCCL stream vs b2_bzip2_compress_dev of the whole input on rank 0" % world}
+        del one
+        if not same:
+            print(json.dumps({"error": "sharded stream differs from the single-GPU stream", "sharded_parity": sharded_parity}))
+            raise SystemExit(3)
 
     # ---- e2e arm: host buffers through the C ABI ----
     e2e_steps = max(1, min(args.steps, 3))
@@ -294,9 +475,38 @@ def main():
         total_raw = nbytes
         value = total_raw * args.steps / (dev_ms_max / 1e3) / 1e6
         peak, peak_src = peaks()
-        radix_gbs = (agg["radix_bytes"] / 1e9) / (agg["ms_radix"] / 1e3) if agg.get("ms_radix") else 0.0
         bwt_gbs = (agg["bwt_bytes"] / 1e9) / (agg["ms_bwt"] / 1e3) if agg.get("ms_bwt") else 0.0
-        tr = traffic_from_profiles()
+        tr = traffic_from_profiles() or {}
+        msd = agg.get("msd_launches", 0) > 0
+        if msd:
+            nl = agg["msd_launches"]
+            kb, ks = agg["msd_bucket_bytes"] / nl, agg["msd_scatter_bytes"] / nl
+            mb_ms, ms_ms = agg["ms_msd_bucket"] / nl, agg["ms_msd_scatter"] / nl
+            bucket_gbs, scatter_gbs = kb / 1e9 / (mb_ms / 1e3), ks / 1e9 / (ms_ms / 1e3)
+            recs = kb / 9.0
+            roof = {"bound": "hbm", "kernel": "k_msd_bucket (shared-memory bucket sort of the forward BWT: records in, BWT column out)",
+                    "achieved": bucket_gbs, "peak": peak, "unit": "GB/s", "frac": bucket_gbs / peak,
+                    "traffic": (tr.get("k_msd_bucket_dram_bytes_per_record") or 0) * recs or None, "traffic_source": tr.get("source"),
+                    "peak_source": peak_src, "launches": int(nl), "algorithmic_bytes_per_launch": kb, "avg_launch_ms": mb_ms,
+                    "algorithmic_bytes_per_unit": "9 per text byte (8-byte record read, 1 byte of the column written)",
+                    "k_msd_scatter": {"achieved": scatter_gbs, "frac": scatter_gbs / peak, "algorithmic_bytes_per_launch": ks, "avg_launch_ms": ms_ms,
+                                      "traffic": (tr.get("k_msd_scatter_dram_bytes_per_record") or 0) * recs or None,
+                                      "algorithmic_bytes_per_unit": "9 per text byte (1 read, 8-byte record written)"}}
+        else:
+            radix_gbs = (agg["radix_bytes"] / 1e9) / (agg["ms_radix"] / 1e3) if agg.get("ms_radix") else 0.0
+            roof = {"bound": "hbm", "kernel": "k_radix_pass (BWT onesweep pass)", "achieved": radix_gbs, "peak": peak, "unit": "GB/s",
+                    "frac": radix_gbs / peak if peak else None, "traffic": None, "peak_source": peak_src, "launches": int(agg["radix_launches"]),
+                    "algorithmic_bytes_per_launch": agg["radix_bytes"] / max(agg["radix_launches"], 1),
+                    "avg_launch_ms": agg["ms_radix"] / max(agg["radix_launches"], 1)}
+        # the survey's formula for an LSD prefix-doubling sort, B = N (91 + 224 R), as an equivalent rate next to the executed bytes
+        rounds = int(agg["bwt_rounds"] // max(args.steps, 1))
+        lsd_equiv = total_raw / world * args.steps * (91 + 224 * rounds) / 1e9 / (agg["ms_bwt"] / 1e3) if agg.get("ms_bwt") else 0.0
+        roof["bwt_stage"] = {"achieved": bwt_gbs, "frac": bwt_gbs / peak if peak else None, "rounds": rounds, "ms_per_step": agg["ms_bwt"] / args.steps,
+                             "algorithmic_bytes_per_step": agg["bwt_bytes"] / args.steps,
+                             "bytes_per_text_byte": agg["bwt_bytes"] / args.steps / (total_raw / world),
+                             "lsd_formula_equivalent_gbs": lsd_equiv, "lsd_formula_equivalent_frac": lsd_equiv / peak,
+                             "note": "achieved counts the bytes of the passes actually executed (SURVEY.md 8d); the *_equivalent figures apply the survey's "
+                                     "91 N + 224 N R formula of a 4-pass LSD sort to the same time"}
         line = {
             "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -309,42 +519,33 @@ def main():
                     "steps": e2e_steps, "api": "b2_bzip2_compress (host pinned in, library-pinned out; upload in 64 MiB chunks and download per batch overlapped with the encode)" if world == 1 else
                     "sharded.compress_file_sharded (pinned host in on every rank, stream gathered to rank 0 over NCCL, D2H on rank 0)"},
             "gpu_launches": int(agg["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_radix_pass (BWT onesweep pass)", "achieved": radix_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": radix_gbs / peak if peak else None,
-                         "traffic": ((tr or {}).get("dram_bytes_per_record") or 0) * (agg["radix_bytes"] / max(agg["radix_launches"], 1) / 16.0) or None,
-                         "traffic_source": (tr or {}).get("source"),
-                         "peak_source": peak_src, "launches": int(agg["radix_launches"]),
-                         "algorithmic_bytes_per_launch": agg["radix_bytes"] / max(agg["radix_launches"], 1),
-                         "avg_launch_ms": agg["ms_radix"] / max(agg["radix_launches"], 1),
-                         "bwt_stage": {"achieved": bwt_gbs, "frac": bwt_gbs / peak if peak else None, "rounds": int(agg["bwt_rounds"] // max(args.steps, 1)),
-                                       "ms_per_step": agg["ms_bwt"] / args.steps}},
-            "stages_ms_per_step": {k: agg[k] / args.steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack", "ms_radix")},
+            "roofline": roof,
+            "stages_ms_per_step": {k: agg[k] / args.steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack", "ms_radix", "ms_msd_scatter", "ms_msd_bucket")},
             "clocks": clocks,
         }
         if world > 1:
             line["sharded_phases_ms_last_step_rank0"] = {k: round(v, 2) for k, v in SH.PHASES.items()}
+            line["sharded_parity"] = sharded_parity
         if world == 1:
-            # decode leg: the stream just produced, HBM resident (b2_bzip2_decompress_dev) -- the second half of the metric
-            d_dec = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-            dn = C.c_size_t()
-            comp = comp_bytes
-            L.b2_bzip2_decompress_dev(d_out.data_ptr(), comp, 0, d_dec.data_ptr(), nbytes, C.byref(dn))
-            dms, dst = 0.0, None
-            dsteps = max(1, min(args.steps, 3))
-            for _ in range(dsteps):
-                rc = L.b2_bzip2_decompress_dev(d_out.data_ptr(), comp, 0, d_dec.data_ptr(), nbytes, C.byref(dn))
-                if rc:
-                    raise SystemExit("decompress_dev failed: " + _native.last_error())
-                dst = _native.stats()
-                dms += dst["ms_total"]
-            ok = bool(torch.equal(d_dec[: dn.value], d_in)) and dn.value == nbytes
-            line["decode"] = {"metric": "bzip2_-9_decode_MBps", "value": nbytes * dsteps / (dms / 1e3) / 1e6, "unit": "MB/s", "steps": dsteps,
-                              "roundtrip_ok": ok, "ms_per_step": dms / dsteps,
-                              "stages_ms": {k: dst[k] for k in ("ms_scan", "ms_hdec", "ms_unmtf", "ms_ibwt", "ms_unrle")}}
+            if not args.no_cpu:
+                line["parity"] = prefix_parity(L, _native, host, d_out, comp_bytes, trace, 32, max(1, min(host_cores(), 32)))
+                if line["parity"]["ok"] is False:
+                    print(json.dumps({"error": "benchmarked stream differs from the oracle", "parity": line["parity"]}))
+                    raise SystemExit(3)
+            # decode leg: the stream just produced -- the second half of the metric
+            pinned_comp = torch.empty(comp_bytes, dtype=torch.uint8, pin_memory=True)
+            pinned_comp.copy_(d_out[:comp_bytes])
+            line["decode"] = decode_arm(L, _native, torch, d_out, comp_bytes, d_in, nbytes, max(1, min(args.steps, 3)), pinned_comp)
+            del pinned_comp
+            if not args.no_extra:
+                del d_out
+                torch.cuda.empty_cache()
+                line["config3"] = config3_leg(L, _native, torch, max(1, min(args.steps, 3)))
+                line["bwtc"] = bwtc_leg(L, _native, torch, host, args.bwtc_mb, 0 if args.no_cpu else 2)
         if not args.no_cpu and world == 1:
             from oracle import oracle as O
             O.build()
-            sample = np.ascontiguousarray(cpu_sample_blocks(host, 8))
+            sample = np.ascontiguousarray(host[: min(len(host), 8 * BS9)])
             tc = time.perf_counter()
             zc = O.bzip2_compress(sample, LEVEL)
             dtc = time.perf_counter() - tc

@@ -15,7 +15,7 @@ EXPORTS = [
     "b2_bzip2_compress", "b2_bzip2_decompress", "b2_bzip2_decompress_block", "b2_bzip2_table",
     "b2_bwt_cyclic", "b2_bwt_cyclic_batch", "b2_suffixsort", "b2_bwt_sentinel", "b2_bwt_inverse", "b2_bwtc_compress", "b2_bwtc_decompress", "b2_crc32_bzip2",
     "b2_bzip2_bound", "b2_bzip2_compress_dev", "b2_bzip2_decompress_dev",
-    "b2_bzip2_plan", "b2_bzip2_plan_spec", "b2_bitshift_dev", "b2_dec_shard_open", "b2_dec_shard_export", "b2_dec_shard_finish", "b2_bzip2_encode_range_dev", "b2_get_stats", "b2_last_trace",
+    "b2_bzip2_plan", "b2_bzip2_plan_spec", "b2_bzip2_share_summary", "b2_bzip2_plan_share", "b2_bitshift_dev", "b2_dec_shard_open", "b2_dec_shard_export", "b2_dec_shard_finish", "b2_bzip2_encode_range_dev", "b2_get_stats", "b2_last_trace",
 ]
 
 
@@ -74,6 +74,8 @@ def lib():
     L.b2_bzip2_decompress_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, szp]
     L.b2_bzip2_plan.argtypes = [C.c_void_p, C.c_size_t, C.c_int, szp]
     L.b2_bzip2_plan_spec.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    L.b2_bzip2_share_summary.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.b2_bzip2_plan_share.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64)]
     L.b2_dec_shard_open.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.b2_dec_shard_export.argtypes = [C.c_void_p]
     L.b2_dec_shard_finish.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]

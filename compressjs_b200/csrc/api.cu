@@ -11,13 +11,15 @@
 
 // stages implemented in the other translation units
 void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel = false,
-                       u32* d_sa_out = nullptr);
+                       u32* d_sa_out = nullptr, u32* d_hist_out = nullptr);
 u32 crc32_device(Ctx& c, const u8* d_p, size_t n);
 void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n,
                            size_t first_block, size_t block_count, int bit_phase, bool whole_file, u64* out_bits,
                            std::vector<u32>* crcs_out, size_t* total_blocks, long long spec_first = -2, size_t spec_count = 0,
                            u64* spec_range = nullptr);
 void bitshift_device(Ctx& c, const void* src, u64 nbits, int phase, void* dst);
+void bzip2_share_summary(Ctx& c, const u8* d_in, size_t n, u64* out);
+void bzip2_plan_share(Ctx& c, const u8* d_buf, size_t n, int level, u64 st0, u64 W0, size_t first, size_t count, u64* info);
 void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out);
 size_t bwtc_bound(size_t n);
 void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n);
@@ -535,6 +537,27 @@ int b2_bzip2_plan_spec(const void* d_in, size_t n, int level, int rank, int worl
     size_t dummy = 0;
     bzip2_compress_device(c, (const u8*)d_in, n, level, nullptr, 0, &dummy, 0, 0, 0, false, nullptr, nullptr, nullptr, -1,
                           ((size_t)rank << 32) | (size_t)world, info);
+    c.sync();
+    return 0;
+  });
+}
+
+int b2_bzip2_share_summary(const void* d_share, size_t n, uint64_t* summary) {
+  return guarded([&]() {
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    bzip2_share_summary(c, (const u8*)d_share, n, summary);
+    c.sync();
+    return 0;
+  });
+}
+
+int b2_bzip2_plan_share(const void* d_buf, size_t n, int level, uint64_t state_in, uint64_t w_in, size_t first, size_t count, uint64_t* info) {
+  return guarded([&]() {
+    if (level < 1 || level > 9) throw B2Error{B2_ERR_BAD_LEVEL, "Invalid block size multiplier"};
+    Ctx& c = ctx_locked();
+    c.reset_call();
+    bzip2_plan_share(c, (const u8*)d_buf, n, level, state_in, w_in, first, count, info);
     c.sync();
     return 0;
   });

@@ -65,21 +65,41 @@ k_build_keys(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u
   if (hist && h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
 }
 
+// Block byte histograms (bucket sizes of the MSD path, digit histogram of every LSD pass, text score): 16-byte loads,
+// one private set of counters per warp.  Tiles are BH_TILE bytes of one block.
+#define BH_TILE 16384
 __global__ void __launch_bounds__(BK_THREADS) k_byte_hist(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, u32* __restrict__ hist) {
-  __shared__ u32 h[256];
-  h[threadIdx.x] = 0;
+  __shared__ u32 h[BK_THREADS / 32][256];
+  const u32 tid = threadIdx.x, w = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < BK_THREADS / 32; k++) h[k][tid] = 0;
   __syncthreads();
   const u32 b = blockIdx.x / tps, lt = blockIdx.x % tps;
   const u32 n = seg_n[b];
-  const u32 start = lt * (BK_THREADS * BK_ITEMS);
+  const u32 start = lt * BH_TILE;
   if (start >= n) return;
-  const u8* t = T + ((size_t)b << SEG_SHIFT);
-  for (int k = 0; k < BK_ITEMS; k++) {
-    const u32 i = start + k * BK_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&h[t[i]], 1u);
+  const u8* t = T + ((size_t)b << SEG_SHIFT) + start;
+  const u32 cnt = min((u32)BH_TILE, n - start);
+#pragma unroll
+  for (int k = 0; k < BH_TILE / 16 / BK_THREADS; k++) {
+    const u32 o = (k * BK_THREADS + tid) * 16;
+    if (o + 16 <= cnt) {
+      const uint4 v = *reinterpret_cast<const uint4*>(t + o);
+      const u32 wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        atomicAdd(&h[w][wv[q] & 0xff], 1u); atomicAdd(&h[w][(wv[q] >> 8) & 0xff], 1u);
+        atomicAdd(&h[w][(wv[q] >> 16) & 0xff], 1u); atomicAdd(&h[w][wv[q] >> 24], 1u);
+      }
+    } else {
+      for (u32 x = o; x < cnt; x++) atomicAdd(&h[w][t[x]], 1u);
+    }
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&hist[b * 256 + threadIdx.x], h[threadIdx.x]);
+  u32 tot = 0;
+#pragma unroll
+  for (int k = 0; k < BK_THREADS / 32; k++) tot += h[k][tid];
+  if (tot) atomicAdd(&hist[b * 256 + tid], tot);
 }
 // four bytes of block text starting at (i + off) mod n, big endian
 __device__ __forceinline__ u32 word_at(const u8* __restrict__ t, u32 n, u32 i, u32 off) {
@@ -502,7 +522,8 @@ static u32 bits_for(u32 maxval) {  // number of bits needed to represent values 
 
 // Forward cyclic BWT of `nblk` blocks in the slot layout.  d_T/d_U: u8[nblk << 20];
 // d_n: device u32[nblk]; h_n: host copy; d_pidx: device u32[nblk].
-void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel, u32* d_sa_out) {
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel, u32* d_sa_out,
+                       u32* d_hist_out) {
   if (nblk == 0) return;
   u32 n_max = 0; u64 n_total = 0;
   for (u32 b = 0; b < nblk; b++) { n_max = h_n[b] > n_max ? h_n[b] : n_max; n_total += h_n[b]; }
@@ -516,14 +537,18 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   u64 *kin = recA, *kout = recB;
   u32 *vin = nullptr, *vout = nullptr;
 
-  DBuf<u32> bytehist(c, (size_t)nblk * 256);
+  // block byte histograms: in the caller's buffer when it wants them (the MTF stage derives its symbol map from them)
+  DBuf<u32> bytehist_own;
+  if (!d_hist_out) bytehist_own.alloc(c, (size_t)nblk * 256);
+  u32* const bytehist = d_hist_out ? d_hist_out : bytehist_own.p;
   DBuf<float> dscore(c, 1);
   CUDA_CHECK(cudaMemsetAsync(bytehist, 0, (size_t)nblk * 256 * 4, c.stream));
   const u32 bk_tps = (n_max + BK_THREADS * BK_ITEMS - 1) / (BK_THREADS * BK_ITEMS);
   // The block byte histograms come first: they are the digit histogram of every pass of the 4-byte-prefix sort, the
   // bucket sizes of the MSD path and the input of the text-likeness score that picks the mode of the batch.
   if (!sentinel) {
-    k_byte_hist<<<bk_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bk_tps, bytehist);
+    const u32 bh_tps = (n_max + BH_TILE - 1) / BH_TILE;
+    k_byte_hist<<<bh_tps * nblk, BK_THREADS, 0, c.stream>>>(d_T, d_n, bh_tps, bytehist);
     KLAUNCH(c); KCHECK();
     c.stats.bwt_bytes += n_total;
   }
@@ -551,7 +576,7 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
     c.to_host(&score, dscore, 4);
     c.sync();
     if (!c.bwt_wide_forced) c.bwt_wide = score > 0.5f;  // next batch of this call
-    if (!h_ctl[2]) {
+    if (!h_ctl[2] && !h_ctl[1]) {
       const u32 Mt = h_ctl[0];
       u32 failed = 0;
       if (Mt > n_total / 8) failed = 1;
@@ -571,12 +596,12 @@ void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32
   c.stats.bwt_bytes += n_total * 9;
   // keys-only sort of the packed records on their upper 32 bits
   // (sentinel mode: the zero padding breaks the "byte histogram = digit histogram" identity, so the sort counts its own)
-  radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, sentinel ? nullptr : bytehist.p);
+  radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, sentinel ? nullptr : bytehist);
   if (wide) {
     k_rekey<<<(nslots + 255) / 256, 256, 0, c.stream>>>(d_T, d_n, nslots, kin);
     KLAUNCH(c); KCHECK();
     c.stats.bwt_bytes += n_total * 20;
-    radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist.p);
+    radix_sort<u64, false>(c, kin, vin, kout, vout, d_n, nblk, SEG_SHIFT, n_max, 32, 4, false, n_total, bytehist);
   }
   u32* SA = saBuf;
   const u32 ri_tps = (n_max + RR_TILE - 1) / RR_TILE;

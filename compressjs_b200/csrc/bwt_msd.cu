@@ -54,7 +54,6 @@ struct MsdScatterSmem {
   __align__(16) u8 raw[16 + MSD_TILE + 16];  // raw[15] = byte before the tile, raw[16..] the tile, then 4 bytes of look-ahead
   __align__(16) u8 rk[MSD_TILE + 16];        // dense symbol ranks of raw[16..]
   __align__(16) u64 rec[MSD_TILE];
-  u8 dig[MSD_TILE];
   u32 cnt[256];
   int gdst[256];
   u8 lut[256];
@@ -66,7 +65,7 @@ __device__ __forceinline__ u32 lut4(const u8* lut, u32 w) {
   return (u32)lut[w & 0xff] | ((u32)lut[(w >> 8) & 0xff] << 8) | ((u32)lut[(w >> 16) & 0xff] << 16) | ((u32)lut[w >> 24] << 24);
 }
 
-__global__ void __launch_bounds__(MSD_THREADS, 4)
+__global__ void __launch_bounds__(MSD_THREADS, MSD_CTAS_PER_SM)
 k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, const u8* __restrict__ lut, const MsdBlk* __restrict__ blk,
               u32* __restrict__ cursor, u64* __restrict__ rec_out, const u32* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -79,19 +78,24 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
   const u32 count = min((u32)MSD_TILE, n - start);
   const u8* Tb = T + ((size_t)b << SEG_SHIFT);
   const u32 tid = threadIdx.x;
-  if (tid == 0) { mbar_init(&s.bar, 1); mbar_fence_init(); }
-  s.lut[tid] = lut[b * 256 + tid];
-  s.cnt[tid] = 0;
-  __syncthreads();
   if (tid == 0) {
     // the whole tile in one bulk copy (a short last tile reads on into the unused rest of the 1 MiB slot)
+    mbar_init(&s.bar, 1); mbar_fence_init();
     mbar_expect_tx(&s.bar, MSD_TILE);
     bulk_g2s(s.raw + 16, Tb + start, MSD_TILE, &s.bar);
   }
-  if (tid == 32) s.raw[15] = start ? Tb[start - 1] : Tb[n - 1];
+  // everything else this tile needs from global memory is requested now, while the copy is in flight
+  const MsdBlk mb = blk[b];
+  const u8 lutv = lut[b * 256 + tid];
+  u8 edge = 0;  // tid 32: the byte before the tile; tid 0..3: look-ahead of the last rotations (cyclic)
+  if (tid == 32) edge = start ? Tb[start - 1] : Tb[n - 1];
+  if (tid < 4) edge = Tb[(start + count + tid) % n];
+  s.lut[tid] = lutv;
+  s.cnt[tid] = 0;
+  __syncthreads();  // also publishes the barrier initialisation to the waiting threads
   mbar_wait(&s.bar, 0);
-  // look-ahead of the last rotations of the tile: the next text bytes, cyclically
-  if (tid < 4) s.raw[16 + count + tid] = Tb[(start + count + tid) % n];
+  if (tid == 32) s.raw[15] = edge;
+  if (tid < 4) s.raw[16 + count + tid] = edge;
   __syncthreads();
   // ---- dense ranks of the own 16 bytes ----
   const uint4 rv = *reinterpret_cast<const uint4*>(s.raw + 16 + tid * 16);
@@ -102,7 +106,6 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
     if (tid < 4) s.rk[count + tid] = s.lut[s.raw[16 + count + tid]];  // look-ahead ranks (same value as the owner's store, if any)
   }
   __syncthreads();
-  const MsdBlk mb = blk[b];
   const u32 a = mb.a, a2 = mb.a2, S_lo = (u32)mb.S, S_hi = (u32)(mb.S >> 32);
   u32 key[MSD_ITEMS], slot[MSD_ITEMS / 2];
   {
@@ -127,17 +130,18 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
     }
   }
   __syncthreads();
-  // ---- per digit: space in the block's bucket (any order: the bucket is sorted afterwards) ----
+  // ---- per digit: space in the block's bucket (any order: the bucket is sorted afterwards).  The global atomic is
+  // issued here and its result is first needed after the staging step.
+  u32 g, ex;
   {
     const u32 c = s.cnt[tid];
     u32 tot;
-    const u32 ex = block_excl_add<MSD_THREADS, u32>(c, s.ws, &tot);
-    const u32 g = c ? atomicAdd(&cursor[b * 256 + tid], c) : 0u;
-    s.gdst[tid] = (int)g - (int)ex;
+    ex = block_excl_add<MSD_THREADS, u32>(c, s.ws, &tot);
+    g = c ? atomicAdd(&cursor[b * 256 + tid], c) : 0u;
     s.cnt[tid] = ex;
   }
   __syncthreads();
-  // ---- stage the tile in digit order ----
+  // ---- stage the tile in digit order; the low word carries (byte before, digit, position inside the tile) for now ----
   {
     const u32 rw[4] = {rv.x, rv.y, rv.z, rv.w};
     u32 prev = s.raw[15 + tid * 16];
@@ -146,19 +150,23 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
       const u32 d = (rw[j >> 2] >> (8 * (j & 3))) & 0xffu;
       if (tid * MSD_ITEMS + j < count) {
         const u32 sl = (j & 1) ? (slot[j >> 1] >> 16) : (slot[j >> 1] & 0xffffu);
-        const u32 p = s.cnt[d] + sl;
-        s.rec[p] = ((u64)key[j] << 32) | (u64)((prev << SEG_SHIFT) | (start + tid * MSD_ITEMS + j));
-        s.dig[p] = (u8)d;
+        s.rec[s.cnt[d] + sl] = ((u64)key[j] << 32) | (u64)((prev << SEG_SHIFT) | (d << 12) | (tid * MSD_ITEMS + j));
       }
       prev = d;
     }
   }
+  s.gdst[tid] = (int)g - (int)ex;
   __syncthreads();
   u64* out = rec_out + ((size_t)b << SEG_SHIFT);
 #pragma unroll
   for (int k = 0; k < MSD_ITEMS; k++) {
     const u32 p = k * MSD_THREADS + tid;
-    if (p < count) out[(int)p + s.gdst[s.dig[p]]] = s.rec[p];
+    if (p < count) {
+      const u64 rvv = s.rec[p];
+      const u32 lw = (u32)rvv;
+      const u32 low = (lw & 0x0ff00000u) | (start + (lw & 0xfffu));
+      out[(int)p + s.gdst[(lw >> 12) & 0xffu]] = (rvv & 0xffffffff00000000ull) | low;
+    }
   }
 }
 
@@ -166,10 +174,15 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
 struct MsdBucketSmem {
   __align__(16) u64 buf[2][MB_BUF];
   __align__(16) u32 cnt[MB_CELLS / 2];  // two 16-bit cell counters per word
+  __align__(16) u8 outb[MB_BUF + 16];   // the bucket's slice of the BWT column, at the alignment (mod 16) it has in global memory
+  u32 multi[MB_BUF / 2];                // cells holding two or more records: first row | size << 16
   u32 ws[MB_THREADS / 32 + 1];
   __align__(8) u64 bar[2];
   u32 w[2], M[2], off[2], st[2];
+  u32 nmulti;
 };
+
+static_assert(sizeof(MsdBucketSmem) <= 227 * 1024, "bucket sort state must fit the 227 KiB of shared memory a CTA can have");
 
 __device__ __forceinline__ u32 cell_of(u32 key) { return key >> (32 - MB_CELL_BITS); }
 
@@ -266,34 +279,89 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
       }
     }
     __syncthreads();
-    // ---- every record ranks itself inside its cell; emit the column ----
-    const u16* cend = reinterpret_cast<const u16*>(s.cnt);  // after the scatter: end of every cell
-    u8* Ub = U + ((size_t)blockb << SEG_SHIFT) + ust;
-#pragma unroll 2
-    for (int k = 0; k < MB_ITEMS; k++) {
-      const u32 p = tid + k * MB_THREADS;
-      if (p < M) {
-        const u64 rv = buf[p];
-        const u32 key = (u32)(rv >> 32), lw = (u32)rv;
-        const u32 c = cell_of(key);
-        const u32 lo = c ? cend[c - 1] : 0u, hi = cend[c];
-        u32 less = 0, eq_before = 0, eq = 0;
-        for (u32 q = lo; q < hi; q++) {
-          const u32 kq = (u32)(buf[q] >> 32);
-          less += kq < key ? 1u : 0u;
-          if (kq == key) { eq++; eq_before += q < p ? 1u : 0u; }
+    // ---- cells in order: a single record is final, larger cells are queued ----
+    u8* ob = s.outb + (ust & 15u);
+    {
+      const uint4* c4 = reinterpret_cast<const uint4*>(s.cnt) + tid * 2;  // after the scatter: end of every cell
+      const uint4 x0 = c4[0], x1 = c4[1];
+      const u32 wv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const u32 lo0 = tid ? (s.cnt[tid * 8 - 1] >> 16) : 0u;
+      u32 lo = lo0, nmul = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const u32 hi = (k & 1) ? (wv[k >> 1] >> 16) : (wv[k >> 1] & 0xffffu);
+        const u32 size = hi - lo;
+        if (size == 1) {
+          const u32 lw = (u32)buf[lo];
+          ob[lo] = (u8)(lw >> SEG_SHIFT);
+          if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + lo;
         }
-        const u32 f = lo + less + eq_before;
-        Ub[f] = (u8)(lw >> SEG_SHIFT);
-        if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + f;
-        if (eq > 1 && eq_before == 0) {
-          // first member of a group of rotations that share their first 5 bytes: hand the group to the resolver
-          u32 t = atomicAdd(&ctl[0], eq);
-          const u32 head = (blockb << SEG_SHIFT) | (ust + lo + less);
-          for (u32 q = lo; q < hi; q++) {
-            const u64 rq = buf[q];
-            if ((u32)(rq >> 32) == key) { tie_head[t] = head; tie_idx[t] = (blockb << SEG_SHIFT) | ((u32)rq & SEG_MASK); t++; }
+        nmul += size > 1 ? 1u : 0u;
+        lo = hi;
+      }
+      // queue positions by a block scan (one shared counter would serialise a couple of thousand atomics per bucket)
+      u32 tot;
+      u32 at = block_excl_add<MB_THREADS, u32>(nmul, s.ws, &tot);
+      if (tid == 0) s.nmulti = tot;
+      if (nmul) {
+        lo = lo0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const u32 hi = (k & 1) ? (wv[k >> 1] >> 16) : (wv[k >> 1] & 0xffffu);
+          if (hi - lo > 1) s.multi[at++] = lo | ((hi - lo) << 16);
+          lo = hi;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- one thread per queued cell: order its few records in place, emit, report equal keys ----
+    {
+      const u32 nm = s.nmulti;
+      for (u32 j = tid; j < nm; j += MB_THREADS) {
+        const u32 mm = s.multi[j], lo = mm & 0xffffu, size = mm >> 16;
+        if (size > MB_MAXCELL) { atomicOr(&ctl[1], 1u); continue; }  // far from uniform after all: the LSD path redoes the batch
+        u64* cb = buf + lo;
+        for (u32 a = 1; a < size; a++) {
+          const u64 x = cb[a];
+          u32 q = a;
+          while (q > 0) {
+            const u64 y = cb[q - 1];
+            if (y <= x) break;
+            cb[q] = y;
+            q--;
           }
+          cb[q] = x;
+        }
+        u32 run0 = 0;
+        for (u32 q = 0; q < size; q++) {
+          const u64 rq = cb[q];
+          const u32 lw = (u32)rq;
+          ob[lo + q] = (u8)(lw >> SEG_SHIFT);
+          if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + lo + q;
+          if (q + 1 == size || (u32)(cb[q + 1] >> 32) != (u32)(rq >> 32)) {
+            const u32 run = q + 1 - run0;
+            if (run > 1) {
+              // rotations that share their first 5 bytes: hand the group to the resolver (bwt.cu k_resolve_direct)
+              u32 t = atomicAdd(&ctl[0], run);
+              const u32 head = (blockb << SEG_SHIFT) | (ust + lo + run0);
+              for (u32 z = run0; z <= q; z++) { tie_head[t] = head; tie_idx[t] = (blockb << SEG_SHIFT) | ((u32)cb[z] & SEG_MASK); t++; }
+            }
+            run0 = q + 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- the column slice goes out in 16-byte pieces ----
+    {
+      const u32 first = ust & 15u, last = first + M;
+      u8* Ug = U + ((size_t)blockb << SEG_SHIFT) + (ust - first);  // 16-byte aligned
+      for (u32 c16 = tid * 16u; c16 < last; c16 += MB_THREADS * 16u) {
+        if (c16 >= first && c16 + 16u <= last) {
+          *reinterpret_cast<uint4*>(Ug + c16) = *reinterpret_cast<const uint4*>(s.outb + c16);
+        } else {
+          const u32 e = min(c16 + 16u, last);
+          for (u32 x = max(c16, first); x < e; x++) Ug[x] = s.outb[x];
         }
       }
     }

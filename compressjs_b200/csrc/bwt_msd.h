@@ -5,12 +5,14 @@
 #define MSD_TILE 4096      // text bytes per scatter tile
 #define MSD_THREADS 256
 #define MSD_ITEMS 16
+#define MSD_CTAS_PER_SM 5
 #define MB_THREADS 1024    // one persistent CTA per SM
 #define MB_ITEMS 10
 #define MB_BUF (MB_THREADS * MB_ITEMS)  // records per shared-memory buffer (80 KiB); two buffers: sort one, prefetch the next
 #define MB_CAP (MB_BUF - 2)             // largest (block, first byte) bucket the path takes
 #define MB_CELL_BITS 14
 #define MB_CELLS (1u << MB_CELL_BITS)   // interpolation cells per bucket
+#define MB_MAXCELL 128u                 // a fuller cell means the keys are far from uniform: give up, the LSD path takes the batch
 
 struct MsdBlk {
   u32 a, a2;  // symbols in use in the block, squared

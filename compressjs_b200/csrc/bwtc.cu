@@ -18,7 +18,7 @@
 #include "enc.h"
 #include "bwtc_core.cuh"
 
-void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel, u32* d_sa_out);
+void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel, u32* d_sa_out, u32* d_hist_out = nullptr);
 void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out);
 
 struct BwtcState {
@@ -113,9 +113,12 @@ void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out
         mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused);
       }
       {
-        StageScope s(c, ST_HUFF);   // the model + coder stage takes the slot of the Huffman stage in the statistics
+        StageScope s(c, ST_HUFF);   // statistics: the model takes the slot of the Huffman stage (ms_huff) ...
         k_bwtc_model<<<nb, 32, 0, c.stream>>>(sym, dm, dn, dpidx, dused, blockSize, fast, triples, tcap, tcount);
         KLAUNCH(c); KCHECK();
+      }
+      {
+        StageScope s(c, ST_PACK);   // ... and the serial range coder the slot of the bit packer (ms_pack)
         k_bwtc_code<<<1, 1, 0, c.stream>>>(st, triples, tcount, nb, tcap);
         KLAUNCH(c); KCHECK();
       }

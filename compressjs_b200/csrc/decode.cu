@@ -944,16 +944,24 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   std::vector<Cand>& cands = S.cands;
   {
     StageScope ss(c, ST_SCAN);
-    const u32 cap = (u32)(n / 8000 + 1024);
+    // Highly repetitive input compresses to a few dozen bytes per block (and multistream files may hold thousands of
+    // tiny members), so the number of magics is not bounded by the usual ~100 KB per block: when the first guess is too
+    // small the scan counts them all and runs once more with exactly that capacity.
+    u32 cap = (u32)(n / 8000 + 1024);
     DBuf<Cand> dc(c, cap);
     DBuf<u32> dcount(c, 1);
-    CUDA_CHECK(cudaMemsetAsync(dcount, 0, 4, c.stream));
-    k_scan_magic<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(din, n, dc, dcount, cap);
-    KLAUNCH(c); KCHECK();
     u32 cnt = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&cnt, dcount, 4, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    if (cnt > cap) throw B2Error{B2_ERR_CUDA, "too many magic candidates"};
+    for (int attempt = 0; attempt < 2; attempt++) {
+      CUDA_CHECK(cudaMemsetAsync(dcount, 0, 4, c.stream));
+      k_scan_magic<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(din, n, dc, dcount, cap);
+      KLAUNCH(c); KCHECK();
+      CUDA_CHECK(cudaMemcpyAsync(&cnt, dcount, 4, cudaMemcpyDeviceToHost, c.stream));
+      CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      if (cnt <= cap) break;
+      cap = cnt;
+      dc.alloc(c, cap);
+    }
+    if (cnt > cap) throw B2Error{B2_ERR_CUDA, "magic scan did not settle"};
     cands.resize(cnt);
     if (cnt) CUDA_CHECK(cudaMemcpyAsync(cands.data(), dc, sizeof(Cand) * cnt, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));

@@ -20,20 +20,24 @@ struct Rle1Plan {
   size_t nblocks = 0;      // entries of h_blocks
   size_t first_index = 0;  // global block index of h_blocks[0] (range plans)
   size_t total_guess = 0;  // ceil(W(N) / blockSize)
+  u64 w_total = 0;         // W at the end of the buffer (RLE1 bytes of the whole input up to there)
   u64 ntiles = 0;
 };
 
 #define RLE_TILE 4096
 
 void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan);
-void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, long long spec_first, size_t spec_count, bool tiles_only);
+// st0 / W0: run state and RLE1 output in front of the buffer when it is a share of a larger input (0, 0 for a whole file);
+// agg_state (host, 2 x u64, optional): receives the aggregate run state of the buffer and the length of its leading run.
+void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, long long spec_first, size_t spec_count, bool tiles_only,
+                  u64 st0 = 0, u64 W0 = 0, u64* agg_state = nullptr);
 // materialise blocks [first, first+count) of the plan into the slot layout at d_T (u8[count<<20]);
 // d_n receives their lengths, d_crc their CRCs.
 void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc);
 
 // MTF + RLE2 (lib/Bzip2.js:743-815): U (slot layout) -> symbols u16 (slot layout), m, freq, used map
 void mtf_rle2_batch(Ctx& c, const u8* d_T, const u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u16* d_sym, u32* d_m, u32* d_freq /*[nblk][258]*/,
-                    u32* d_used /*[nblk][8]*/);
+                    u32* d_used /*[nblk][8]*/, const u32* d_bytehist = nullptr /*[nblk][256] byte histograms of the blocks, if known*/);
 
 #define HUFF_MAXSYM 258
 #define HUFF_MAXGROUPS 6

@@ -23,7 +23,7 @@
 #include "enc.h"
 
 void bwt_forward_batch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u32* d_pidx, bool sentinel = false,
-                       u32* d_sa_out = nullptr);
+                       u32* d_sa_out = nullptr, u32* d_hist_out = nullptr);
 
 // ---- bit writers (stream is MSB first; words are stored big-endian) ----------------------
 __device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
@@ -315,7 +315,7 @@ struct EncSession {
   u32 cap_blocks = 0;
   DBuf<u8> T, U, dsel, dselmtf;
   DBuf<u16> sym;
-  DBuf<u32> dn, dcrc, dpidx, dm, dfreq, dused;
+  DBuf<u32> dn, dcrc, dpidx, dm, dfreq, dused, dhist;
   DBuf<HuffBlk> dhb;
   DBuf<u64> dbitoff;
   std::vector<u32> hn, hm, hp;
@@ -344,7 +344,7 @@ struct EncSession {
     cap_blocks = nb;
     T.alloc(c, (size_t)nb << SEG_SHIFT); U.alloc(c, (size_t)nb << SEG_SHIFT); sym.alloc(c, (size_t)nb << SEG_SHIFT);
     dn.alloc(c, nb); dcrc.alloc(c, nb); dpidx.alloc(c, nb); dm.alloc(c, nb);
-    dfreq.alloc(c, (size_t)nb * HUFF_MAXSYM); dused.alloc(c, (size_t)nb * 8);
+    dfreq.alloc(c, (size_t)nb * HUFF_MAXSYM); dused.alloc(c, (size_t)nb * 8); dhist.alloc(c, (size_t)nb * 256);
     dsel.alloc(c, (size_t)nb * SEL_STRIDE); dselmtf.alloc(c, (size_t)nb * SEL_STRIDE);
     dhb.alloc(c, nb); dbitoff.alloc(c, nb);
     hn.resize(nb); hm.resize(nb); hp.resize(nb); hhb.resize(nb); hoff.resize(nb);
@@ -372,11 +372,11 @@ struct EncSession {
       {
         StageScope s(c, ST_BWT);
         CUDA_CHECK(cudaMemsetAsync(dpidx, 0, nb * 4, c.stream));
-        bwt_forward_batch(c, T, U, dn, hn.data(), nb, dpidx);
+        bwt_forward_batch(c, T, U, dn, hn.data(), nb, dpidx, false, nullptr, dhist);
       }
       {
         StageScope s(c, ST_MTF);
-        mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused);
+        mtf_rle2_batch(c, T, U, dn, hn.data(), nb, sym, dm, dfreq, dused, dhist);
       }
       {
         StageScope s(c, ST_HUFF);
@@ -478,6 +478,41 @@ void bzip2_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_ou
   const u64 bits = S.finish(out_n);
   if (!whole_file && out_bits) *out_bits = bits - (u64)bit_phase;
   if (crcs_out) *crcs_out = S.all_crc;
+}
+
+// ---- multi-GPU: every rank holds a share of the input (plus some bytes of the next share) ---------------------
+// summary of a share for the planner of the other ranks: out = {aggregate run state, length of the leading run,
+// RLE1 bytes of the share when no run enters it, share length}
+void bzip2_share_summary(Ctx& c, const u8* d_in, size_t n, u64* out) {
+  out[0] = out[1] = out[2] = 0; out[3] = n;
+  if (!n) return;
+  Rle1Plan plan;
+  u64 agg[2] = {0, 0};
+  StageScope s(c, ST_RLE1);
+  rle1_plan_ex(c, d_in, n, 9, plan, -1, 0, true, 0, 0, agg);  // tiles only: the level does not matter
+  out[0] = agg[0]; out[1] = agg[1]; out[2] = plan.w_total;
+}
+// Cut blocks [first, first+count) of the whole input inside this rank's buffer (share + halo): st0 / W0 = run state
+// and RLE1 output in front of the buffer (from the summaries of the ranks before).  The blocks are located by the
+// speculated boundary W = first * blockSize, exact unless a run-phase slip happened earlier in the file: the caller
+// checks that the pieces of all ranks chain up.  info = {raw start, raw end (buffer offsets), first, planned, cut,
+// W at the end of the buffer}.  The plan is kept for the b2_bzip2_encode_range_dev call that follows.
+void bzip2_plan_share(Ctx& c, const u8* d_buf, size_t n, int level, u64 st0, u64 W0, size_t first, size_t count, u64* info) {
+  if (c.plan_cache) { delete static_cast<Rle1Plan*>(c.plan_cache); c.plan_cache = nullptr; }
+  Rle1Plan* planp = new Rle1Plan();
+  struct Owner { Rle1Plan* p; bool keep; ~Owner() { if (!keep) delete p; } } owner{planp, false};
+  {
+    StageScope s(c, ST_RLE1);
+    rle1_plan_ex(c, d_buf, n, level, *planp, (long long)first, count, false, st0, W0, nullptr);
+  }
+  info[0] = planp->nblocks ? planp->h_blocks.front().s : 0;
+  info[1] = planp->nblocks ? planp->h_blocks.back().e : 0;
+  info[2] = first;
+  info[3] = count;
+  info[4] = planp->nblocks;
+  info[5] = planp->w_total;
+  c.plan_cache = planp; c.plan_ptr = d_buf; c.plan_n = n; c.plan_level = level;
+  owner.keep = true;
 }
 
 // Bzip2.compressFile with HOST buffers (b2_bzip2_compress).  With a pinned input the upload is cut into chunks

@@ -13,8 +13,12 @@
 //                   the chunk); the rank of a byte is the number of live keys above its own, counted
 //                   through a bucketed live-key bitmap with suffix sums, and the bytes of one step
 //                   that precede each other are settled with SWAR pair compares
-//   k_rle2        : zero ranks form runs -> bijective base-2 RUNA/RUNB digits; chained scans
-//                   (run starts, output offsets) across tiles; symbols u16 + histogram + EOB
+//                   The same pass summarises the chunk for the zero-run coder: leading / trailing zeros and the number
+//                   of symbols its non-zero ranks and interior runs will emit.
+//   k_rle2_scan   : one warp per block walks the chunk summaries: output offset and carried-in run length of every chunk
+//                   (a run belongs to the chunk that holds the non-zero rank ending it); final run + EOB + m
+//   k_rle2        : zero ranks form runs -> bijective base-2 RUNA/RUNB digits (lib/Bzip2.js:783-794); every chunk knows
+//                   its offsets, so there is no chain between tiles; symbols u16 + histogram
 #include "enc.h"
 
 #define MTF_CHUNK 4096
@@ -38,6 +42,11 @@ __global__ void __launch_bounds__(256) k_used(const u8* __restrict__ U, const u3
     if (loc[k]) atomicOr(&f[k], loc[k]);
   __syncthreads();
   if (threadIdx.x < 8 && f[threadIdx.x]) atomicOr(&used[seg * 8 + threadIdx.x], f[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_used_from_hist(const u32* __restrict__ hist, u32* __restrict__ used) {
+  const u32 bal = __ballot_sync(FULL_MASK, hist[blockIdx.x * 256 + threadIdx.x] != 0);
+  if ((threadIdx.x & 31) == 0) used[blockIdx.x * 8 + (threadIdx.x >> 5)] = bal;
 }
 
 // lastpos[(seg*cps + chunk)*256 + c] = (last position of byte c inside the chunk) + 1, 0 if none
@@ -89,7 +98,7 @@ struct MtfWarp {
 //   * only the last use of a byte inside the window rewrites its key.
 __global__ void __launch_bounds__(MR_WARPS * 32)
 k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, const u32* __restrict__ lastpos,
-            const u32* __restrict__ used, u8* __restrict__ R, u32 nblk) {
+            const u32* __restrict__ used, u8* __restrict__ R, u32 nblk, uint4* __restrict__ rsum) {
   __shared__ MtfWarp sm[MR_WARPS];
   const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 gchunk = blockIdx.x * MR_WARPS + w;
@@ -131,6 +140,9 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
   const u8* src = U + ((size_t)seg << SEG_SHIFT) + start;
   u8* dst = R + ((size_t)seg << SEG_SHIFT) + start;
   const u32 H = 0x80008000u, ONE = 0x00010001u;
+  // zero-run summary of the chunk (warp-uniform state + a per-lane count of emitted symbols)
+  u32 z_open = 0, z_lead = 0, z_acc = 0;
+  bool z_seen = false;
   for (u32 base = 0; base < count; base += 32) {
     const bool valid = base + lane < count;
     const u32 c = valid ? (u32)src[base + lane] : (256u + lane);
@@ -197,6 +209,25 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
       rank += __popc(acc);
     }
     if (valid) dst[base + lane] = (u8)rank;
+    {
+      const u32 nzm = __ballot_sync(FULL_MASK, valid && rank != 0);
+      const u32 nvalid = min(32u, count - base);
+      if (valid && rank != 0) {
+        const u32 below = nzm & lanemask_lt();
+        if (below) {
+          const u32 L = lane - (31 - __clz(below)) - 1;          // zeros since the previous non-zero of this step
+          z_acc += 1 + (L ? 31 - __clz(L + 1) : 0);
+        } else if (z_seen) {
+          const u32 L = z_open + lane;
+          z_acc += 1 + (L ? 31 - __clz(L + 1) : 0);
+        } else {
+          z_lead = z_open + lane;                                 // the run that reaches back to the chunk start is not ours to count
+          z_acc += 1;
+        }
+      }
+      if (nzm) { z_seen = true; z_open = nvalid - 1 - (31 - __clz(nzm)); }
+      else z_open += nvalid;
+    }
     // ---- the last use of every byte in the window rewrites its key ----
     if (valid && is_last) {
       atomicAnd(&s.bm[q >> 7][(q & 127u) >> 5], ~(1u << (q & 31u)));
@@ -207,34 +238,88 @@ k_mtf_ranks(const u8* __restrict__ U, const u32* __restrict__ seg_n, u32 cps, co
     if (lane == 0) s.bm[tb >> 7][(tb & 127u) >> 5] = newbits;  // windows are 32-aligned: this word is ours alone
     __syncwarp();
   }
+  {
+    const u32 inner = warp_reduce_add(z_acc);
+    const u32 lead = z_seen ? warp_reduce_max(z_lead) : count;
+    if (lane == 0) rsum[gchunk] = make_uint4(lead, z_seen ? z_open : count, inner, z_seen ? 0u : 1u);
+  }
+}
+
+// One warp per block: walk the chunk summaries in order (lib/Bzip2.js:783-794 flushes a run when the next non-zero
+// rank arrives, so the run is charged to the chunk holding that rank).  plan[chunk] = (output offset, zeros carried in).
+__global__ void __launch_bounds__(32)
+k_rle2_scan(const uint4* __restrict__ rsum, const u32* __restrict__ seg_n, u32 cps, const u32* __restrict__ used, uint2* __restrict__ plan,
+            u16* __restrict__ A, u32* __restrict__ m_out, u32* __restrict__ freq) {
+  const u32 seg = blockIdx.x, lane = threadIdx.x;
+  const u32 n = seg_n[seg];
+  if (n == 0) return;
+  const u32 nch = (n + MTF_CHUNK - 1) / MTF_CHUNK;
+  u32 carry = 0, o = 0;
+  for (u32 c0 = 0; c0 < nch; c0 += 32) {
+    const u32 k = c0 + lane;
+    uint4 v = make_uint4(0, 0, 0, 1);
+    if (k < nch) v = rsum[(size_t)seg * cps + k];
+    u32 my_o = 0, my_c = 0;
+    const u32 lim = min(32u, nch - c0);
+    for (u32 j = 0; j < lim; j++) {
+      const u32 lead = __shfl_sync(FULL_MASK, v.x, j), trail = __shfl_sync(FULL_MASK, v.y, j);
+      const u32 inner = __shfl_sync(FULL_MASK, v.z, j), allz = __shfl_sync(FULL_MASK, v.w, j);
+      if (lane == j) { my_o = o; my_c = carry; }
+      if (allz) carry += lead;
+      else {
+        const u32 r = carry + lead;
+        o += (r ? 31 - __clz(r + 1) : 0) + inner;
+        carry = trail;
+      }
+    }
+    if (k < nch) plan[(size_t)seg * cps + k] = make_uint2(my_o, my_c);
+  }
+  if (lane == 0) {
+    u16* a = A + ((size_t)seg << SEG_SHIFT);
+    u32* fq = freq + (size_t)seg * HUFF_MAXSYM;
+    u32 L = carry, f0 = 0, f1 = 0;
+    while (L) {  // the run still open at the end of the block
+      if (L & 1) { a[o++] = 0; f0++; L -= 1; }
+      else { a[o++] = 1; f1++; L -= 2; }
+      L >>= 1;
+    }
+    u32 alpha = 0;
+    for (int k = 0; k < 8; k++) alpha += __popc(used[seg * 8 + k]);
+    a[o] = (u16)(alpha + 1);  // end of block symbol
+    if (f0) atomicAdd(&fq[0], f0);
+    if (f1) atomicAdd(&fq[1], f1);
+    atomicAdd(&fq[alpha + 1], 1u);
+    m_out[seg] = o + 1;
+  }
 }
 
 // ---- RLE2 ---------------------------------------------------------------------------------
 #define R2_THREADS 256
-#define R2_ITEMS 8
-#define R2_TILE (R2_THREADS * R2_ITEMS)
+#define R2_ITEMS 16
+#define R2_TILE (R2_THREADS * R2_ITEMS)   // == MTF_CHUNK: one tile per chunk summary
 
 __global__ void __launch_bounds__(R2_THREADS)
-k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const u32* __restrict__ used, u16* __restrict__ A,
-       u32* __restrict__ m_out, u32* __restrict__ freq, u32* ticket, u64* st_run, u64* st_off) {
+k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const uint2* __restrict__ plan, u16* __restrict__ A,
+       u32* __restrict__ freq) {
   __shared__ u32 hist[HUFF_MAXSYM];
   __shared__ u32 ws[R2_THREADS / 32 + 1];
-  __shared__ u32 s_tile, s_crun, s_coff;
   const u32 tid = threadIdx.x;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (u32 i = tid; i < HUFF_MAXSYM; i += R2_THREADS) hist[i] = 0;
-  __syncthreads();
-  const u32 tile = s_tile;
-  const u32 seg = tile / tps, lt = tile % tps;
+  const u32 seg = blockIdx.x / tps, lt = blockIdx.x % tps;
   const u32 n = seg_n[seg];
   const u32 start = lt * R2_TILE;
   if (start >= n) return;
+  for (u32 i = tid; i < HUFF_MAXSYM; i += R2_THREADS) hist[i] = 0;
+  const uint2 pl = plan[(size_t)seg * tps + lt];
   const u8* r = R + ((size_t)seg << SEG_SHIFT);
   u16* a = A + ((size_t)seg << SEG_SHIFT);
   const u32 p0 = start + tid * R2_ITEMS;
-  u8 v[R2_ITEMS + 1];
+  u8 v[R2_ITEMS];
+  {
+    const uint4 x = *reinterpret_cast<const uint4*>(r + p0);  // inside the 1 MiB slot; bytes past n are ignored below
+    const u32 xw[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-  for (int j = 0; j <= R2_ITEMS; j++) v[j] = (p0 + j < n) ? r[p0 + j] : 1;  // beyond the end behaves like "non zero"
+    for (int j = 0; j < R2_ITEMS; j++) v[j] = (u8)(xw[j >> 2] >> (8 * (j & 3)));
+  }
   // last non-zero position (+1) among this thread's items
   u32 lastnz = 0;
 #pragma unroll
@@ -252,69 +337,41 @@ k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const u
     u32 xe = __shfl_up_sync(FULL_MASK, xi, 1);
     if (tid == 0) xe = 0;
     if (tid < R2_THREADS / 32) ws[tid] = xe;
-    if (tid == R2_THREADS / 32 - 1) ws[R2_THREADS / 32] = xi;
   }
   __syncthreads();
   const u32 ex_run = max(exw, ws[tid >> 5]);
-  const u32 tot_run = ws[R2_THREADS / 32];
   __syncthreads();
-  if (tid < 32) {
-    u32 rr = lookback_warp(st_run + (size_t)seg * tps, lt, tot_run, OpMax());
-    if (tid == 0) s_crun = rr;
-  }
-  __syncthreads();
-  u32 rs = max(s_crun, ex_run);  // run start candidate = position after the last non-zero before p
-  // per item emission counts
-  u32 cnt[R2_ITEMS];
+  u32 rs = max(start - pl.y, ex_run);  // position after the last non-zero before p (pl.y zeros were carried into the tile)
+  // symbols emitted per item: a non-zero rank flushes the run in front of it, then writes itself
   u32 rlen[R2_ITEMS];
   u32 sum = 0;
 #pragma unroll
   for (int j = 0; j < R2_ITEMS; j++) {
     const u32 p = p0 + j;
-    cnt[j] = 0; rlen[j] = 0;
-    if (p < n) {
-      if (v[j] != 0) { cnt[j] = 1; rs = p + 1; }
-      else if (v[j + 1] != 0 || p + 1 == n) {  // the zero run ends here
-        const u32 L = p - rs + 1;
-        rlen[j] = L;
-        cnt[j] = 31 - __clz(L + 1);
-      }
+    rlen[j] = 0;
+    if (p < n && v[j] != 0) {
+      const u32 L = p - rs;
+      rlen[j] = L;
+      sum += 1 + (L ? 31 - __clz(L + 1) : 0);
+      rs = p + 1;
     }
-    sum += cnt[j];
   }
   u32 tot_off;
   const u32 ex_off = block_excl_add<R2_THREADS, u32>(sum, ws, &tot_off);
-  if (tid < 32) {
-    u32 oo = lookback_warp(st_off + (size_t)seg * tps, lt, tot_off, OpAdd());
-    if (tid == 0) s_coff = oo;
-  }
-  __syncthreads();
-  u32 o = s_coff + ex_off;
-  u32 alpha = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) alpha += __popc(used[seg * 8 + k]);
+  u32 o = pl.x + ex_off;
 #pragma unroll
   for (int j = 0; j < R2_ITEMS; j++) {
     const u32 p = p0 + j;
-    if (p < n) {
-      if (v[j] != 0) {
-        const u32 s = (u32)v[j] + 1;
-        a[o] = (u16)s;
-        atomicAdd(&hist[s], 1u);
-      } else if (rlen[j]) {
-        u32 L = rlen[j], oo = o;
-        while (L) {  // lib/Bzip2.js:783-794 emitLastRun
-          if (L & 1) { a[oo++] = 0; atomicAdd(&hist[0], 1u); L -= 1; }
-          else { a[oo++] = 1; atomicAdd(&hist[1], 1u); L -= 2; }
-          L >>= 1;
-        }
+    if (p < n && v[j] != 0) {
+      u32 L = rlen[j];
+      while (L) {  // lib/Bzip2.js:783-794 emitLastRun
+        if (L & 1) { a[o++] = 0; atomicAdd(&hist[0], 1u); L -= 1; }
+        else { a[o++] = 1; atomicAdd(&hist[1], 1u); L -= 2; }
+        L >>= 1;
       }
-      o += cnt[j];
-      if (p + 1 == n) {  // end of block symbol
-        a[o] = (u16)(alpha + 1);
-        atomicAdd(&hist[alpha + 1], 1u);
-        m_out[seg] = o + 1;
-      }
+      const u32 sy = (u32)v[j] + 1;
+      a[o++] = (u16)sy;
+      atomicAdd(&hist[sy], 1u);
     }
   }
   __syncthreads();
@@ -323,7 +380,7 @@ k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const u
 }
 
 void mtf_rle2_batch(Ctx& c, const u8* d_T, const u8* d_U, const u32* d_n, const u32* h_n, u32 nblk, u16* d_sym, u32* d_m, u32* d_freq,
-                    u32* d_used) {
+                    u32* d_used, const u32* d_bytehist) {
   (void)d_T;
   u32 n_max = 0;
   for (u32 b = 0; b < nblk; b++) n_max = h_n[b] > n_max ? h_n[b] : n_max;
@@ -332,25 +389,26 @@ void mtf_rle2_batch(Ctx& c, const u8* d_T, const u8* d_U, const u32* d_n, const 
   CUDA_CHECK(cudaMemsetAsync(d_used, 0, (size_t)nblk * 8 * 4, c.stream));
   CUDA_CHECK(cudaMemsetAsync(d_freq, 0, (size_t)nblk * HUFF_MAXSYM * 4, c.stream));
   CUDA_CHECK(cudaMemsetAsync(d_m, 0, (size_t)nblk * 4, c.stream));
-  k_used<<<utiles * nblk, 256, 0, c.stream>>>(d_U, d_n, utiles, d_used);
+  if (d_bytehist) k_used_from_hist<<<nblk, 256, 0, c.stream>>>(d_bytehist, d_used);  // the BWT column is a permutation of the block
+  else k_used<<<utiles * nblk, 256, 0, c.stream>>>(d_U, d_n, utiles, d_used);
   KLAUNCH(c); KCHECK();
   const u32 cps = (n_max + MTF_CHUNK - 1) / MTF_CHUNK;
   DBuf<u32> lastpos(c, (size_t)nblk * cps * 256);
   DBuf<u8> R(c, (size_t)nblk << SEG_SHIFT);
+  DBuf<uint4> rsum(c, (size_t)nblk * cps);
+  DBuf<uint2> plan(c, (size_t)nblk * cps);
   k_mtf_lastpos<<<cps * nblk, 256, 0, c.stream>>>(d_U, d_n, cps, lastpos);
   KLAUNCH(c); KCHECK();
   k_mtf_prefix<<<nblk, 256, 0, c.stream>>>(d_n, cps, lastpos);
   KLAUNCH(c); KCHECK();
   {
     const u32 chunks = cps * nblk;
-    k_mtf_ranks<<<(chunks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, c.stream>>>(d_U, d_n, cps, lastpos, d_used, R, nblk);
+    k_mtf_ranks<<<(chunks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, c.stream>>>(d_U, d_n, cps, lastpos, d_used, R, nblk, rsum);
     KLAUNCH(c); KCHECK();
   }
-  const u32 tps = (n_max + R2_TILE - 1) / R2_TILE;
-  DBuf<u64> st(c, (size_t)2 * nblk * tps);
-  DBuf<u32> ticket(c, 1);
-  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)2 * nblk * tps * 8, c.stream));
-  CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
-  k_rle2<<<tps * nblk, R2_THREADS, 0, c.stream>>>(R, d_n, tps, d_used, d_sym, d_m, d_freq, ticket, st.p, st.p + (size_t)nblk * tps);
+  k_rle2_scan<<<nblk, 32, 0, c.stream>>>(rsum, d_n, cps, d_used, plan, d_sym, d_m, d_freq);
+  KLAUNCH(c); KCHECK();
+  static_assert(R2_TILE == MTF_CHUNK, "one zero-run tile per MTF chunk");
+  k_rle2<<<cps * nblk, R2_THREADS, 0, c.stream>>>(R, d_n, cps, plan, d_sym, d_freq);
   KLAUNCH(c); KCHECK();
 }

@@ -249,7 +249,8 @@ __device__ __forceinline__ u64 rs_combine(u64 A, u64 B) {
 
 #define RS_THREADS 1024
 __global__ void __launch_bounds__(RS_THREADS)
-k_rle_scan(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u32* __restrict__ carry, u64* __restrict__ prefix) {
+k_rle_scan(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u32* __restrict__ carry, u64* __restrict__ prefix, u64 st0, u64 W0,
+           u64* __restrict__ agg_out) {
   __shared__ u64 sa[RS_THREADS], sb[RS_THREADS];
   const u32 tid = threadIdx.x;
   const u64 per = (ntiles + RS_THREADS - 1) / RS_THREADS;
@@ -272,7 +273,8 @@ k_rle_scan(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u32* __restrict_
     __syncthreads();
     u64* tmp = src; src = dst; dst = tmp;
   }
-  u64 st = tid ? src[tid - 1] : 0;
+  u64 st = rs_combine(st0, tid ? src[tid - 1] : 0);  // st0: run state entering the buffer (a share of a larger input)
+  if (tid == 0 && agg_out) *agg_out = src[RS_THREADS - 1];
   __syncthreads();
   // 3. carries + per-tile output sums (stored in prefix[] for now)
   u64 mysum = 0;
@@ -298,8 +300,8 @@ k_rle_scan(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u32* __restrict_
     __syncthreads();
     u64* tmp = src; src = dst; dst = tmp;
   }
-  u64 run = tid ? src[tid - 1] : 0;
-  const u64 grand = src[RS_THREADS - 1];
+  u64 run = W0 + (tid ? src[tid - 1] : 0);
+  const u64 grand = W0 + src[RS_THREADS - 1];
   for (u64 t = t0; t < t1; t++) {
     const u64 S = prefix[t];
     prefix[t] = run;
@@ -353,7 +355,7 @@ k_rle_scan_g1(const TileSum* __restrict__ sums, u64 ntiles, u64 N, u64* __restri
 // one CTA: exclusive scan of ngroups values (state operator when STATE, plain addition otherwise); out[ngroups] = total
 template <bool STATE>
 __global__ void __launch_bounds__(RS_THREADS)
-k_rle_scan_groups(const u64* __restrict__ in, u32 ngroups, u64* __restrict__ out) {
+k_rle_scan_groups(const u64* __restrict__ in, u32 ngroups, u64* __restrict__ out, u64 init, u64* __restrict__ agg_out) {
   __shared__ u64 sa[RS_THREADS], sb[RS_THREADS];
   const u32 tid = threadIdx.x;
   const u32 per = (ngroups + RS_THREADS - 1) / RS_THREADS;
@@ -371,12 +373,14 @@ k_rle_scan_groups(const u64* __restrict__ in, u32 ngroups, u64* __restrict__ out
     u64* tmp = src; src = dst; dst = tmp;
   }
   u64 run = tid ? src[tid - 1] : 0;
+  run = STATE ? rs_combine(init, run) : init + run;
+  if (tid == 0 && agg_out) *agg_out = src[RS_THREADS - 1];  // combination of all groups without `init`
   for (u32 g = g0; g < g1; g++) {
     const u64 v = in[g];
     out[g] = run;
     run = STATE ? rs_combine(run, v) : run + v;
   }
-  if (tid == RS_THREADS - 1) out[ngroups] = src[RS_THREADS - 1];
+  if (tid == RS_THREADS - 1) out[ngroups] = STATE ? rs_combine(init, src[RS_THREADS - 1]) : init + src[RS_THREADS - 1];
 }
 __global__ void __launch_bounds__(RG_THREADS)
 k_rle_scan_g3(const TileSum* __restrict__ sums, u64 ntiles, u64 N, const u64* __restrict__ group_start, u32* __restrict__ carry,
@@ -494,8 +498,8 @@ k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ c
     nblocks_out += r;
     maxblocks = (r == P - 1 && open_end) ? maxblocks - (first - range_first) : next - first;
   }
-  u64 s = 0, Ws = 0;
-  bool Ws_valid = true;  // W(0) = 0
+  u64 s = 0, Ws = prefix[0];
+  bool Ws_valid = true;  // W(0) = 0 (or the W base of a share)
   u32 k = 0;
   if (u_start > 0) {
     // speculative start (multi-GPU range plan): the first raw position x with W(x) >= u_start, i.e. where a
@@ -823,7 +827,23 @@ u32 crc32_device(Ctx& c, const u8* d_p, size_t n) {
 // spec_first < 0: exact plan of the whole input.  Otherwise only blocks [spec_first, spec_first+spec_count) are
 // walked, starting from the speculative boundary W(s) = spec_first * BS (see k_rle_blocks); plan.first_index
 // records the global index of h_blocks[0] and plan.total_guess = ceil(W(N) / BS).
-void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, long long spec_first, size_t spec_count, bool tiles_only) {
+// length of the run the buffer starts with (in bytes, not reduced): tiles of one and the same byte, then the lead of
+// the first tile that is not
+__global__ void k_share_lead(const TileSum* __restrict__ sums, u64 ntiles, u64* __restrict__ out) {
+  if (threadIdx.x) return;
+  u64 lead = 0;
+  const u8 fc = sums[0].fc;
+  for (u64 t = 0; t < ntiles; t++) {
+    const TileSum s = sums[t];
+    if (s.fc != fc) break;
+    lead += s.lead;
+    if (!s.allsame) break;
+  }
+  *out = lead;
+}
+
+void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, long long spec_first, size_t spec_count, bool tiles_only,
+                  u64 st0, u64 W0, u64* agg_state) {
   crc_setup();
   plan.nblocks = 0;
   plan.h_blocks.clear();
@@ -835,33 +855,41 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
   if (plan.ntiles != ntiles || !plan.tile_prefix.p) {
     plan.ntiles = ntiles;
     DBuf<TileSum> sums(c, ntiles);
+    DBuf<u64> dagg(c, 4);
     plan.tile_carry.alloc(c, ntiles);
     plan.tile_prefix.alloc(c, ntiles + 1);
     k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums);
     KLAUNCH(c); KCHECK();
     static const bool force_groups = getenv("B2_RLE_SCAN_GROUPS") != nullptr;  // test hook: multi-CTA scan on small inputs too
     if (ntiles <= 4 * RG_TILES && !force_groups) {
-      k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix);
+      k_rle_scan<<<1, RS_THREADS, 0, c.stream>>>(sums, ntiles, n, plan.tile_carry, plan.tile_prefix, st0, W0, dagg);
       KLAUNCH(c); KCHECK();
     } else {
       const u32 ng = (u32)((ntiles + RG_TILES - 1) / RG_TILES);
       DBuf<u64> gagg(c, ng), gstart(c, ng + 1), gsum(c, ng), gbase(c, ng + 1);
       k_rle_scan_g1<<<ng, RG_THREADS, 0, c.stream>>>(sums, ntiles, n, gagg);
       KLAUNCH(c); KCHECK();
-      k_rle_scan_groups<true><<<1, RS_THREADS, 0, c.stream>>>(gagg, ng, gstart);
+      k_rle_scan_groups<true><<<1, RS_THREADS, 0, c.stream>>>(gagg, ng, gstart, st0, dagg);
       KLAUNCH(c); KCHECK();
       k_rle_scan_g3<<<ng, RG_THREADS, 0, c.stream>>>(sums, ntiles, n, gstart, plan.tile_carry, plan.tile_prefix, gsum);
       KLAUNCH(c); KCHECK();
-      k_rle_scan_groups<false><<<1, RS_THREADS, 0, c.stream>>>(gsum, ng, gbase);
+      k_rle_scan_groups<false><<<1, RS_THREADS, 0, c.stream>>>(gsum, ng, gbase, W0, nullptr);
       KLAUNCH(c); KCHECK();
       k_rle_scan_g5<<<ng, RG_THREADS, 0, c.stream>>>(ntiles, gbase, ng, plan.tile_prefix);
       KLAUNCH(c); KCHECK();
+    }
+    if (agg_state) {
+      // share summary for the multi-GPU planner: aggregate run state, length of the leading run, (W total follows below)
+      k_share_lead<<<1, 32, 0, c.stream>>>(sums, ntiles, dagg.p + 1);
+      KLAUNCH(c); KCHECK();
+      c.to_host(agg_state, dagg, 16);
     }
   }
   u64 wtotal = 0;
   c.to_host(&wtotal, plan.tile_prefix.p + ntiles, 8);
   c.sync();
   plan.total_guess = (size_t)((wtotal + BS - 1) / BS);
+  plan.w_total = wtotal;
   if (tiles_only) return;
   u32 maxblocks = (u32)(n / ((u64)BS * 4 / 5) + 2);
   u64 u_start = 0;
@@ -912,7 +940,7 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
   if (nb) c.to_host(plan.h_blocks.data(), plan.blocks, sizeof(BlkInfo) * nb);
   c.sync();
 }
-void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) { rle1_plan_ex(c, d_in, n, level, plan, -1, 0, false); }
+void rle1_plan(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan) { rle1_plan_ex(c, d_in, n, level, plan, -1, 0, false, 0, 0, nullptr); }
 void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, size_t first, size_t count, u8* d_T, u32* d_n, u32* d_crc) {
   if (count == 0) return;
   std::vector<u64> tbase(count + 1), pbase(count + 1);

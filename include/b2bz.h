@@ -101,6 +101,17 @@ int b2_bzip2_plan(const void* d_in, size_t n, int level, size_t* total_blocks);
  * (compressjs_b200/sharded.py does); otherwise fall back to b2_bzip2_plan.  The plan is cached for the next
  * b2_bzip2_encode_range_dev on the same buffer. */
 int b2_bzip2_plan_spec(const void* d_in, size_t n, int level, int rank, int world, uint64_t* info);
+/* Sharded input: every rank holds only a contiguous share of the input (followed by a halo: the first bytes of the
+ * next share, so that a block that starts in the share can be finished).
+ * summary[0..3] = {aggregate RLE1 run state of the share (packed, opaque), length of its leading run, RLE1 bytes of the
+ * share when no run enters it, share length}; the host layer combines the summaries of all ranks in order
+ * (compressjs_b200/sharded.py: share_plan_inputs) into the run state / RLE1 output in front of every share. */
+int b2_bzip2_share_summary(const void* d_share, size_t n, uint64_t* summary);
+/* Cuts blocks [first, first+count) of the whole input inside the buffer d_buf[0, n) = share + halo, given the run state
+ * and RLE1 output in front of it.  Speculative like b2_bzip2_plan_spec (same checks by the caller); info[0..5] = raw
+ * start, raw end (offsets inside d_buf), first, planned, blocks cut, RLE1 output up to the end of the buffer.  The plan
+ * is cached for the next b2_bzip2_encode_range_dev(d_buf, n, level, first, count, ...). */
+int b2_bzip2_plan_share(const void* d_buf, size_t n, int level, uint64_t state_in, uint64_t w_in, size_t first, size_t count, uint64_t* info);
 /* dst := the first nbits of src moved to start at bit `phase` (0..7, MSB first), zero outside; dst must hold
  * ceil((phase+nbits)/32)*4 bytes and may not overlap src.  Used to align a fragment to its global bit offset. */
 int b2_bitshift_dev(const void* d_src, uint64_t nbits, int phase, void* d_dst);

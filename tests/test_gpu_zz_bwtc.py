@@ -19,6 +19,19 @@ def test_bwtc_samples(name, level):
     assert BWTC.decompressFile(z) == d
 
 
+@pytest.mark.parametrize("name", ["sample4", "sample5"])
+def test_bwtc_900k_blocks(name):
+    """Full 900 000-byte blocks at -9 (sample5: 900000/900000/330640, the README size 272 997 B)."""
+    from compressjs_b200 import BWTC
+    d = T.fixture(name + ".ref")
+    z = BWTC.compressFile(d, None, 9)
+    assert z == O.bwtc_compress(d, 9)
+    gold = T.golden().get("bwtc_%s_-9" % name)
+    if gold:
+        assert len(z) == gold["size"]
+    assert BWTC.decompressFile(z) == d
+
+
 @pytest.mark.parametrize("data", [b"", b"a", b"ab", b"\x00" * 5000, bytes(range(256)) * 9])
 def test_bwtc_edges(data):
     from compressjs_b200 import BWTC
