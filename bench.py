@@ -357,10 +357,16 @@ def main():
 
     shard = args.mb << 20
     nbytes = shard * world
-    # weak scaling: the job is ONE stream of world x shard bytes; every rank holds the input (the block
-    # cutting scan needs it), encodes a contiguous range of blocks, and the fragments are gathered over NCCL.
-    host = np.concatenate([gen_ascii(shard, SEED + r) for r in range(world)]) if world > 1 else gen_ascii(shard, SEED)
-    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    HALO = 4 << 20
+    # weak scaling: the job is ONE stream of world x shard bytes.  One GPU: the whole input.  Several: every rank
+    # holds (and uploads) only its own share plus a halo of the next share; the ranks exchange share summaries, cut
+    # and encode their blocks, and the fragments travel over NCCL straight into place on rank 0 (sharded.py).
+    if world == 1:
+        host = gen_ascii(shard, SEED)
+    else:
+        own = gen_ascii(shard, SEED + rank)
+        host = np.concatenate([own, gen_ascii(shard, SEED + rank + 1)[:HALO]]) if rank + 1 < world else own
+    pinned = torch.empty(host.size, dtype=torch.uint8, pin_memory=True)
     pinned.numpy()[:] = host
     d_in = pinned.cuda(non_blocking=False)
     cap = L.b2_bzip2_bound(nbytes)
@@ -374,7 +380,7 @@ def main():
             _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
             state["comp"] = out_n.value
             return _native.stats()
-        out = SH.compress_file_sharded(d_in, LEVEL)
+        out = SH.compress_shares(d_in, shard, LEVEL)
         st = _native.stats()
         if out is not None:
             state["comp"] = out.numel()
@@ -392,16 +398,16 @@ def main():
                     raise SystemExit("e2e stream differs from the HBM-resident stream")
             L.b2_free(out)
             return st, n.value
-        d = pinned.cuda(non_blocking=True)          # H2D of the step's input
+        if state.get("shm") is None:                # once: a pinned host buffer mapped by all ranks of the box
+            state["shm"] = SH.SharedHostBuffer(cap)
+        d = pinned.cuda(non_blocking=True)          # H2D of the step's input: the own share + halo only
         torch.cuda.current_stream().synchronize()   # the library works on its own stream
-        out = SH.compress_file_sharded(d, LEVEL)
-        nn = 0
-        if out is not None:
-            nn = out.numel()
-            if state.get("pinned_out") is None or state["pinned_out"].numel() < nn:
-                state["pinned_out"] = torch.empty(nn + (nn >> 3), dtype=torch.uint8, pin_memory=True)
-            state["pinned_out"][:nn].copy_(out, non_blocking=True)   # D2H of the step's result into pinned memory
-            torch.cuda.current_stream().synchronize()
+        # every rank downloads its fragment over its own PCIe link straight into place in the shared host buffer
+        nn = SH.compress_shares(d, shard, LEVEL, host_out=state["shm"].tensor) or 0
+        if check and rank == 0:
+            got = state["shm"].tensor[:nn].cuda()
+            if nn != state["comp"] or not torch.equal(got, state["out"][:nn]):
+                raise SystemExit("e2e stream (host buffer) differs from the HBM-resident stream")
         return _native.stats(), nn
 
     def barrier():
@@ -444,13 +450,17 @@ def main():
 
     # ---- multi-rank parity: the stream assembled from the ranks' fragments == the one-GPU stream of the same input ----
     sharded_parity = None
+    d_full = None
     if world > 1 and rank == 0:
+        full = np.concatenate([gen_ascii(shard, SEED + r) for r in range(world)])
+        d_full = torch.from_numpy(full).cuda()
+        del full
         one = torch.empty(cap, dtype=torch.uint8, device="cuda")
-        _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, one.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
+        _check(L.b2_bzip2_compress_dev(d_full.data_ptr(), nbytes, LEVEL, one.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
         same = out_n.value == state["out"].numel() and bool(torch.equal(one[: out_n.value], state["out"]))
         sharded_parity = {"ok": same, "bytes": int(out_n.value),
                           "sha256_16": hashlib.sha256(state["out"].cpu().numpy().tobytes()).hexdigest()[:16],
-                          "what": "%d-rank NCCL stream vs b2_bzip2_compress_dev of the whole input on rank 0" % world}
+                          "what": "%d-rank stream (sharded input, fragments placed over NCCL) vs b2_bzip2_compress_dev of the whole input on rank 0" % world}
         del one
         if not same:
             print(json.dumps({"error": "sharded stream differs from the single-GPU stream", "sharded_parity": sharded_parity}))
@@ -471,6 +481,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_wall = t.item()
 
+    # ---- several GPUs: sharded decode of the stream just produced (BASELINE configs[4] style: every rank holds the
+    # compressed stream, decodes its share of the blocks, the decoded shards meet on rank 0) ----
+    sharded_decode = None
+    if world > 1:
+        szt = torch.tensor([state["comp"] if rank == 0 else 0], dtype=torch.int64, device="cuda")
+        dist.broadcast(szt, 0)
+        comp = int(szt.item())
+        d_comp = state["out"][:comp].contiguous() if rank == 0 else torch.empty(comp, dtype=torch.uint8, device="cuda")
+        dist.broadcast(d_comp, 0)
+        dsteps = max(1, min(args.steps, 3))
+        res = SH.decompress_file_sharded(d_comp)      # warm-up + round trip
+        ok = None
+        if rank == 0:
+            ok = res.numel() == nbytes and bool(torch.equal(res, d_full))
+        del res
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(dsteps):
+            res = SH.decompress_file_sharded(d_comp)
+            del res
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sharded_decode = {"metric": "bzip2_-9_decode_MBps", "value": nbytes * dsteps / (tt.item() / 1e3) / 1e6, "unit": "MB/s", "steps": dsteps,
+                          "ms_per_step": tt.item() / dsteps, "roundtrip_ok": ok, "compressed_bytes": comp,
+                          "what": "decompress_file_sharded: %d ranks, %d MiB raw per rank, decoded stream assembled on rank 0" % (world, args.mb)}
+        del d_comp
     if rank == 0:
         total_raw = nbytes
         value = total_raw * args.steps / (dev_ms_max / 1e3) / 1e6
@@ -515,9 +554,9 @@ def main():
                        "level": LEVEL, "bytes_per_gpu": shard, "total_bytes": nbytes, "blocks_per_gpu": int(agg["blocks"] // max(args.steps, 1)),
                        "l2": "inputs (%d MiB) larger than L2 (126 MB); no flush needed" % args.mb, "bwt_batch_blocks": int(os.environ.get("B2_BWT_BATCH", "296")),
                        "compressed_bytes": comp_bytes, "wall_ms_per_step": wall_ms_max / args.steps},
-            "e2e": {"value": total_raw * e2e_steps / e2e_wall / 1e6, "unit": "MB/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": e2e_comp,
+            "e2e": {"value": total_raw * e2e_steps / e2e_wall / 1e6, "unit": "MB/s", "h2d_bytes_per_step": nbytes if world == 1 else nbytes + (world - 1) * HALO, "d2h_bytes_per_step": e2e_comp,
                     "steps": e2e_steps, "api": "b2_bzip2_compress (host pinned in, library-pinned out; upload in 64 MiB chunks and download per batch overlapped with the encode)" if world == 1 else
-                    "sharded.compress_file_sharded (pinned host in on every rank, stream gathered to rank 0 over NCCL, D2H on rank 0)"},
+                    "sharded.compress_shares (every rank uploads its share + a 4 MiB halo from pinned host memory and downloads its fragment into its place in one page-locked host buffer shared by the ranks)"},
             "gpu_launches": int(agg["kernel_launches"]),
             "roofline": roof,
             "stages_ms_per_step": {k: agg[k] / args.steps for k in ("ms_rle1", "ms_bwt", "ms_mtf", "ms_huff", "ms_pack", "ms_radix", "ms_msd_scatter", "ms_msd_bucket")},
@@ -526,6 +565,7 @@ def main():
         if world > 1:
             line["sharded_phases_ms_last_step_rank0"] = {k: round(v, 2) for k, v in SH.PHASES.items()}
             line["sharded_parity"] = sharded_parity
+            line["decode"] = sharded_decode
         if world == 1:
             if not args.no_cpu:
                 line["parity"] = prefix_parity(L, _native, host, d_out, comp_bytes, trace, 32, max(1, min(host_cores(), 32)))
@@ -561,6 +601,8 @@ def main():
             line["cpu_baseline"]["libbz2_compressed_bytes"] = len(zl)
             line["cpu_baseline"]["reference_js_published_MBps"] = 0.0936   # README.md:70 of the reference (enwik8, node 0.8, 2013 laptop)
         print(json.dumps(line))
+    if state.get("shm") is not None:
+        state["shm"].close()
     if world > 1:
         dist.destroy_process_group()
 

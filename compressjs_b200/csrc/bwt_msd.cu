@@ -175,16 +175,62 @@ struct MsdBucketSmem {
   __align__(16) u64 buf[2][MB_BUF];
   __align__(16) u32 cnt[MB_CELLS / 2];  // two 16-bit cell counters per word
   __align__(16) u8 outb[MB_BUF + 16];   // the bucket's slice of the BWT column, at the alignment (mod 16) it has in global memory
-  u32 multi[MB_BUF / 2];                // cells holding two or more records: first row | size << 16
-  u32 ws[MB_THREADS / 32 + 1];
+  u32 multi[MB_BUF / 2];                // queued cells: four lists (2, 3, 4 records: first row; more: first row | size << 16)
+  __align__(8) u64 ws64[MB_THREADS / 32 + 1];
   __align__(8) u64 bar[2];
   u32 w[2], M[2], off[2], st[2];
-  u32 nmulti;
+  u32 nl[4];  // cells of 2, 3, 4 and of more records
 };
 
 static_assert(sizeof(MsdBucketSmem) <= 227 * 1024, "bucket sort state must fit the 227 KiB of shared memory a CTA can have");
 
 __device__ __forceinline__ u32 cell_of(u32 key) { return key >> (32 - MB_CELL_BITS); }
+
+// K records of one cell, starting at row `lo` of the bucket: order them (odd-even transposition network), write their
+// bytes to the column slice, report runs of equal keys (rotations that share their first 5 bytes) to the resolver
+// (bwt.cu k_resolve_direct).
+template <int K>
+__device__ __forceinline__ void small_cell(const u64* __restrict__ buf, u32 lo, u8* __restrict__ ob, u32 base, u32 urow, u32* __restrict__ pidx,
+                                           u32* __restrict__ tie_head, u32* __restrict__ tie_idx, u32* ctl) {
+  u64 v[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) v[i] = buf[lo + i];
+#pragma unroll
+  for (int round = 0; round < K; round++) {
+#pragma unroll
+    for (int i = round & 1; i + 1 < K; i += 2) {
+      const u64 a = v[i], b = v[i + 1];
+      const bool sw = a > b;
+      v[i] = sw ? b : a;
+      v[i + 1] = sw ? a : b;
+    }
+  }
+  bool any_tie = false;
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    const u32 lw = (u32)v[i];
+    ob[lo + i] = (u8)(lw >> SEG_SHIFT);
+    if ((lw & SEG_MASK) == 0) pidx[base >> SEG_SHIFT] = urow + lo + i;
+    if (i + 1 < K) any_tie |= (u32)(v[i] >> 32) == (u32)(v[i + 1] >> 32);
+  }
+  if (any_tie) {
+    int run0 = 0;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      if (i + 1 == K || (u32)(v[i + 1] >> 32) != (u32)(v[i] >> 32)) {
+        const int run = i + 1 - run0;
+        if (run > 1) {
+          u32 t = atomicAdd(&ctl[0], (u32)run);
+          const u32 head = base | (urow + lo + run0);
+#pragma unroll
+          for (int z = 0; z < K; z++)
+            if (z >= run0 && z <= i) { tie_head[t] = head; tie_idx[t] = base | ((u32)v[z] & SEG_MASK); t++; }
+        }
+        run0 = i + 1;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(MB_THREADS, 1)
 k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __restrict__ U, u32* __restrict__ pidx,
@@ -247,78 +293,81 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
       }
     }
     __syncthreads();
-    // ---- exclusive scan of the cell counts (each thread owns 8 words = 16 cells) ----
+    // ---- exclusive scan of the cell counts (each thread owns 8 words = 16 cells, two 16-bit counts per word, handled
+    // two at a time).  Cells of one record are flagged (bit 15 of their start): their record is final when it is
+    // scattered.  Cells of 2, 3, 4 and of more records are queued in four lists for the ordering passes below. ----
+    u8* ob = s.outb + (ust & 15u);
     {
       uint4* c4 = reinterpret_cast<uint4*>(s.cnt) + tid * 2;
       uint4 x0 = c4[0], x1 = c4[1];
       u32 wv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      u32 sum = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) sum += (wv[k] & 0xffffu) + (wv[k] >> 16);
-      u32 tot;
-      u32 run = block_excl_add<MB_THREADS, u32>(sum, s.ws, &tot);
+      // records | cells of 2 << 14 | cells of 3 << 27 | cells of 4 << 39 | larger cells << 51
+      u64 agg = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        const u32 lo = wv[k] & 0xffffu, hi = wv[k] >> 16;
-        wv[k] = run | ((run + lo) << 16);
-        run += lo + hi;
+        const u32 w = wv[k];
+        agg += (w & 0xffffu) + (w >> 16);
+        if (__vcmpgtu2(w, 0x00010001u)) {  // some cell of this pair holds more than one record (about one pair in five)
+          const u32 lo = w & 0xffffu, hi = w >> 16;
+          agg += ((u64)((lo == 2) + (hi == 2)) << 14) + ((u64)((lo == 3) + (hi == 3)) << 27) + ((u64)((lo == 4) + (hi == 4)) << 39) +
+                 ((u64)((lo > 4) + (hi > 4)) << 51);
+        }
+      }
+      u64 tot;
+      const u64 ex = block_excl_add<MB_THREADS, u64>(agg, s.ws64, &tot);
+      const u32 t2 = (u32)(tot >> 14) & 0x1fffu, t3 = (u32)(tot >> 27) & 0xfffu, t4 = (u32)(tot >> 39) & 0xfffu, tN = (u32)(tot >> 51);
+      if (tid == 0) { s.nl[0] = t2; s.nl[1] = t3; s.nl[2] = t4; s.nl[3] = tN; }
+      u32 run = (u32)ex & 0x3fffu;
+      u32 i2 = (u32)(ex >> 14) & 0x1fffu, i3 = t2 + ((u32)(ex >> 27) & 0xfffu), i4 = t2 + t3 + ((u32)(ex >> 39) & 0xfffu),
+          iN = t2 + t3 + t4 + (u32)(ex >> 51);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const u32 w = wv[k];
+        const u32 lo = w & 0xffffu, hi = w >> 16;
+        const u32 s0 = run, s1 = run + lo;
+        wv[k] = (s0 | (s1 << 16)) | (__vcmpeq2(w, 0x00010001u) & 0x80008000u);
+        run = s1 + hi;
+        if (__vcmpgtu2(w, 0x00010001u)) {
+          if (lo == 2) s.multi[i2++] = s0; else if (lo == 3) s.multi[i3++] = s0; else if (lo == 4) s.multi[i4++] = s0;
+          else if (lo > 4) s.multi[iN++] = s0 | (lo << 16);
+          if (hi == 2) s.multi[i2++] = s1; else if (hi == 3) s.multi[i3++] = s1; else if (hi == 4) s.multi[i4++] = s1;
+          else if (hi > 4) s.multi[iN++] = s1 | (hi << 16);
+        }
       }
       c4[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       c4[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
     }
     __syncthreads();
-    // ---- scatter in place (every record of the bucket sits in a register by now) ----
+    // ---- scatter (every record of the bucket sits in a register by now).  A record alone in its cell is final: its
+    // byte goes straight to the column slice; the others are stored in cell order for the ordering passes. ----
 #pragma unroll
     for (int k = 0; k < MB_ITEMS; k++) {
       const u32 p = tid + k * MB_THREADS;
       if (p < M) {
         const u32 c = cell_of((u32)(r[k] >> 32));
         const u32 sh = (c & 1u) * 16u;
-        const u32 old = atomicAdd(&s.cnt[c >> 1], 1u << sh);
-        buf[(old >> sh) & 0xffffu] = r[k];
-      }
-    }
-    __syncthreads();
-    // ---- cells in order: a single record is final, larger cells are queued ----
-    u8* ob = s.outb + (ust & 15u);
-    {
-      const uint4* c4 = reinterpret_cast<const uint4*>(s.cnt) + tid * 2;  // after the scatter: end of every cell
-      const uint4 x0 = c4[0], x1 = c4[1];
-      const u32 wv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      const u32 lo0 = tid ? (s.cnt[tid * 8 - 1] >> 16) : 0u;
-      u32 lo = lo0, nmul = 0;
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const u32 hi = (k & 1) ? (wv[k >> 1] >> 16) : (wv[k >> 1] & 0xffffu);
-        const u32 size = hi - lo;
-        if (size == 1) {
-          const u32 lw = (u32)buf[lo];
-          ob[lo] = (u8)(lw >> SEG_SHIFT);
-          if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + lo;
-        }
-        nmul += size > 1 ? 1u : 0u;
-        lo = hi;
-      }
-      // queue positions by a block scan (one shared counter would serialise a couple of thousand atomics per bucket)
-      u32 tot;
-      u32 at = block_excl_add<MB_THREADS, u32>(nmul, s.ws, &tot);
-      if (tid == 0) s.nmulti = tot;
-      if (nmul) {
-        lo = lo0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-          const u32 hi = (k & 1) ? (wv[k >> 1] >> 16) : (wv[k >> 1] & 0xffffu);
-          if (hi - lo > 1) s.multi[at++] = lo | ((hi - lo) << 16);
-          lo = hi;
+        const u32 half = (atomicAdd(&s.cnt[c >> 1], 1u << sh) >> sh) & 0xffffu;
+        const u32 pos = half & 0x7fffu;
+        if (half & 0x8000u) {
+          const u32 lw = (u32)r[k];
+          ob[pos] = (u8)(lw >> SEG_SHIFT);
+          if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + pos;
+        } else {
+          buf[pos] = r[k];
         }
       }
     }
     __syncthreads();
-    // ---- one thread per queued cell: order its few records in place, emit, report equal keys ----
+    // ---- cells of 2, 3 and 4 records: one thread per cell, a fixed compare-exchange network in registers ----
     {
-      const u32 nm = s.nmulti;
-      for (u32 j = tid; j < nm; j += MB_THREADS) {
-        const u32 mm = s.multi[j], lo = mm & 0xffffu, size = mm >> 16;
+      const u32 n2 = s.nl[0], n3 = s.nl[1], n4 = s.nl[2], nN = s.nl[3];
+      const u32 base = (blockb << SEG_SHIFT), urow = ust;
+      for (u32 j = tid; j < n2; j += MB_THREADS) small_cell<2>(buf, s.multi[j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
+      for (u32 j = tid; j < n3; j += MB_THREADS) small_cell<3>(buf, s.multi[n2 + j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
+      for (u32 j = tid; j < n4; j += MB_THREADS) small_cell<4>(buf, s.multi[n2 + n3 + j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
+      // ---- larger cells (a handful per bucket on uniform data): one thread orders the cell in place ----
+      for (u32 j = tid; j < nN; j += MB_THREADS) {
+        const u32 mm = s.multi[n2 + n3 + n4 + j], lo = mm & 0xffffu, size = mm >> 16;
         if (size > MB_MAXCELL) { atomicOr(&ctl[1], 1u); continue; }  // far from uniform after all: the LSD path redoes the batch
         u64* cb = buf + lo;
         for (u32 a = 1; a < size; a++) {
@@ -341,10 +390,9 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
           if (q + 1 == size || (u32)(cb[q + 1] >> 32) != (u32)(rq >> 32)) {
             const u32 run = q + 1 - run0;
             if (run > 1) {
-              // rotations that share their first 5 bytes: hand the group to the resolver (bwt.cu k_resolve_direct)
               u32 t = atomicAdd(&ctl[0], run);
-              const u32 head = (blockb << SEG_SHIFT) | (ust + lo + run0);
-              for (u32 z = run0; z <= q; z++) { tie_head[t] = head; tie_idx[t] = (blockb << SEG_SHIFT) | ((u32)cb[z] & SEG_MASK); t++; }
+              const u32 head = base | (ust + lo + run0);
+              for (u32 z = run0; z <= q; z++) { tie_head[t] = head; tie_idx[t] = base | ((u32)cb[z] & SEG_MASK); t++; }
             }
             run0 = q + 1;
           }

@@ -64,6 +64,15 @@ static napi_value DecompressBlock(napi_env env, napi_callback_info info) {
   napi_value buf; napi_create_external_buffer(env, out_n, out, fin, nullptr, &buf);
   return buf;
 }
+// integer argument that must be a JS number; false (and B2_ERR_BAD_ARG thrown by the caller) otherwise
+static bool int_arg(napi_env env, napi_value v, int32_t* out) {
+  napi_valuetype ty;
+  if (napi_typeof(env, v, &ty) != napi_ok || ty != napi_number) return false;
+  return napi_get_value_int32(env, v, out) == napi_ok;
+}
+// n bytes must exist in both the source and the destination view
+static bool len_ok(int32_t n, size_t a, size_t b) { return n >= 0 && (size_t)n <= a && (size_t)n <= b; }
+
 // table(buffer, multistream) -> [[bitpos, size], ...]   (Bunzip.table, lib/Bzip2.js:508)
 static napi_value Table(napi_env env, napi_callback_info info) {
   size_t argc = 2; napi_value argv[2];
@@ -91,7 +100,7 @@ static napi_value Bwtransform2(napi_env env, napi_callback_info info) {
   napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
   const uint8_t *T, *U; size_t tn, un; int32_t n = 0;
   if (!buf_arg(env, argv[0], &T, &tn) || !buf_arg(env, argv[1], &U, &un)) return fail(env, B2_ERR_BAD_ARG);
-  napi_get_value_int32(env, argv[2], &n);
+  if (argc < 3 || !int_arg(env, argv[2], &n) || !len_ok(n, tn, un)) return fail(env, B2_ERR_BAD_ARG);
   int32_t p = b2_bwt_cyclic(T, (uint8_t*)U, n);
   if (p < 0) return fail(env, p);
   napi_value r; napi_create_int32(env, p, &r);
@@ -132,8 +141,7 @@ static napi_value Suffixsort(napi_env env, napi_callback_info info) {
   napi_typedarray_type ty; size_t len; void* sa; napi_value ab; size_t off;
   if (!buf_arg(env, argv[0], &T, &tn)) return fail(env, B2_ERR_BAD_ARG);
   if (napi_get_typedarray_info(env, argv[1], &ty, &len, &sa, &ab, &off) != napi_ok || ty != napi_int32_array) return fail(env, B2_ERR_BAD_ARG);
-  napi_get_value_int32(env, argv[2], &n);
-  if (n < 0 || (size_t)n > tn || (size_t)n > len) return fail(env, B2_ERR_BAD_ARG);
+  if (argc < 3 || !int_arg(env, argv[2], &n) || !len_ok(n, tn, len)) return fail(env, B2_ERR_BAD_ARG);
   int rc = b2_suffixsort(T, (int32_t*)sa, n);
   if (rc < 0) return fail(env, rc);
   napi_value r; napi_create_int32(env, 0, &r);
@@ -145,7 +153,7 @@ static napi_value Bwtransform(napi_env env, napi_callback_info info) {
   napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
   const uint8_t *T, *U; size_t tn, un; int32_t n = 0;
   if (!buf_arg(env, argv[0], &T, &tn) || !buf_arg(env, argv[1], &U, &un)) return fail(env, B2_ERR_BAD_ARG);
-  napi_get_value_int32(env, argv[2], &n);
+  if (argc < 3 || !int_arg(env, argv[2], &n) || !len_ok(n, tn, un)) return fail(env, B2_ERR_BAD_ARG);
   int32_t p = b2_bwt_sentinel(T, (uint8_t*)U, n);
   if (p < 0) return fail(env, p);
   napi_value r; napi_create_int32(env, p, &r);
@@ -157,8 +165,8 @@ static napi_value Unbwtransform(napi_env env, napi_callback_info info) {
   napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
   const uint8_t *T, *U; size_t tn, un; int32_t n = 0, pidx = 0;
   if (!buf_arg(env, argv[0], &T, &tn) || !buf_arg(env, argv[1], &U, &un)) return fail(env, B2_ERR_BAD_ARG);
-  napi_get_value_int32(env, argv[2], &n);
-  napi_get_value_int32(env, argv[3], &pidx);
+  if (argc < 4 || !int_arg(env, argv[2], &n) || !int_arg(env, argv[3], &pidx) || !len_ok(n, tn, un) || pidx < 0 || pidx > n)
+    return fail(env, B2_ERR_BAD_ARG);
   int rc = b2_bwt_inverse(T, (uint8_t*)U, n, pidx);
   if (rc < 0) return fail(env, rc);
   return nullptr;

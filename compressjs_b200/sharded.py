@@ -9,9 +9,16 @@ bitstream gather (north_star: "NCCL over NVLink only for the final bitstream gat
      (b2_bzip2_encode_range_dev)
   2. all_gather of (fragment bits, block count)   -> every rank knows its global bit offset
   3. the fragment is shifted to (global offset mod 8) so that only whole bytes move
-  4. gather of the byte fragments to rank 0 (NCCL), neighbouring fragments share at most one
-     byte, which is OR-ed; rank 0 adds "BZh"+level and the trailer (stream CRC folded over the
-     per-block CRCs in order, lib/Bzip2.js:917,925-927)
+  4. the byte fragments travel to rank 0 straight into their final place in the output buffer
+     (NCCL send/recv into offset views; no padded staging, no second copy); neighbouring fragments
+     share at most one byte, which is OR-ed from the two edge bytes that ride along with the sizes;
+     rank 0 adds "BZh"+level and the trailer (stream CRC combined from the per-rank folds of the
+     block CRCs, lib/Bzip2.js:917,925-927)
+
+With a sharded INPUT (compress_shares) a rank holds only its share of the bytes plus a halo: the ranks
+exchange tiny share summaries (RLE1 run state, leading run, RLE1 output) so that every rank knows the
+run state and the RLE1 output in front of its share, cuts its blocks speculatively and checks that the
+pieces chain up (b2_bzip2_share_summary / b2_bzip2_plan_share).
 
 The resulting stream is byte-identical to Bzip2.compressFile on one GPU (and to the oracle).
 The shifting / merging below is plain torch tensor code so that the same logic runs on CPU tensors
@@ -20,6 +27,8 @@ is injected.
 """
 import ctypes as C
 import time
+
+import numpy as np
 
 import torch
 import torch.distributed as dist
@@ -121,6 +130,167 @@ def assemble(level, frags, bits, crcs_per_rank, device):
     return out
 
 
+def rotl32(v, k):
+    k %= 32
+    return ((v << k) | (v >> (32 - k))) & 0xFFFFFFFF if k else v & 0xFFFFFFFF
+
+
+class SharedHostBuffer:
+    """A page-locked host buffer that all ranks of one box map (POSIX shared memory, registered with CUDA in every
+    process): every GPU downloads its fragment over its own PCIe link straight to its final place in the stream."""
+
+    def __init__(self, nbytes, group=None):
+        from multiprocessing import shared_memory, resource_tracker
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        names = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=max(int(nbytes), 4096))
+            names = [self.shm.name]
+        if dist.is_initialized():
+            dist.broadcast_object_list(names, src=0, group=group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=names[0])
+            try:  # only the creator unlinks the segment
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.owner = rank == 0
+        self.tensor = torch.frombuffer(self.shm.buf, dtype=torch.uint8)
+        self.registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.tensor.numel(), 0)
+            self.registered = int(rc) == 0
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.registered = False
+        self.tensor = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+def place_fragments(frag, nbits, count, crcs, level, device, group=None, host_out=None):
+    """Every rank contributes a fragment (uint8 tensor starting at bit 0, nbits long) with `count` blocks and their
+    CRCs; returns the complete .bz2 stream on rank 0 (None elsewhere).  The interior bytes of every fragment are
+    received directly at their final byte offset of the output.  With host_out (a SharedHostBuffer's tensor, the same
+    memory on every rank) the stream is assembled in host memory instead: every rank downloads its own fragment into
+    place and rank 0 gets the stream's length back."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    t0 = time.perf_counter()
+    if world == 1:
+        return assemble(level, [frag], [nbits], [crcs], device)
+    # 1. sizes, block counts and the fold of the own block CRCs (lib/Bzip2.js:917 is linear: folds combine by rotation)
+    mine = torch.tensor([nbits, count, fold_stream_crc(crcs)], dtype=torch.int64, device=device)
+    allv = [torch.zeros(3, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(allv, mine, group=group)
+    meta = [[int(x) for x in v.tolist()] for v in allv]
+    bits = [m[0] for m in meta]
+    offs, o = [], 32
+    for b in bits:
+        offs.append(o)
+        o += b
+    total_bits = o + 80
+    phase = offs[rank] % 8
+    t0 = _tick("allgather_sizes", t0)
+    shifted = shift_right_bits(frag, nbits, phase)
+    nb = (phase + nbits + 7) // 8 if nbits else 0
+    t0 = _tick("shift", t0)
+    # 2. the two edge bytes of every fragment (they may share their byte with a neighbour)
+    eb = torch.zeros(2, dtype=torch.uint8, device=device)
+    if nb:
+        eb[0] = shifted[0]
+        eb[1] = shifted[nb - 1]
+    alle = [torch.zeros(2, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(alle, eb, group=group)
+    nbs = [((offs[r] % 8) + bits[r] + 7) // 8 if bits[r] else 0 for r in range(world)]
+    if host_out is not None:
+        # 3'. interiors: every GPU writes its own piece of the host buffer (parallel PCIe links), then a barrier
+        if nb > 2:
+            b0 = offs[rank] // 8
+            host_out[b0 + 1: b0 + nb - 1].copy_(shifted[1: nb - 1], non_blocking=True)
+            if shifted.is_cuda:
+                torch.cuda.current_stream().synchronize()
+        dist.barrier(group=group)
+        t0 = _tick("d2h_place", t0)
+        if rank != 0:
+            return None
+        hb = host_out.numpy()
+        for r in range(world):
+            if nbs[r]:
+                b0 = offs[r] // 8
+                e0, e1 = int(alle[r][0]), int(alle[r][1])
+                if r == 0 or (offs[r] % 8) == 0:
+                    hb[b0] = e0
+                else:
+                    hb[b0] |= e0
+                if nbs[r] > 1:
+                    hb[b0 + nbs[r] - 1] = e1
+        scrc = 0
+        for m in meta:
+            scrc = rotl32(scrc, m[1]) ^ m[2]
+        b0t, tb = trailer_bytes(o, scrc)
+        first_shared = (o % 8) != 0
+        for k, v in enumerate(tb):
+            if k == 0 and first_shared:
+                hb[b0t] |= v
+            else:
+                hb[b0t + k] = v
+        hb[:4] = np.frombuffer(b"BZh" + bytes([0x30 + level]), dtype=np.uint8)
+        _tick("edges_trailer", t0)
+        return (total_bits + 7) // 8
+    # 3. interiors: point to point into the output
+    ops, out = [], None
+    if rank == 0:
+        nbytes_out = (total_bits + 7) // 8
+        out = torch.empty(nbytes_out, dtype=torch.uint8, device=device)
+        for r in range(1, world):
+            if nbs[r] > 2:
+                b0 = offs[r] // 8
+                ops.append(dist.P2POp(dist.irecv, out[b0 + 1: b0 + nbs[r] - 1], r, group))
+        if nbs[0] > 2:
+            b0 = offs[0] // 8
+            out[b0 + 1: b0 + nbs[0] - 1] = shifted[1: nbs[0] - 1]
+    elif nb > 2:
+        ops.append(dist.P2POp(dist.isend, shifted[1: nb - 1].contiguous(), 0, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    t0 = _tick("p2p_place", t0)
+    if rank != 0:
+        return None
+    # 4. header, edge bytes, trailer
+    edge = {}
+    for r in range(world):
+        if nbs[r]:
+            b0 = offs[r] // 8
+            e0, e1 = int(alle[r][0]), int(alle[r][1])
+            edge[b0] = edge.get(b0, 0) | e0
+            edge[b0 + nbs[r] - 1] = edge.get(b0 + nbs[r] - 1, 0) | e1
+    scrc = 0
+    for m in meta:
+        scrc = rotl32(scrc, m[1]) ^ m[2]
+    b0t, tb = trailer_bytes(o, scrc)
+    tail = {}
+    for k, v in enumerate(tb):
+        tail[b0t + k] = v
+    fix = dict(tail)
+    for k, v in edge.items():
+        if k >= 4:
+            fix[k] = fix.get(k, 0) | v
+    hdr = list(b"BZh" + bytes([0x30 + level]))
+    idx = torch.tensor(list(range(4)) + list(fix.keys()), dtype=torch.int64, device=device)
+    val = torch.tensor(hdr + list(fix.values()), dtype=torch.uint8, device=device)
+    out[idx] = val
+    _tick("edges_trailer", t0)
+    return out
+
+
 def compress_sharded(encode_range, nblocks, level, device, group=None):
     """encode_range(first, count) -> (uint8 tensor fragment starting at bit 0, nbits, [block crcs]).
     Returns the complete .bz2 stream as a uint8 tensor on rank 0 (None elsewhere)."""
@@ -129,44 +299,8 @@ def compress_sharded(encode_range, nblocks, level, device, group=None):
     first, count = block_range(nblocks, rank, world)
     t0 = time.perf_counter()
     frag, nbits, crcs = encode_range(first, count)
-    t0 = _tick("encode_range", t0)
-    if world == 1:
-        return assemble(level, [frag], [nbits], [crcs], device)
-    # 2. everybody learns every fragment's size
-    mine = torch.tensor([nbits, count], dtype=torch.int64, device=device)
-    allv = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(allv, mine, group=group)
-    bits = [int(v[0]) for v in allv]
-    counts = [int(v[1]) for v in allv]
-    off = 32 + sum(bits[:rank])
-    phase = off % 8
-    t0 = _tick("allgather_sizes", t0)
-    shifted = shift_right_bits(frag, nbits, phase)
-    t0 = _tick("shift", t0)
-    # 3. gather the (padded) byte fragments and the block CRCs on rank 0
-    maxlen = max((32 + sum(bits[:r])) % 8 + bits[r] + 7 for r in range(world)) // 8 + 1
-    maxcnt = max(counts + [1])
-    pad = torch.zeros(maxlen, dtype=torch.uint8, device=device)
-    pad[: shifted.numel()] = shifted
-    crct = torch.zeros(maxcnt, dtype=torch.int64, device=device)
-    if count:
-        crct[:count] = torch.tensor([int(c) for c in crcs], dtype=torch.int64, device=device)
-    if rank == 0:
-        glist = [torch.empty(maxlen, dtype=torch.uint8, device=device) for _ in range(world)]
-        clist = [torch.zeros(maxcnt, dtype=torch.int64, device=device) for _ in range(world)]
-        t0 = _tick("pad_alloc", t0)
-        dist.gather(pad, glist, dst=0, group=group)
-        dist.gather(crct, clist, dst=0, group=group)
-        t0 = _tick("nccl_gather", t0)
-        crcs_per_rank = [clist[r][: counts[r]].tolist() for r in range(world)]
-        out = assemble(level, glist, bits, crcs_per_rank, device)
-        _tick("assemble", t0)
-        return out
-    t0 = _tick("pad_alloc", t0)
-    dist.gather(pad, None, dst=0, group=group)
-    dist.gather(crct, None, dst=0, group=group)
-    _tick("nccl_gather", t0)
-    return None
+    _tick("encode_range", t0)
+    return place_fragments(frag, nbits, count, crcs, level, device, group)
 
 
 def _range_encoder(L, d_in, n, level):
@@ -251,6 +385,134 @@ def compress_file_sharded(d_in, level=9, group=None):
     return compress_sharded(enc, nblocks, level, d_in.device, group)
 
 
+# ---- sharded input ---------------------------------------------------------------------------------
+# Host mirror of the RLE1 scan state of csrc/rle1.cu (rs_make / rs_combine): bit 63 non-empty, bit 62 "one run",
+# first byte << 24, last byte << 16, trailing run length mod 255 << 8, length mod 255.
+def outfresh(c):
+    """RLE1 bytes produced by c bytes of one run consumed from a fresh state (lib/Bzip2.js:636-667)."""
+    q, r = divmod(c, 255)
+    return 5 * q + (r if r <= 3 else 5)
+
+
+def rs_combine(A, B):
+    if not (A >> 63):
+        return B
+    if not (B >> 63):
+        return A
+    a_all, b_all = (A >> 62) & 1, (B >> 62) & 1
+    a_fc, a_lc, a_tr, a_len = (A >> 24) & 255, (A >> 16) & 255, (A >> 8) & 255, A & 255
+    b_fc, b_lc, b_tr, b_len = (B >> 24) & 255, (B >> 16) & 255, (B >> 8) & 255, B & 255
+    join = a_lc == b_fc
+    trail = (a_tr + b_len) % 255 if (b_all and join) else b_tr
+    return (1 << 63) | ((a_all & b_all & int(join)) << 62) | (a_fc << 24) | (b_lc << 16) | (trail << 8) | ((a_len + b_len) % 255)
+
+
+def share_plan_inputs(summaries, level):
+    """summaries[r] = (state, lead, w_fresh, n) of rank r's share (b2_bzip2_share_summary), in rank order.
+    Returns ([(state_in, w_in, first, count, raw_offset)] per rank, total blocks, total RLE1 bytes).
+    A block belongs to the rank in whose share it starts: block k starts behind the byte that completes k * blockSize
+    RLE1 bytes (if no run-phase slip happened before it -- the ranks verify that afterwards)."""
+    BS = level * 100000 - 19
+    st, W, g = 0, 0, 0
+    ins = []
+    for (state, lead, w_fresh, n) in summaries:
+        ins.append((st, W, g))
+        if n:
+            c = ((st >> 8) & 255) if (st >> 63) and ((st >> 16) & 255) == ((state >> 24) & 255) else 0
+            W += outfresh(c + lead) - outfresh(c) + (w_fresh - outfresh(lead))
+            st = rs_combine(st, state)
+            g += n
+    total = (W + BS - 1) // BS
+
+    def before(w):      # blocks that start at or before the raw position whose RLE1 prefix is w
+        return 0 if w == 0 else min(total, w // BS + 1)
+    firsts = [before(w) for (_, w, _) in ins] + [total]
+    res = []
+    for r, (st_in, w_in, g0) in enumerate(ins):
+        n = summaries[r][3]
+        first = firsts[r]
+        count = (firsts[r + 1] - first) if n else 0
+        res.append((st_in, w_in, first, count, g0))
+    return res, total, W
+
+
+def _i64(v):
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _u64(v):
+    return v + (1 << 64) if v < 0 else v
+
+
+def compress_shares(d_buf, share_len, level=9, group=None, host_out=None):
+    """Whole-file bzip2 encode when every rank holds only ITS share of the input: d_buf = CUDA uint8 tensor with the
+    share (share_len bytes) followed by a halo (the first bytes of the next shares; empty on the last rank).  The shares
+    are contiguous in rank order.  Returns the stream on rank 0 (None elsewhere)."""
+    from . import _native
+    L = _native.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = d_buf.device
+    PHASES.clear()
+    t0 = time.perf_counter()
+    summ = (C.c_uint64 * 4)()
+    rc = L.b2_bzip2_share_summary(d_buf.data_ptr(), share_len, summ)
+    if rc:
+        raise RuntimeError("b2_bzip2_share_summary: " + _native.last_error())
+    mine = torch.tensor([_i64(int(v)) for v in summ], dtype=torch.int64, device=dev)
+    if world > 1:
+        allv = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allv, mine, group=group)
+    else:
+        allv = [mine]
+    summaries = [tuple(_u64(int(x)) for x in v.tolist()) for v in allv]
+    plan, total, _ = share_plan_inputs(summaries, level)
+    st_in, w_in, first, count, g0 = plan[rank]
+    n_total = sum(sm[3] for sm in summaries)
+    t0 = _tick("share_summaries", t0)
+    info = (C.c_uint64 * 6)()
+    rc = L.b2_bzip2_plan_share(d_buf.data_ptr(), d_buf.numel(), level, st_in, w_in, first, count, info)
+    if rc:
+        raise RuntimeError("b2_bzip2_plan_share: " + _native.last_error())
+    row = [int(v) for v in info]
+    mine = torch.tensor([row[0] + g0, row[1] + g0, row[2], row[3], row[4], total], dtype=torch.int64, device=dev)
+    if world > 1:
+        alli = [torch.zeros(6, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(alli, mine, group=group)
+    else:
+        alli = [mine]
+    infos = [tuple(int(x) for x in v.tolist()) for v in alli]
+    _tick("plan_share+verify", t0)
+    if not spec_plan_ok(infos, n_total):
+        # a run-phase slip or a block longer than the halo: every rank gets the whole input and the exact plan decides
+        PHASES["fallback_full_input"] = 1.0
+        lens = [sm[3] for sm in summaries]
+        parts = [torch.empty(max(ln, 1), dtype=torch.uint8, device=dev) for ln in lens]
+        maxlen = max(lens + [1])
+        pad = torch.zeros(maxlen, dtype=torch.uint8, device=dev)
+        pad[:share_len] = d_buf[:share_len]
+        if world > 1:
+            gl = [torch.empty(maxlen, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(gl, pad, group=group)
+            full = torch.cat([gl[r][: lens[r]] for r in range(world)])
+        else:
+            full = d_buf[:share_len]
+        del parts
+        return compress_file_sharded(full, level, group)
+    t0 = time.perf_counter()
+    enc = _range_encoder(L, d_buf, d_buf.numel(), level)
+    frag, nbits, crcs = enc(first, count)
+    _tick("encode_range", t0)
+    return place_fragments(frag, nbits, count, crcs, level, dev, group, host_out)
+
+
+def share_bounds(n, rank, world, halo):
+    """Equal contiguous shares of n bytes: (first byte, share length, bytes to hold = share + halo)."""
+    g0 = rank * n // world
+    g1 = (rank + 1) * n // world
+    return g0, g1 - g0, min(n, g1 + halo) - g0
+
+
 # ---- sharded decode -------------------------------------------------------------------------------
 def decode_shard_rows(L, d_in, rank, world):
     """Stage 1 on one rank: returns (info, rows) -- rows = int64 tensor [own candidates, 6] on the CPU."""
@@ -325,17 +587,19 @@ def decompress_file_sharded(d_in, multistream=False, group=None):
         raise Bzip2Error(code, res["msg"] if who == rank else "Data error")
     if world == 1:
         return out
-    # gather the shards on rank 0
-    maxlen = max(int(v[3]) for v in allv)
-    padb = torch.empty(max(maxlen, 1), dtype=torch.uint8, device=device)
-    padb[: out.numel()] = out
+    # the shards travel to rank 0 straight into their place in the decoded stream (send/recv into offset views)
+    ops, full = [], None
     if rank == 0:
-        glist = [torch.empty_like(padb) for _ in range(world)]
-        dist.gather(padb, glist, dst=0, group=group)
         full = torch.empty(int(allv[0][4]), dtype=torch.uint8, device=device)
-        for r in range(world):
+        o0, l0 = int(allv[0][2]), int(allv[0][3])
+        full[o0: o0 + l0] = out[:l0]
+        for r in range(1, world):
             o, ln = int(allv[r][2]), int(allv[r][3])
-            full[o: o + ln] = glist[r][:ln]
-        return full
-    dist.gather(padb, None, dst=0, group=group)
-    return None
+            if ln:
+                ops.append(dist.P2POp(dist.irecv, full[o: o + ln], r, group))
+    elif out.numel():
+        ops.append(dist.P2POp(dist.isend, out.contiguous(), 0, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return full

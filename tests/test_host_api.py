@@ -161,3 +161,18 @@ def test_bwtc_core_matches_oracle():
             ref = O.bwtc_compress(d, level)
             assert enc(d, level) == ref
             assert dec(ref, len(d)) == d
+
+
+def test_napi_addon_type_checks_against_the_napi_surface():
+    """The N-API addon cannot be built here (no node, no node-gyp); it must at least compile as C++ against the
+    declarations of the N-API calls it makes (tests/host/node_api_stub) and its build recipe must be present."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    napi = os.path.join(root, "compressjs_b200", "napi")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "host", "node_api_stub"),
+                        os.path.join(napi, "addon.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(os.path.join(napi, "binding.gyp"))
+    pkg = json.load(open(os.path.join(napi, "package.json")))
+    assert pkg["main"] == "index.js" and pkg["gypfile"] is True
