@@ -175,11 +175,11 @@ struct MsdBucketSmem {
   __align__(16) u64 buf[2][MB_BUF];
   __align__(16) u32 cnt[MB_CELLS / 2];  // two 16-bit cell counters per word
   __align__(16) u8 outb[MB_BUF + 16];   // the bucket's slice of the BWT column, at the alignment (mod 16) it has in global memory
-  u32 multi[MB_BUF / 2];                // queued cells: four lists (2, 3, 4 records: first row; more: first row | size << 16)
+  u32 multi[MB_BUF / 2];                // queued cells: 2 records from the front (first row), more from the back (first row | size << 16)
   __align__(8) u64 ws64[MB_THREADS / 32 + 1];
   __align__(8) u64 bar[2];
   u32 w[2], M[2], off[2], st[2];
-  u32 nl[4];  // cells of 2, 3, 4 and of more records
+  u32 nl[2];  // queued cells of 2 records / of more
 };
 
 static_assert(sizeof(MsdBucketSmem) <= 227 * 1024, "bucket sort state must fit the 227 KiB of shared memory a CTA can have");
@@ -294,48 +294,51 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
     }
     __syncthreads();
     // ---- exclusive scan of the cell counts (each thread owns 8 words = 16 cells, two 16-bit counts per word, handled
-    // two at a time).  Cells of one record are flagged (bit 15 of their start): their record is final when it is
-    // scattered.  Cells of 2, 3, 4 and of more records are queued in four lists for the ordering passes below. ----
+    // two at a time without branches).  Cells of one record are flagged (bit 15 of their start): their record is final
+    // when it is scattered.  Cells of 2 records and larger cells are queued in two lists for the ordering passes. ----
     u8* ob = s.outb + (ust & 15u);
     {
       uint4* c4 = reinterpret_cast<uint4*>(s.cnt) + tid * 2;
       uint4 x0 = c4[0], x1 = c4[1];
       u32 wv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      // records | cells of 2 << 14 | cells of 3 << 27 | cells of 4 << 39 | larger cells << 51
-      u64 agg = 0;
+      u32 sum = 0, c2 = 0, cN = 0, mm = 0;  // c2 / cN count per half; mm: bit k = even cell of word k queued, bit 16 + k = odd cell
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const u32 w = wv[k];
-        agg += (w & 0xffffu) + (w >> 16);
-        if (__vcmpgtu2(w, 0x00010001u)) {  // some cell of this pair holds more than one record (about one pair in five)
-          const u32 lo = w & 0xffffu, hi = w >> 16;
-          agg += ((u64)((lo == 2) + (hi == 2)) << 14) + ((u64)((lo == 3) + (hi == 3)) << 27) + ((u64)((lo == 4) + (hi == 4)) << 39) +
-                 ((u64)((lo > 4) + (hi > 4)) << 51);
-        }
+        sum += (w & 0xffffu) + (w >> 16);
+        const u32 e2 = __vcmpeq2(w, 0x00020002u) & 0x00010001u, g2 = __vcmpgtu2(w, 0x00020002u) & 0x00010001u;
+        c2 += e2;
+        cN += g2;
+        mm |= (e2 | g2) << k;
       }
+      const u32 n2 = (c2 & 0xffffu) + (c2 >> 16), nN = (cN & 0xffffu) + (cN >> 16);
       u64 tot;
-      const u64 ex = block_excl_add<MB_THREADS, u64>(agg, s.ws64, &tot);
-      const u32 t2 = (u32)(tot >> 14) & 0x1fffu, t3 = (u32)(tot >> 27) & 0xfffu, t4 = (u32)(tot >> 39) & 0xfffu, tN = (u32)(tot >> 51);
-      if (tid == 0) { s.nl[0] = t2; s.nl[1] = t3; s.nl[2] = t4; s.nl[3] = tN; }
+      const u64 ex = block_excl_add<MB_THREADS, u64>((u64)sum | ((u64)n2 << 14) | ((u64)nN << 28), s.ws64, &tot);
+      if (tid == 0) { s.nl[0] = (u32)(tot >> 14) & 0x3fffu; s.nl[1] = (u32)(tot >> 28); }
       u32 run = (u32)ex & 0x3fffu;
-      u32 i2 = (u32)(ex >> 14) & 0x1fffu, i3 = t2 + ((u32)(ex >> 27) & 0xfffu), i4 = t2 + t3 + ((u32)(ex >> 39) & 0xfffu),
-          iN = t2 + t3 + t4 + (u32)(ex >> 51);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const u32 w = wv[k];
-        const u32 lo = w & 0xffffu, hi = w >> 16;
-        const u32 s0 = run, s1 = run + lo;
-        wv[k] = (s0 | (s1 << 16)) | (__vcmpeq2(w, 0x00010001u) & 0x80008000u);
-        run = s1 + hi;
-        if (__vcmpgtu2(w, 0x00010001u)) {
-          if (lo == 2) s.multi[i2++] = s0; else if (lo == 3) s.multi[i3++] = s0; else if (lo == 4) s.multi[i4++] = s0;
-          else if (lo > 4) s.multi[iN++] = s0 | (lo << 16);
-          if (hi == 2) s.multi[i2++] = s1; else if (hi == 3) s.multi[i3++] = s1; else if (hi == 4) s.multi[i4++] = s1;
-          else if (hi > 4) s.multi[iN++] = s1 | (hi << 16);
-        }
+        const u32 s1 = run + (w & 0xffffu);
+        wv[k] = (run | (s1 << 16)) | (__vcmpeq2(w, 0x00010001u) & 0x80008000u);
+        run = s1 + (w >> 16);
       }
       c4[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       c4[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+      __syncwarp();  // the starts are read back below through a differently typed pointer: keep the order
+      // queue the own cells that hold two or more records (two on average); starts are read back from shared memory
+      u32 i2 = (u32)(ex >> 14) & 0x3fffu, iN = (u32)(ex >> 28);
+      const u16* cst = reinterpret_cast<const u16*>(s.cnt) + tid * 16;
+      while (mm) {
+        const u32 b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const u32 c = 2 * (b & 15u) + (b >> 4);          // cell inside the thread's 16
+        const u32 st = cst[c] & 0x3fffu;
+        const u32 nx = c == 15 ? run : (cst[c + 1] & 0x3fffu);
+        const u32 size = nx - st;
+        if (size == 2) s.multi[i2++] = st;
+        else s.multi[MB_BUF / 2 - 1 - iN++] = st | (size << 16);
+      }
     }
     __syncthreads();
     // ---- scatter (every record of the bucket sits in a register by now).  A record alone in its cell is final: its
@@ -358,16 +361,15 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
       }
     }
     __syncthreads();
-    // ---- cells of 2, 3 and 4 records: one thread per cell, a fixed compare-exchange network in registers ----
+    // ---- cells of 2 records, then the larger ones: one thread per cell; 2, 3 and 4 records go through a fixed
+    // compare-exchange network in registers, anything larger (a handful per bucket on uniform data) is ordered in place ----
     {
-      const u32 n2 = s.nl[0], n3 = s.nl[1], n4 = s.nl[2], nN = s.nl[3];
+      const u32 n2 = s.nl[0], nN = s.nl[1];
       const u32 base = (blockb << SEG_SHIFT), urow = ust;
-      for (u32 j = tid; j < n2; j += MB_THREADS) small_cell<2>(buf, s.multi[j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
-      for (u32 j = tid; j < n3; j += MB_THREADS) small_cell<3>(buf, s.multi[n2 + j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
-      for (u32 j = tid; j < n4; j += MB_THREADS) small_cell<4>(buf, s.multi[n2 + n3 + j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
-      // ---- larger cells (a handful per bucket on uniform data): one thread orders the cell in place ----
       for (u32 j = tid; j < nN; j += MB_THREADS) {
-        const u32 mm = s.multi[n2 + n3 + n4 + j], lo = mm & 0xffffu, size = mm >> 16;
+        const u32 mm = s.multi[MB_BUF / 2 - 1 - j], lo = mm & 0xffffu, size = mm >> 16;
+        if (size == 3) { small_cell<3>(buf, lo, ob, base, urow, pidx, tie_head, tie_idx, ctl); continue; }
+        if (size == 4) { small_cell<4>(buf, lo, ob, base, urow, pidx, tie_head, tie_idx, ctl); continue; }
         if (size > MB_MAXCELL) { atomicOr(&ctl[1], 1u); continue; }  // far from uniform after all: the LSD path redoes the batch
         u64* cb = buf + lo;
         for (u32 a = 1; a < size; a++) {
@@ -398,6 +400,7 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
           }
         }
       }
+      for (u32 j = tid; j < n2; j += MB_THREADS) small_cell<2>(buf, s.multi[j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
     }
     __syncthreads();
     // ---- the column slice goes out in 16-byte pieces ----
