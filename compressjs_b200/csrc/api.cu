@@ -396,7 +396,7 @@ int b2_bwtc_decompress(const uint8_t* in, size_t n, uint8_t** out, size_t* out_n
       size_t pos = 4; uint64_t fs = 0;
       if (n < 5 || memcmp(in, "bwtc", 4)) throw B2Error{B2_ERR_BAD_MAGIC, "Bad magic"};
       for (;;) {
-        if (pos >= n || pos > 14) throw B2Error{B2_ERR_DATA_ERROR, "truncated BWTC header"};
+        if (pos >= n || pos > 4 + 9) throw B2Error{B2_ERR_DATA_ERROR, "truncated or oversized BWTC header"};
         const uint32_t ch = in[pos++];
         if (ch & 0x80) { fs += ch & 0x7F; break; }
         fs = (fs + ch) * 128;

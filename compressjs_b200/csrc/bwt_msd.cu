@@ -175,11 +175,11 @@ struct MsdBucketSmem {
   __align__(16) u64 buf[2][MB_BUF];
   __align__(16) u32 cnt[MB_CELLS / 2];  // two 16-bit cell counters per word
   __align__(16) u8 outb[MB_BUF + 16];   // the bucket's slice of the BWT column, at the alignment (mod 16) it has in global memory
-  u32 multi[MB_BUF / 2];                // queued cells: 2 records from the front (first row), more from the back (first row | size << 16)
+  u32 multi[MB_BUF / 2];                // queued cells, four lists (2, 3, 4, more records): first row | size << 16
   __align__(8) u64 ws64[MB_THREADS / 32 + 1];
   __align__(8) u64 bar[2];
   u32 w[2], M[2], off[2], st[2];
-  u32 nl[2];  // queued cells of 2 records / of more
+  u32 nl[4];  // queued cells of 2, 3, 4 records / of more
 };
 
 static_assert(sizeof(MsdBucketSmem) <= 227 * 1024, "bucket sort state must fit the 227 KiB of shared memory a CTA can have");
@@ -230,6 +230,45 @@ __device__ __forceinline__ void small_cell(const u64* __restrict__ buf, u32 lo, 
       }
     }
   }
+}
+
+// A cell of `size` records handled by one warp: every record counts the records of the cell that sort before it (full
+// 64-bit compare: key, then the unique low word), which is its row; rows of equal keys are reported as tie runs by the
+// first record of the run.  rank: per-cell scratch (one u16 per record: row -> index of the record that landed there).
+__device__ __forceinline__ void big_cell(const u64* __restrict__ cb, u32 size, u32 lo, u8* __restrict__ ob, u32 base, u32 urow,
+                                         u32* __restrict__ pidx, u32* __restrict__ tie_head, u32* __restrict__ tie_idx, u32* ctl,
+                                         u16* __restrict__ rank) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 e0 = 0; e0 < size; e0 += 32) {
+    const u32 e = e0 + lane;
+    if (e < size) {
+      const u64 x = cb[e];
+      u32 less = 0;
+      for (u32 q = 0; q < size; q++) less += cb[q] < x ? 1u : 0u;
+      const u32 lw = (u32)x;
+      ob[lo + less] = (u8)(lw >> SEG_SHIFT);
+      if ((lw & SEG_MASK) == 0) pidx[base >> SEG_SHIFT] = urow + lo + less;
+      rank[less] = (u16)e;
+    }
+  }
+  __syncwarp();
+  // tie runs: walk the rows in order (lane 0 only: ties are rare and short)
+  if (lane == 0) {
+    u32 run0 = 0;
+    for (u32 r = 0; r < size; r++) {
+      const u32 kr = (u32)(cb[rank[r]] >> 32);
+      if (r + 1 == size || (u32)(cb[rank[r + 1]] >> 32) != kr) {
+        const u32 run = r + 1 - run0;
+        if (run > 1) {
+          u32 t = atomicAdd(&ctl[0], run);
+          const u32 head = base | (urow + lo + run0);
+          for (u32 z = run0; z <= r; z++) { tie_head[t] = head; tie_idx[t] = base | ((u32)cb[rank[z]] & SEG_MASK); t++; }
+        }
+        run0 = r + 1;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(MB_THREADS, 1)
@@ -294,40 +333,50 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
     }
     __syncthreads();
     // ---- exclusive scan of the cell counts (each thread owns 8 words = 16 cells, two 16-bit counts per word, handled
-    // two at a time without branches).  Cells of one record are flagged (bit 15 of their start): their record is final
-    // when it is scattered.  Cells of 2 records and larger cells are queued in two lists for the ordering passes. ----
+    // two at a time without branches: counts are < 2^14, so "count >= k" is bit 15 of count + (0x8000 - k) in both halves
+    // at once).  Cells of one record are flagged (bit 15 of their start): their record is final when it is scattered.
+    // Cells of 2, 3, 4 and of more records are queued in four lists for the ordering passes. ----
     u8* ob = s.outb + (ust & 15u);
     {
       uint4* c4 = reinterpret_cast<uint4*>(s.cnt) + tid * 2;
       uint4 x0 = c4[0], x1 = c4[1];
       u32 wv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      u32 sum = 0, c2 = 0, cN = 0, mm = 0;  // c2 / cN count per half; mm: bit k = even cell of word k queued, bit 16 + k = odd cell
+      const u32 H = 0x00010001u;
+      u32 sum = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, mm = 0;  // a_k: cells with >= k records, per half; mm: bit k / 16 + k = cell of word k queued
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const u32 w = wv[k];
         sum += (w & 0xffffu) + (w >> 16);
-        const u32 e2 = __vcmpeq2(w, 0x00020002u) & 0x00010001u, g2 = __vcmpgtu2(w, 0x00020002u) & 0x00010001u;
-        c2 += e2;
-        cN += g2;
-        mm |= (e2 | g2) << k;
+        const u32 ge2 = ((w + 0x7ffe7ffeu) >> 15) & H;
+        a2 += ge2;
+        a3 += ((w + 0x7ffd7ffdu) >> 15) & H;
+        a4 += ((w + 0x7ffc7ffcu) >> 15) & H;
+        a5 += ((w + 0x7ffb7ffbu) >> 15) & H;
+        mm |= ge2 << k;
       }
-      const u32 n2 = (c2 & 0xffffu) + (c2 >> 16), nN = (cN & 0xffffu) + (cN >> 16);
+      const u32 g2 = (a2 & 0xffffu) + (a2 >> 16), g3 = (a3 & 0xffffu) + (a3 >> 16), g4 = (a4 & 0xffffu) + (a4 >> 16), g5 = (a5 & 0xffffu) + (a5 >> 16);
+      // records | cells of 2 << 14 | cells of 3 << 27 | cells of 4 << 39 | larger cells << 51
       u64 tot;
-      const u64 ex = block_excl_add<MB_THREADS, u64>((u64)sum | ((u64)n2 << 14) | ((u64)nN << 28), s.ws64, &tot);
-      if (tid == 0) { s.nl[0] = (u32)(tot >> 14) & 0x3fffu; s.nl[1] = (u32)(tot >> 28); }
+      const u64 ex = block_excl_add<MB_THREADS, u64>((u64)sum | ((u64)(g2 - g3) << 14) | ((u64)(g3 - g4) << 27) | ((u64)(g4 - g5) << 39) | ((u64)g5 << 51),
+                                                      s.ws64, &tot);
+      const u32 t2 = (u32)(tot >> 14) & 0x1fffu, t3 = (u32)(tot >> 27) & 0xfffu, t4 = (u32)(tot >> 39) & 0xfffu, tN = (u32)(tot >> 51);
+      if (tid == 0) { s.nl[0] = t2; s.nl[1] = t3; s.nl[2] = t4; s.nl[3] = tN; }
       u32 run = (u32)ex & 0x3fffu;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const u32 w = wv[k];
         const u32 s1 = run + (w & 0xffffu);
-        wv[k] = (run | (s1 << 16)) | (__vcmpeq2(w, 0x00010001u) & 0x80008000u);
+        // exactly one record: >= 1 and not >= 2
+        const u32 one = (((w + 0x7fff7fffu) >> 15) & H) & ~((w + 0x7ffe7ffeu) >> 15);
+        wv[k] = (run | (s1 << 16)) | (one << 15);
         run = s1 + (w >> 16);
       }
       c4[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       c4[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
       __syncwarp();  // the starts are read back below through a differently typed pointer: keep the order
       // queue the own cells that hold two or more records (two on average); starts are read back from shared memory
-      u32 i2 = (u32)(ex >> 14) & 0x3fffu, iN = (u32)(ex >> 28);
+      u32 i2 = (u32)(ex >> 14) & 0x1fffu, i3 = t2 + ((u32)(ex >> 27) & 0xfffu), i4 = t2 + t3 + ((u32)(ex >> 39) & 0xfffu),
+          iN = t2 + t3 + t4 + (u32)(ex >> 51);
       const u16* cst = reinterpret_cast<const u16*>(s.cnt) + tid * 16;
       while (mm) {
         const u32 b = __ffs(mm) - 1;
@@ -336,8 +385,8 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
         const u32 st = cst[c] & 0x3fffu;
         const u32 nx = c == 15 ? run : (cst[c + 1] & 0x3fffu);
         const u32 size = nx - st;
-        if (size == 2) s.multi[i2++] = st;
-        else s.multi[MB_BUF / 2 - 1 - iN++] = st | (size << 16);
+        const u32 at = size == 2 ? i2++ : (size == 3 ? i3++ : (size == 4 ? i4++ : iN++));
+        s.multi[at] = st | (size << 16);
       }
     }
     __syncthreads();
@@ -361,46 +410,23 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
       }
     }
     __syncthreads();
-    // ---- cells of 2 records, then the larger ones: one thread per cell; 2, 3 and 4 records go through a fixed
-    // compare-exchange network in registers, anything larger (a handful per bucket on uniform data) is ordered in place ----
+    // ---- ordering passes.  Cells of 2, 3 and 4 records: one thread per cell, a fixed compare-exchange network in
+    // registers (the rarer sizes go to the high thread numbers so that no warp collects all the long jobs); larger cells
+    // (a handful per bucket on uniform data, the rule on skewed data): one WARP per cell, every lane ranks its records
+    // by counting. ----
     {
-      const u32 n2 = s.nl[0], nN = s.nl[1];
+      const u32 n2 = s.nl[0], n3 = s.nl[1], n4 = s.nl[2], nN = s.nl[3];
       const u32 base = (blockb << SEG_SHIFT), urow = ust;
-      for (u32 j = tid; j < nN; j += MB_THREADS) {
-        const u32 mm = s.multi[MB_BUF / 2 - 1 - j], lo = mm & 0xffffu, size = mm >> 16;
-        if (size == 3) { small_cell<3>(buf, lo, ob, base, urow, pidx, tie_head, tie_idx, ctl); continue; }
-        if (size == 4) { small_cell<4>(buf, lo, ob, base, urow, pidx, tie_head, tie_idx, ctl); continue; }
-        if (size > MB_MAXCELL) { atomicOr(&ctl[1], 1u); continue; }  // far from uniform after all: the LSD path redoes the batch
-        u64* cb = buf + lo;
-        for (u32 a = 1; a < size; a++) {
-          const u64 x = cb[a];
-          u32 q = a;
-          while (q > 0) {
-            const u64 y = cb[q - 1];
-            if (y <= x) break;
-            cb[q] = y;
-            q--;
-          }
-          cb[q] = x;
-        }
-        u32 run0 = 0;
-        for (u32 q = 0; q < size; q++) {
-          const u64 rq = cb[q];
-          const u32 lw = (u32)rq;
-          ob[lo + q] = (u8)(lw >> SEG_SHIFT);
-          if ((lw & SEG_MASK) == 0) pidx[blockb] = ust + lo + q;
-          if (q + 1 == size || (u32)(cb[q + 1] >> 32) != (u32)(rq >> 32)) {
-            const u32 run = q + 1 - run0;
-            if (run > 1) {
-              u32 t = atomicAdd(&ctl[0], run);
-              const u32 head = base | (ust + lo + run0);
-              for (u32 z = run0; z <= q; z++) { tie_head[t] = head; tie_idx[t] = base | ((u32)cb[z] & SEG_MASK); t++; }
-            }
-            run0 = q + 1;
-          }
-        }
+      const u32 rt = MB_THREADS - 1 - tid;
+      for (u32 j = rt >> 5; j < nN; j += MB_THREADS / 32) {
+        const u32 mmv = s.multi[n2 + n3 + n4 + j], lo = mmv & 0xffffu, size = mmv >> 16;
+        if (size > MB_MAXCELL) { if ((tid & 31u) == 0) atomicOr(&ctl[1], 1u); continue; }  // far from uniform after all: the LSD path redoes the batch
+        big_cell(buf + lo, size, lo, ob, base, urow, pidx, tie_head, tie_idx, ctl, reinterpret_cast<u16*>(s.cnt) + lo);  // the cell counters are free by now
       }
-      for (u32 j = tid; j < n2; j += MB_THREADS) small_cell<2>(buf, s.multi[j], ob, base, urow, pidx, tie_head, tie_idx, ctl);
+      for (u32 j = rt; j < n4; j += MB_THREADS) small_cell<4>(buf, s.multi[n2 + n3 + j] & 0xffffu, ob, base, urow, pidx, tie_head, tie_idx, ctl);
+      for (u32 j = (tid + MB_THREADS / 2) & (MB_THREADS - 1); j < n3; j += MB_THREADS)
+        small_cell<3>(buf, s.multi[n2 + j] & 0xffffu, ob, base, urow, pidx, tie_head, tie_idx, ctl);
+      for (u32 j = tid; j < n2; j += MB_THREADS) small_cell<2>(buf, s.multi[j] & 0xffffu, ob, base, urow, pidx, tie_head, tie_idx, ctl);
     }
     __syncthreads();
     // ---- the column slice goes out in 16-byte pieces ----

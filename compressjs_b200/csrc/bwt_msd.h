@@ -12,7 +12,7 @@
 #define MB_CAP (MB_BUF - 2)             // largest (block, first byte) bucket the path takes
 #define MB_CELL_BITS 14
 #define MB_CELLS (1u << MB_CELL_BITS)   // interpolation cells per bucket
-#define MB_MAXCELL 128u                 // a fuller cell means the keys are far from uniform: give up, the LSD path takes the batch
+#define MB_MAXCELL 512u                 // a fuller cell means the keys are far from uniform: give up, the LSD path takes the batch
 
 struct MsdBlk {
   u32 a, a2;  // symbols in use in the block, squared

@@ -48,19 +48,49 @@ k_bwtc_model(const u16* __restrict__ sym, const u32* __restrict__ d_m, const u32
   tcount[b] = e.n;
 }
 
-// one thread: the blocks of a batch through the file's range coder
-__global__ void k_bwtc_code(BwtcState* st, const u64* __restrict__ triples, const u32* __restrict__ tcount, u32 nblk, u32 tcap) {
-  if (threadIdx.x || blockIdx.x) return;
+// One warp: the blocks of a batch through the file's range coder.  The recurrence on (low, range) is serial and runs in
+// lane 0; what can be taken off its critical path is done by the whole warp, 32 symbols at a time: the coalesced load
+// of the triples, their unpacking, and a reciprocal of every total so that the serial step replaces the integer
+// division range / tot_f (RangeCoder.js:83) by a multiply-high and an exact correction.
+__device__ __forceinline__ void bc_enc_code_fast(bc_enc* rc, u32 sy_f, u32 lt_f, u32 tot_f, u32 magic) {
+  bc_enc_normalize(rc);
+  u32 r = __umulhi(rc->range, magic);          // floor(range * floor((2^32 - 1) / tot) / 2^32) <= range / tot
+  u32 rem = rc->range - r * tot_f;
+  while (rem >= tot_f) { r++; rem -= tot_f; }  // at most two steps
+  const u32 tmp = r * lt_f;
+  rc->low += tmp;
+  if (lt_f + sy_f < tot_f) rc->range = r * sy_f; else rc->range -= tmp;
+}
+__global__ void __launch_bounds__(32) k_bwtc_code(BwtcState* st, const u64* __restrict__ triples, const u32* __restrict__ tcount, u32 nblk, u32 tcap) {
+  __shared__ u32 s_sy[32], s_lt[32], s_tot[32], s_mg[32];
+  const u32 lane = threadIdx.x;
   bc_enc rc = st->rc;
   u32 overflow = st->overflow;
-  for (u32 b = 0; b < nblk; b++) {
+  for (u32 b = 0; b < nblk && !overflow; b++) {
     const u32 n = tcount[b];
     if (n > tcap) { overflow = 1; break; }
     const u64* t = triples + (size_t)b * tcap;
-    for (u32 k = 0; k < n; k++) bc_enc_code(&rc, t[k]);
+    u64 nxt = lane < n ? t[lane] : 0ull;        // one batch ahead: the load latency hides behind the serial steps
+    for (u32 k0 = 0; k0 < n; k0 += 32) {
+      const u64 tr = nxt;
+      if (k0 + 32 + lane < n) nxt = t[k0 + 32 + lane];
+      const u32 tot = (u32)(tr >> 42);
+      s_sy[lane] = (u32)(tr & 0x1FFFFF);
+      s_lt[lane] = (u32)((tr >> 21) & 0x1FFFFF);
+      s_tot[lane] = tot;
+      s_mg[lane] = tot ? 0xFFFFFFFFu / tot : 0u;
+      __syncwarp();
+      if (lane == 0) {
+        const u32 cnt = min(32u, n - k0);
+        for (u32 j = 0; j < cnt; j++) bc_enc_code_fast(&rc, s_sy[j], s_lt[j], s_tot[j], s_mg[j]);
+      }
+      __syncwarp();
+    }
   }
-  st->rc = rc;
-  st->overflow = overflow;
+  if (lane == 0) {
+    st->rc = rc;
+    st->overflow = overflow;
+  }
 }
 
 __global__ void k_bwtc_finish(BwtcState* st) {
@@ -119,7 +149,7 @@ void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out
       }
       {
         StageScope s(c, ST_PACK);   // ... and the serial range coder the slot of the bit packer (ms_pack)
-        k_bwtc_code<<<1, 1, 0, c.stream>>>(st, triples, tcount, nb, tcap);
+        k_bwtc_code<<<1, 32, 0, c.stream>>>(st, triples, tcount, nb, tcap);
         KLAUNCH(c); KCHECK();
       }
       c.stats.blocks += nb;
@@ -181,7 +211,8 @@ void bwtc_decompress_device(Ctx& c, const u8* d_in, size_t n, const u8* h_head, 
   size_t pos = 4;
   u64 fs = 0;
   for (;;) {                                                   // lib/Util.js:211-220 readUnsignedNumber
-    if (pos >= head_n || pos > 14) throw B2Error{B2_ERR_DATA_ERROR, "truncated BWTC header"};
+    // nine 7-bit groups hold any size below 2^63; a longer number cannot be the size of a real file and would overflow
+    if (pos >= head_n || pos > 4 + 9) throw B2Error{B2_ERR_DATA_ERROR, "truncated or oversized BWTC header"};
     const u32 ch = h_head[pos++];
     if (ch & 0x80) { fs += ch & 0x7F; break; }
     fs = (fs + ch) * 128;
@@ -191,7 +222,11 @@ void bwtc_decompress_device(Ctx& c, const u8* d_in, size_t n, const u8* h_head, 
   *out_n = (size_t)size;
   if (size > out_cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small"};
   // the level is inside the coded stream: size the buffers for the smallest block size
-  const u32 maxblocks = (u32)(size / 100000u + 2);
+  // (the header is not trusted: a block costs at least a few coded bytes, so n compressed bytes cannot hold more than
+  // n / 2 blocks, and the decoded size must be something this GPU can hold)
+  if (size > ((u64)1 << 40)) throw B2Error{B2_ERR_DATA_ERROR, "Data error: implausible BWTC size field"};
+  const u64 mb64 = std::min<u64>(size / 100000u + 2, (u64)n / 2 + 2);
+  const u32 maxblocks = (u32)mb64;
   DBuf<u8> L(c, (size_t)maxblocks << SEG_SHIFT);
   DBuf<u32> lengths(c, maxblocks), pidx1(c, maxblocks);
   DBuf<BwtcDecResult> res(c, 1);

@@ -424,37 +424,19 @@ struct ChunkSum {
   u32 bad;
 };
 
-// move list[idx] to the front; returns the moved value (valid in lane 0; other lanes get junk in the
-// upper bytes).  List = 8 bytes per lane (lo, hi).  Every lane builds two byte-permute selectors:
-// the bytes at positions <= p shift up by one (p = 7 below lane idx/8, idx%8 in that lane, none above),
-// byte 0 takes the carry (previous lane's top byte, or the moved value in lane 0).
-__device__ __forceinline__ u32 shl_clamp(u32 a, u32 n) {
-  u32 r;
-  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));  // PTX clamps shift amounts > 31: result 0
-  return r;
-}
-__device__ __forceinline__ u32 mtf_take(u32& lo, u32& hi, u32 idx, u32 lane) {
-  const u32 fl = idx >> 3, pos = idx & 7;
-  const u32 mine = __byte_perm(lo, hi, pos);
-  const u32 c = __shfl_sync(FULL_MASK, mine, fl);
-  const u32 up = __shfl_up_sync(FULL_MASK, hi, 1);
-  const u32 cw = lane == 0 ? c : up;
-  const u32 xl = lane == 0 ? (0x3210u ^ 0x2104u) : (0x3210u ^ 0x2107u);  // carry byte: cw byte 0 / byte 3
-  const u32 q4 = lane < fl ? 32u : (lane == fl ? 4 * pos + 4 : 0u);
-  const u32 M = shl_clamp(1u, q4) - 1u;
-  const u32 sel_lo = 0x3210u ^ (xl & M);
-  const u32 sel_hi = 0x3210u ^ (0x1317u & (M >> 16));
-  const u32 nhi = __byte_perm(hi, lo, sel_hi);
-  lo = __byte_perm(lo, cw, sel_lo);
-  hi = nhi;
-  return c & 255u;
-}
-
-__global__ void __launch_bounds__(UM_WARPS * 32)
+// One THREAD per 4 Ki-symbol chunk: the serial list pass of the reference (lib/Bzip2.js:355-360) on a private list that
+// starts as the identity, so what comes out are POSITIONS IN THE CHUNK'S START LIST (k_unmtf_map turns them into bytes
+// once k_unmtf_scan has composed the chunks' final lists).  The list lives in shared memory as 32-bit words, word k of
+// thread t at [k][t]: every lane owns a bank, whatever word it touches.  Moving list[idx] to the front shifts idx/4
+// words by one byte: a short loop whose length follows the rank (small on anything compressible), against the 48
+// warp instructions per symbol of a warp-wide register list.
+#define UA_THREADS 128
+__global__ void __launch_bounds__(UA_THREADS)
 k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, ChunkSum* __restrict__ sums, u8* __restrict__ perms,
           u8* __restrict__ symb) {
-  const u32 w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u32 gchunk = blockIdx.x * UM_WARPS + w;
+  __shared__ u32 W[64][UA_THREADS];
+  const u32 t = threadIdx.x;
+  const u32 gchunk = blockIdx.x * UA_THREADS + t;
   const u32 ci = gchunk / cps, ch = gchunk % cps;
   if (ci >= ncand) return;
   const CandRes* r = res + ci;
@@ -465,48 +447,61 @@ k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncan
   const u32 count = min((u32)UM_CHUNK, m - start);
   const u16* s = sym + ((size_t)ci << SEG_SHIFT) + start;
   const u32 symTotal = r->sym_total;
-  u32 lo = 0x03020100u + lane * 0x08080808u, hi = 0x07060504u + lane * 0x08080808u;  // identity list
+#pragma unroll 8
+  for (u32 k = 0; k < 64; k++) W[k][t] = 0x03020100u + k * 0x04040404u;  // identity list
   u64 leadval = 0; u32 nlead = 0, rest = 0, krun = 0, bad = 0;
   bool seen_lit = false;
-  // symb[i] = position IN THE CHUNK'S START LIST of the byte that symbol i stands for (the list front for
-  // a run digit): k_unmtf_map turns it into the byte once k_unmtf_scan knows the start lists.
   u8* sb = symb + ((size_t)ci << SEG_SHIFT) + start;
   u32 front = 0;
-  u32 nxt = lane < count ? s[lane] : 0xffffu;
-  for (u32 base = 0; base < count; base += 32) {
-    const u32 mine = nxt;
-    nxt = (base + 32 + lane < count) ? s[base + 32 + lane] : 0xffffu;
-    const u32 lim = min(32u, count - base);
-    u32 keep = 0;
-    for (u32 t = 0; t < lim; t++) {
-      const u32 sy = __shfl_sync(FULL_MASK, mine, t);
-      if (sy <= 1) {
-        if (!seen_lit) {
-          if (nlead < 21) leadval += (u64)(sy + 1) << nlead; else bad = 1;   // >= 2^21 bytes: over any dbufSize
-          nlead++;
+  for (u32 base = 0; base < count; base += 8) {
+    // eight symbols per step: one 16-byte load, one 8-byte store (the slot is 1 MiB: reading past `count` stays inside it)
+    const uint4 q = *reinterpret_cast<const uint4*>(s + base);
+    const u32 qw[4] = {q.x, q.y, q.z, q.w};
+    u32 keep_lo = 0, keep_hi = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const u32 sy = (qw[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+      if (base + j < count) {
+        if (sy <= 1) {
+          if (!seen_lit) {
+            if (nlead < 21) leadval += (u64)(sy + 1) << nlead; else bad = 1;   // >= 2^21 bytes: over any dbufSize
+            nlead++;
+          } else {
+            if (krun < 21) rest = min(rest + ((sy + 1) << krun), 0x3fffffffu); else bad = 1;  // saturate: no wrap-around
+            krun++;
+          }
         } else {
-          if (krun < 21) rest = min(rest + ((sy + 1) << krun), 0x3fffffffu); else bad = 1;  // saturate: no wrap-around
-          krun++;
-        }
-      } else {
-        seen_lit = true; krun = 0;
-        if (sy <= symTotal) {
-          front = mtf_take(lo, hi, sy - 1, lane);
-          rest++;
+          seen_lit = true; krun = 0;
+          if (sy <= symTotal) {
+            const u32 idx = sy - 1, wq = idx >> 2, bp = idx & 3u;
+            const u32 x = W[wq][t];
+            const u32 b = (x >> (8 * bp)) & 0xffu;
+            u32 carry = b;
+            for (u32 k = 0; k < wq; k++) {
+              const u32 y = W[k][t];
+              W[k][t] = (y << 8) | carry;
+              carry = y >> 24;
+            }
+            const u32 msk = bp == 3 ? 0xffffffffu : ((1u << (8 * (bp + 1))) - 1u);
+            W[wq][t] = (((x << 8) | carry) & msk) | (x & ~msk);
+            front = b;
+            rest++;
+          }
         }
       }
-      if (lane == t) keep = front;
+      if (j < 4) keep_lo |= front << (8 * j); else keep_hi |= front << (8 * (j - 4));
     }
-    if (base + lane < count) sb[base + lane] = (u8)keep;
+    *reinterpret_cast<uint2*>(sb + base) = make_uint2(keep_lo, keep_hi);
   }
-  if (lane == 0) {
+  {
     ChunkSum cs;
     cs.leadval = leadval; cs.nlead = nlead; cs.rest = rest; cs.trail = seen_lit ? krun : nlead; cs.allrun = seen_lit ? 0u : 1u;
     cs.nsyms = count; cs.bad = bad;
     sums[gchunk] = cs;
   }
   u32* p = reinterpret_cast<u32*>(perms + (size_t)gchunk * 256);
-  p[lane * 2] = lo; p[lane * 2 + 1] = hi;
+#pragma unroll 8
+  for (u32 k = 0; k < 64; k++) p[k] = W[k][t];
 }
 
 struct ChunkStart {
@@ -1030,7 +1025,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
       {
         StageScope ss(c, ST_UNMTF);
         const u32 chunks = cnt * cps;
-        k_unmtf_a<<<(chunks + UM_WARPS - 1) / UM_WARPS, UM_WARPS * 32, 0, c.stream>>>(sym, rb, cnt, cps, sums, perms, symb);
+        k_unmtf_a<<<(chunks + UA_THREADS - 1) / UA_THREADS, UA_THREADS, 0, c.stream>>>(sym, rb, cnt, cps, sums, perms, symb);
         KLAUNCH(c); KCHECK();
         k_unmtf_scan<<<cnt, 32, 0, c.stream>>>(rb, cnt, cps, dbuf_size, sums, perms, lists, starts);
         KLAUNCH(c); KCHECK();

@@ -12,8 +12,6 @@
 //     accumulates every table's cost (staged through shared memory, conflict-free stride 25)
 //   * the stable median split needs no sort: histogram of costs -> threshold cost, then an
 //     ordered prefix count among the groups that sit exactly on the threshold
-//   * the frequency recount of lib/Bzip2.js:717-727 is folded into the selector pass (symbols are counted for the
-//     table the group picks) and corrected for the groups the split moves: 5.6 instead of 9 passes over a block
 //   * tables are rebuilt with a rank-by-counting sort of (freq<<9|sym) and one thread per table
 //     running the exact in-place allocator
 #include "enc.h"
@@ -89,9 +87,6 @@ __device__ __forceinline__ void tile_store(const TileRegs& t, u32* tile) {
   for (int k = 0; k < HF_TILE_WORDS / HF_THREADS; k++) tile[k * HF_THREADS + threadIdx.x] = t.r[k];
 }
 
-// COUNT: the symbols of every group are also counted into the frequency table of the group's selector while the tile
-// is in shared memory (s.freq must be zero on entry), which saves the separate recount pass over the block.
-template <bool COUNT>
 __device__ void assign_selectors(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 nsel, u32 ntab) {
   const u32 tid = threadIdx.x;
   const u32 nwords = (m + 1) >> 1;
@@ -125,39 +120,35 @@ __device__ void assign_selectors(HuffSmem& s, const u32* __restrict__ symw, u32 
       }
       s.sel[g] = (u8)best;
       s.cost[g] = (u16)bc;
-      if (COUNT) {
-        u32* f = s.freq[best];
-        for (u32 k = 0; k < 25; k++) {
-          const u32 w = s.tile[tid * 25 + k];
-          if (2 * k < cnt) atomicAdd(&f[w & 0xffffu], 1u);
-          if (2 * k + 1 < cnt) atomicAdd(&f[w >> 16], 1u);
-        }
-      }
     }
     __syncthreads();
   }
 }
 
-// After the split (lib/Bzip2.js:710-727): the groups that moved from table `which` to the new table `ng` take their
-// symbols with them.  Same frequencies as the reference's full recount, but only the moved groups are read again.
-__device__ void move_counts(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 nsel, u32 which, u32 ng) {
+__device__ void recount(HuffSmem& s, const u32* __restrict__ symw, u32 m, u32 nsel, u32 ntab, u32 A) {
   const u32 tid = threadIdx.x;
-  u32* fw = s.freq[which];
-  u32* fn = s.freq[ng];
-  for (u32 g = tid; g < nsel; g += HF_THREADS) {
-    if (s.sel[g] != ng) continue;
-    const u32 cnt = min(50u, m - 50u * g);
-    const u32* p = symw + (size_t)g * 25;
-    u32 w[25];
-#pragma unroll
-    for (int k = 0; k < 25; k++) w[k] = (2 * k < (int)cnt) ? p[k] : 0u;
-#pragma unroll
-    for (int k = 0; k < 25; k++) {
-      if (2 * k < (int)cnt) { atomicAdd(&fn[w[k] & 0xffffu], 1u); atomicSub(&fw[w[k] & 0xffffu], 1u); }
-      if (2 * k + 1 < (int)cnt) { atomicAdd(&fn[w[k] >> 16], 1u); atomicSub(&fw[w[k] >> 16], 1u); }
-    }
-  }
+  const u32 nwords = (m + 1) >> 1;
+  for (u32 i = tid; i < ntab * (HUFF_MAXSYM + 2); i += HF_THREADS) (&s.freq[0][0])[i] = 0;
+  TileRegs tr;
+  tile_fetch(tr, symw, 0, nwords);
   __syncthreads();
+  for (u32 g0 = 0; g0 < nsel; g0 += HF_TILE_GROUPS) {
+    tile_store(tr, s.tile);
+    __syncthreads();
+    if (g0 + HF_TILE_GROUPS < nsel) tile_fetch(tr, symw, (g0 + HF_TILE_GROUPS) * 25, nwords);
+    const u32 g = g0 + tid;
+    if (g < nsel) {
+      const u32 cnt = min(50u, m - 50u * g);
+      u32* f = s.freq[s.sel[g]];
+      for (u32 k = 0; k < 25; k++) {
+        const u32 w = s.tile[tid * 25 + k];
+        if (2 * k < cnt) atomicAdd(&f[w & 0xffffu], 1u);
+        if (2 * k + 1 < cnt) atomicAdd(&f[w >> 16], 1u);
+      }
+    }
+    __syncthreads();
+  }
+  (void)A;
 }
 
 // ---- move-to-front over <= 6 table ids, list packed as six nibbles -------------------------------
@@ -241,9 +232,7 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
   u32 ng = 2;
   build_tables(s, ng, A);
   while (ng < target) {
-    for (u32 i = tid; i < (ng + 1) * (HUFF_MAXSYM + 2); i += HF_THREADS) (&s.freq[0][0])[i] = 0;  // the tables are built: count afresh
-    __syncthreads();
-    assign_selectors<true>(s, symw, m, nsel, ng);
+    assign_selectors(s, symw, m, nsel, ng);
     // which table is used most? (first maximum, lib/Bzip2.js:699)
     if (tid < HUFF_MAXGROUPS) s.gcount[tid] = 0;
     for (u32 i = tid; i < 1024; i += HF_THREADS) s.chist[i] = 0;
@@ -301,11 +290,11 @@ k_huffman(const u16* __restrict__ sym, const u32* __restrict__ m_arr, const u32*
       }
     }
     __syncthreads();
-    move_counts(s, symw, m, nsel, which, ng);
     ng++;
+    recount(s, symw, m, nsel, ng, A);
     build_tables(s, ng, A);
   }
-  assign_selectors<false>(s, symw, m, nsel, ng);  // lib/Bzip2.js:843
+  assign_selectors(s, symw, m, nsel, ng);  // lib/Bzip2.js:843
   // ---- results + bit accounting ----
   // sum of the code bits
   unsigned long long bits = 0;

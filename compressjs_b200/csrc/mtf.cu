@@ -303,6 +303,9 @@ k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const u
        u32* __restrict__ freq) {
   __shared__ u32 hist[HUFF_MAXSYM];
   __shared__ u32 ws[R2_THREADS / 32 + 1];
+  // the tile's symbols are staged here at the alignment (mod 8 symbols = 16 bytes) they have in global memory, then
+  // copied out in 16-byte pieces: at most one symbol per rank plus the digits of the run that was carried in
+  __shared__ __align__(16) u16 stage[R2_TILE + 48];
   const u32 tid = threadIdx.x;
   const u32 seg = blockIdx.x / tps, lt = blockIdx.x % tps;
   const u32 n = seg_n[seg];
@@ -358,23 +361,36 @@ k_rle2(const u8* __restrict__ R, const u32* __restrict__ seg_n, u32 tps, const u
   }
   u32 tot_off;
   const u32 ex_off = block_excl_add<R2_THREADS, u32>(sum, ws, &tot_off);
-  u32 o = pl.x + ex_off;
+  const u32 first = pl.x & 7u;
+  u32 o = first + ex_off;  // index into `stage`
 #pragma unroll
   for (int j = 0; j < R2_ITEMS; j++) {
     const u32 p = p0 + j;
     if (p < n && v[j] != 0) {
       u32 L = rlen[j];
       while (L) {  // lib/Bzip2.js:783-794 emitLastRun
-        if (L & 1) { a[o++] = 0; atomicAdd(&hist[0], 1u); L -= 1; }
-        else { a[o++] = 1; atomicAdd(&hist[1], 1u); L -= 2; }
+        if (L & 1) { stage[o++] = 0; atomicAdd(&hist[0], 1u); L -= 1; }
+        else { stage[o++] = 1; atomicAdd(&hist[1], 1u); L -= 2; }
         L >>= 1;
       }
       const u32 sy = (u32)v[j] + 1;
-      a[o++] = (u16)sy;
+      stage[o++] = (u16)sy;
       atomicAdd(&hist[sy], 1u);
     }
   }
   __syncthreads();
+  {
+    const u32 last = first + tot_off;
+    u16* ag = a + (pl.x - first);  // 16-byte aligned: the slot base is, and (pl.x - first) is a multiple of 8 symbols
+    for (u32 c8 = tid * 8u; c8 < last; c8 += R2_THREADS * 8u) {
+      if (c8 >= first && c8 + 8u <= last) {
+        *reinterpret_cast<uint4*>(ag + c8) = *reinterpret_cast<const uint4*>(stage + c8);
+      } else {
+        const u32 e = min(c8 + 8u, last);
+        for (u32 x = max(c8, first); x < e; x++) ag[x] = stage[x];
+      }
+    }
+  }
   for (u32 i = tid; i < HUFF_MAXSYM; i += R2_THREADS)
     if (hist[i]) atomicAdd(&freq[(size_t)seg * HUFF_MAXSYM + i], hist[i]);
 }
