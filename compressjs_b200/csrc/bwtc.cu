@@ -48,6 +48,108 @@ k_bwtc_model(const u16* __restrict__ sym, const u32* __restrict__ d_m, const u32
   tcount[b] = e.n;
 }
 
+// Fenwick model (levels 6..9) with one WARP per block: the tree lives in shared memory, the nodes on the path from a
+// leaf to the root sit in different lanes (lane l owns node (numSyms + symbol) >> l), so the cumulative frequency is one
+// warp reduction over the left siblings and the update one add per lane; the rescale (every ~128 symbols,
+// lib/FenwickModel.js:125-161) runs over the leaves in parallel and re-sums the tree level by level.
+// Same triples as bc_fen_encode (bwtc_core.cuh), which the host tests check against the oracle.
+struct FenWarp { u32 tree[2 * 260]; };
+__device__ __forceinline__ void fenw_sum(u32* tree, u32 numSyms, u32 lane) {
+  for (int k = 8; k >= 0; k--) {               // nodes [2^k, 2^(k+1)) only depend on deeper ones
+    const u32 lo = 1u << k, hi = min(2u << k, numSyms);
+    for (u32 i = lo + lane; i < hi; i += 32) tree[i] = tree[2 * i] + tree[2 * i + 1];
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void fenw_rescale(u32* tree, u32 numSyms, u32 lane) {
+  u32 noEscape = 1;
+  for (u32 i = lane; i + 1 < numSyms; i += 32) {
+    u32 prob = tree[numSyms + i];
+    if (prob & BC_ESC_MASK) { noEscape = 0; continue; }
+    prob = (prob & BC_SCALE_MASK) >> 1;
+    if (prob == 0) { prob = 1; noEscape = 0; }
+    tree[numSyms + i] = prob;
+  }
+  noEscape = __all_sync(FULL_MASK, noEscape);
+  if (lane == 0) {
+    u32 prob = (tree[2 * numSyms - 1] & BC_SCALE_MASK) >> 1;
+    if (noEscape) prob = 0; else if (prob == 0) prob = 1u << 16;
+    tree[2 * numSyms - 1] = prob;
+  }
+  __syncwarp();
+  fenw_sum(tree, numSyms, lane);
+}
+// one trip up the tree (bc_fen_step); every lane returns the triple
+__device__ __forceinline__ u64 fenw_step(u32* tree, u32 numSyms, u32 symbol, u32 sy_leaf, int esc, u32 lane) {
+  const u32 i = numSyms + symbol;
+  u32 mask = BC_SYM_MASK, shift = 16, update = BC_F_PROB_INCR << 16;
+  const u32 root = tree[1];
+  if (esc) { mask = BC_ESC_MASK; update -= 1; shift = 0; }
+  else if (symbol == numSyms - 1 && (root & BC_ESC_MASK) == 1) update = 0u - tree[i];  // the last escape
+  const u32 node = lane < 31 ? (i >> lane) : 0u;
+  const bool on_path = node > 1;
+  u32 contrib = (on_path && (node & 1u)) ? tree[node - 1] : 0u;   // left sibling
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(FULL_MASK, contrib, o);
+  __syncwarp();
+  if (on_path) tree[node] += update;
+  if (lane == 31) tree[1] = root + update;
+  __syncwarp();
+  const u64 tr = bc_triple((sy_leaf & mask) >> shift, (contrib & mask) >> shift, (root & mask) >> shift);
+  if ((((root + update) & BC_SYM_MASK) >> 16) >= BC_F_PROB_MAX) fenw_rescale(tree, numSyms, lane);
+  return tr;
+}
+__global__ void __launch_bounds__(32)
+k_bwtc_model_fenwick(const u16* __restrict__ sym, const u32* __restrict__ d_m, const u32* __restrict__ d_n, const u32* __restrict__ d_pidx1,
+                     const u32* __restrict__ d_used, u32 blockSize, u64* __restrict__ triples, u32 tcap, u32* __restrict__ tcount) {
+  __shared__ FenWarp fw;
+  __shared__ u32 s_hdr[2];
+  const u32 b = blockIdx.x, lane = threadIdx.x;
+  u64* out = triples + (size_t)b * tcap;
+  const u32 m = d_m[b], nsym = m ? m - 1 : 0;
+  if (lane == 0) {
+    bc_emit e;
+    e.t = out; e.n = 0; e.cap = tcap;
+    s_hdr[1] = bc_block_header(&e, blockSize, d_n[b], d_pidx1[b], d_used + (size_t)b * 8);
+    s_hdr[0] = e.n;
+  }
+  __syncwarp();
+  u32 n_out = s_hdr[0];
+  const u32 size = s_hdr[1] + 1, numSyms = size + 1;      // bc_fen_init(alphabetSize + 1)
+  u32* tree = fw.tree;
+  for (u32 i = lane; i < 2 * 260; i += 32) tree[i] = 0;
+  __syncwarp();
+  for (u32 i = lane; i < size; i += 32) tree[numSyms + i] = 1;
+  if (lane == 0) tree[numSyms + size] = BC_F_PROB_INCR << 16;
+  __syncwarp();
+  fenw_sum(tree, numSyms, lane);
+  const u16* sp = sym + ((size_t)b << SEG_SHIFT);
+  for (u32 k0 = 0; k0 < nsym; k0 += 32) {
+    const u32 mine = k0 + lane < nsym ? sp[k0 + lane] : 0u;
+    const u32 cnt = min(32u, nsym - k0);
+    for (u32 j = 0; j < cnt; j++) {
+      const u32 symbol = __shfl_sync(FULL_MASK, mine, j);
+      const u32 sy_leaf = tree[numSyms + symbol];
+      u64 t0, t1 = 0;
+      u32 produced = 1;
+      if ((sy_leaf & BC_SYM_MASK) == 0) {
+        const u32 escSym = numSyms - 1;
+        t0 = fenw_step(tree, numSyms, escSym, tree[numSyms + escSym], 0, lane);
+        t1 = fenw_step(tree, numSyms, symbol, sy_leaf, 1, lane);
+        produced = 2;
+      } else {
+        t0 = fenw_step(tree, numSyms, symbol, sy_leaf, 0, lane);
+      }
+      if (lane == 0) {
+        if (n_out < tcap) out[n_out] = t0;
+        if (produced == 2 && n_out + 1 < tcap) out[n_out + 1] = t1;
+      }
+      n_out += produced;
+    }
+  }
+  if (lane == 0) tcount[b] = n_out;
+}
+
 // One warp: the blocks of a batch through the file's range coder.  The recurrence on (low, range) is serial and runs in
 // lane 0; what can be taken off its critical path is done by the whole warp, 32 symbols at a time: the coalesced load
 // of the triples, their unpacking, and a reciprocal of every total so that the serial step replaces the integer
@@ -62,9 +164,12 @@ __device__ __forceinline__ void bc_enc_code_fast(bc_enc* rc, u32 sy_f, u32 lt_f,
   if (lt_f + sy_f < tot_f) rc->range = r * sy_f; else rc->range -= tmp;
 }
 __global__ void __launch_bounds__(32) k_bwtc_code(BwtcState* st, const u64* __restrict__ triples, const u32* __restrict__ tcount, u32 nblk, u32 tcap) {
-  __shared__ u32 s_sy[32], s_lt[32], s_tot[32], s_mg[32];
   const u32 lane = threadIdx.x;
+  // every lane runs the same recurrence on its own copy of the coder state (one instruction stream, no divergence);
+  // the triple of step j is broadcast from lane j, so the shuffles of later steps issue ahead of the serial chain.
+  // Only lane 0's copy writes bytes.
   bc_enc rc = st->rc;
+  if (lane) rc.cap = 0;  // bc_out of the other lanes stores nothing (their byte counter still advances in step)
   u32 overflow = st->overflow;
   for (u32 b = 0; b < nblk && !overflow; b++) {
     const u32 n = tcount[b];
@@ -74,17 +179,17 @@ __global__ void __launch_bounds__(32) k_bwtc_code(BwtcState* st, const u64* __re
     for (u32 k0 = 0; k0 < n; k0 += 32) {
       const u64 tr = nxt;
       if (k0 + 32 + lane < n) nxt = t[k0 + 32 + lane];
-      const u32 tot = (u32)(tr >> 42);
-      s_sy[lane] = (u32)(tr & 0x1FFFFF);
-      s_lt[lane] = (u32)((tr >> 21) & 0x1FFFFF);
-      s_tot[lane] = tot;
-      s_mg[lane] = tot ? 0xFFFFFFFFu / tot : 0u;
-      __syncwarp();
-      if (lane == 0) {
-        const u32 cnt = min(32u, n - k0);
-        for (u32 j = 0; j < cnt; j++) bc_enc_code_fast(&rc, s_sy[j], s_lt[j], s_tot[j], s_mg[j]);
+      const u32 tot = (u32)(tr >> 42), sy = (u32)(tr & 0x1FFFFF), lt = (u32)((tr >> 21) & 0x1FFFFF);
+      const u32 mg = tot ? 0xFFFFFFFFu / tot : 0u;
+      const u32 cnt = min(32u, n - k0);
+      if (cnt == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          bc_enc_code_fast(&rc, __shfl_sync(FULL_MASK, sy, j), __shfl_sync(FULL_MASK, lt, j), __shfl_sync(FULL_MASK, tot, j), __shfl_sync(FULL_MASK, mg, j));
+      } else {
+        for (u32 j = 0; j < cnt; j++)
+          bc_enc_code_fast(&rc, __shfl_sync(FULL_MASK, sy, j), __shfl_sync(FULL_MASK, lt, j), __shfl_sync(FULL_MASK, tot, j), __shfl_sync(FULL_MASK, mg, j));
       }
-      __syncwarp();
     }
   }
   if (lane == 0) {
@@ -144,7 +249,8 @@ void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out
       }
       {
         StageScope s(c, ST_HUFF);   // statistics: the model takes the slot of the Huffman stage (ms_huff) ...
-        k_bwtc_model<<<nb, 32, 0, c.stream>>>(sym, dm, dn, dpidx, dused, blockSize, fast, triples, tcap, tcount);
+        if (fast) k_bwtc_model<<<nb, 32, 0, c.stream>>>(sym, dm, dn, dpidx, dused, blockSize, fast, triples, tcap, tcount);
+        else k_bwtc_model_fenwick<<<nb, 32, 0, c.stream>>>(sym, dm, dn, dpidx, dused, blockSize, triples, tcap, tcount);
         KLAUNCH(c); KCHECK();
       }
       {

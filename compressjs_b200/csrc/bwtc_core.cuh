@@ -157,8 +157,8 @@ BC_FN void bc_dsm_encode(bc_dsm* m, bc_emit* e, bc_u32 symbol) {  // :94-111 wit
 // produces them (0 = RUNA, 1 = RUNB, rank+1; lib/BWTC.js:112-137 is the same coding without an end-of-block
 // symbol), nsym of them.  scratch holds the model.
 typedef union { bc_fen fen; bc_dsm dsm; } bc_model;
-BC_FN void bc_block_triples(bc_emit* e, bc_model* scratch, bc_u32 blockSize, bc_u32 length, bc_u32 pidx1, const bc_u32* used,
-                            const bc_u16* sym, bc_u32 nsym, int fast) {
+// block header (lib/BWTC.js:50-83): size flag / length, primary index, the tree of used bytes; returns the alphabet size
+BC_FN bc_u32 bc_block_header(bc_emit* e, bc_u32 blockSize, bc_u32 length, bc_u32 pidx1, const bc_u32* used) {
   const int lgbits = bc_lgbits(blockSize);
   if (length == blockSize) bc_put(e, 1, 0, 3);                                    // :50-52 "full size block"
   else { bc_put(e, 1, 1, 3); bc_put_distance(e, lgbits, length); }                // :54-55
@@ -173,7 +173,11 @@ BC_FN void bc_block_triples(bc_emit* e, bc_model* scratch, bc_u32 blockSize, bc_
     if (i >= 256) bc_put_bit(e, useTree[i]);
     else bc_put(e, 1, useTree[i] == 0 ? 0u : (useTree[i] == full ? 2u : 1u), 3);
   }
-  const bc_u32 alphabetSize = useTree[1];
+  return useTree[1];
+}
+BC_FN void bc_block_triples(bc_emit* e, bc_model* scratch, bc_u32 blockSize, bc_u32 length, bc_u32 pidx1, const bc_u32* used,
+                            const bc_u16* sym, bc_u32 nsym, int fast) {
+  const bc_u32 alphabetSize = bc_block_header(e, blockSize, length, pidx1, used);
   if (fast) {                                                                     // :109-111
     bc_dsm_init(&scratch->dsm, alphabetSize + 1);
     for (bc_u32 k = 0; k < nsym; k++) bc_dsm_encode(&scratch->dsm, e, sym[k]);

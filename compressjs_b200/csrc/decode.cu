@@ -57,26 +57,34 @@ struct CandRes {
 };
 
 // ---- magic scan ---------------------------------------------------------------------------
+// One thread per aligned 32-bit word of the stream = 32 bit offsets: the words w, w+1, w+2 (big endian) hold the 80 bits
+// that a candidate starting in word w can span (48-bit magic + the 32 bits behind it need w+3 as well).  The first 32
+// bits of the magic are tested with one funnel shift and one compare per offset.
 __global__ void k_scan_magic(const u8* __restrict__ in, u64 n, Cand* __restrict__ cands, u32* count, u32 cap) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u64 hi = 0;  // bytes i .. i+7
-  u32 lo = 0;  // bytes i+8 .. i+11
-  for (int k = 0; k < 8; k++) hi = (hi << 8) | (i + k < n ? in[i + k] : 0);
-  for (int k = 8; k < 12; k++) lo = (lo << 8) | (i + k < n ? in[i + k] : 0);
-  for (int s = 0; s < 8; s++) {
-    const u64 w = s ? ((hi << s) | (lo >> (32 - s))) : hi;
-    const u64 v = w >> 16;
-    if (v == WHOLEPI || v == SQRTPI) {
-      const u32 idx = atomicAdd(count, 1u);
-      if (idx < cap) {
-        Cand c;
-        c.pos = i * 8 + s;
-        c.type = v == WHOLEPI ? 1u : 2u;
-        // 32 bits behind the 48-bit magic: bits 48..79 of the window starting at (i, s)
-        const u64 w2 = ((w << 48) | ((u64)((s ? (lo << s) : lo)) << 16));
-        c.next32 = (u32)(w2 >> 32);
-        cands[idx] = c;
+  const u64 wi = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 nwords = (n + 3) / 4;      // the private copy of the input is zero padded (dec_open): reads up to n + 31 are safe
+  if (wi >= nwords) return;
+  const u32* words = reinterpret_cast<const u32*>(in);
+  const u32 w0 = __byte_perm(words[wi], 0, 0x0123), w1 = __byte_perm(words[wi + 1], 0, 0x0123), w2 = __byte_perm(words[wi + 2], 0, 0x0123),
+            w3 = __byte_perm(words[wi + 3], 0, 0x0123);
+  const u32 M1 = (u32)(WHOLEPI >> 16), M2 = (u32)(SQRTPI >> 16);
+#pragma unroll 8
+  for (u32 b = 0; b < 32; b++) {
+    const u32 h = __funnelshift_l(w1, w0, b);            // stream bits [b, b + 32) of this word pair
+    if (h == M1 || h == M2) {
+      const u32 mid = __funnelshift_l(w2, w1, b);        // bits [b + 32, b + 64)
+      const u64 v = ((u64)h << 16) | (mid >> 16);
+      const u64 pos = wi * 32 + b;
+      if ((v == WHOLEPI || v == SQRTPI) && pos < n * 8) {
+        const u32 idx = atomicAdd(count, 1u);
+        if (idx < cap) {
+          Cand c;
+          c.pos = pos;
+          c.type = v == WHOLEPI ? 1u : 2u;
+          const u32 lo = __funnelshift_l(w3, w2, b);     // bits [b + 64, b + 96)
+          c.next32 = (mid << 16) | (lo >> 16);           // the 32 bits behind the 48-bit magic
+          cands[idx] = c;
+        }
       }
     }
   }
@@ -932,7 +940,10 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   int level = hdr[3] - 0x30;
   if (level < 1 || level > 9) throw B2Error{DEC_NOT_BZIP, "Not bzip data: level out of range"};
   S.dbuf_size = 100000u * (u32)level;
-  const u32 dbuf_size = S.dbuf_size;
+  // The kernels decode every candidate under the largest block size: the members of a multistream file may have
+  // different levels (lib/Bzip2.js:105-124 re-reads the level per member), and which member a candidate belongs to is
+  // only known when the host walks the chain, where the member's own limit is applied (dec_finish).
+  const u32 dbuf_size = 900000u;
   const u8* din = S.din;
 
   // ---- 1. candidates ----
@@ -948,7 +959,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
     u32 cnt = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
       CUDA_CHECK(cudaMemsetAsync(dcount, 0, 4, c.stream));
-      k_scan_magic<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(din, n, dc, dcount, cap);
+      k_scan_magic<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, c.stream>>>(din, n, dc, dcount, cap);
       KLAUNCH(c); KCHECK();
       CUDA_CHECK(cudaMemcpyAsync(&cnt, dcount, 4, cudaMemcpyDeviceToHost, c.stream));
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
@@ -1092,7 +1103,7 @@ static int dec_finish(Ctx& c, DecSession& S, int multistream, u8* d_out, size_t 
   std::vector<Cand>& cands = S.cands;
   std::vector<Cand>& bc = S.bc;
   std::vector<CandRes>& hres = S.hres;
-  const u32 dbuf_size = S.dbuf_size;
+  u32 cur_dbuf = S.dbuf_size;  // dbufSize of the member the walk is in (lib/Bzip2.js:121)
   const u32 ur_tps = UR_TPS;
   // ---- 3. walk the chain in stream order (lib/Bzip2.js:454-481 / 508-548) ----
   std::vector<Event> events;
@@ -1107,10 +1118,19 @@ static int dec_finish(Ctx& c, DecSession& S, int multistream, u8* d_out, size_t 
   for (size_t i = 0; i < nb_all; i++) cand_to_blk[S.blk_idx[i]] = (long)i;
   auto block_event = [&](size_t bi) -> bool {  // returns false when the walk must stop (error recorded)
     const CandRes& r = hres[bi];
+    // the member's own limits, in the reference's order: randomised bit (:143), origPointer (:146), then the body
+    if (r.status != DEC_OBSOLETE && r.orig > cur_dbuf) {
+      events.push_back({2, bi, 0, 0, DEC_DATA_ERROR, "Data error: initial position out of bounds"});
+      return false;
+    }
     if (r.status != 0) {
       std::string msg = r.status == DEC_OBSOLETE ? "Obsolete (pre 0.9.5) bzip format not supported." : "Data error";
       if (r.detail == 1) msg += ": initial position out of bounds";
       events.push_back({2, bi, 0, 0, r.status, msg});
+      return false;
+    }
+    if (r.n > cur_dbuf) {  // dbufCount would have run over dbufSize (lib/Bzip2.js:338,354)
+      events.push_back({2, bi, 0, 0, DEC_DATA_ERROR, "Data error"});
       return false;
     }
     outbase[bi] = total_out;
@@ -1145,7 +1165,7 @@ static int dec_finish(Ctx& c, DecSession& S, int multistream, u8* d_out, size_t 
           if (avail != 4 || h2[0] != 'B' || h2[1] != 'Z' || h2[2] != 'h') { events.push_back({2, 0, 0, 0, DEC_NOT_BZIP, "Not bzip data: bad magic"}); break; }
           const int lv = h2[3] - 0x30;
           if (lv < 1 || lv > 9) { events.push_back({2, 0, 0, 0, DEC_NOT_BZIP, "Not bzip data: level out of range"}); break; }
-          if ((u32)lv * 100000u != dbuf_size) { events.push_back({2, 0, 0, 0, B2_ERR_BAD_ARG, "multistream members with different block sizes are not supported"}); break; }
+          cur_dbuf = (u32)lv * 100000u;
           stream_crc = 0;
           pos = (bytepos + 4) * 8;
         } else break;
@@ -1245,7 +1265,7 @@ void dec_shard_export(u64* buf) {
   for (size_t i = g_shard->lo; i < g_shard->hi; i++) {
     const CandRes& r = g_shard->hres[i];
     u64* o = buf + (i - g_shard->lo) * 6;
-    o[0] = (u64)(long long)r.status; o[1] = r.detail; o[2] = r.endbit; o[3] = r.n; o[4] = r.rawlen; o[5] = 0;
+    o[0] = (u64)(long long)r.status; o[1] = r.detail; o[2] = r.endbit; o[3] = r.n; o[4] = r.rawlen; o[5] = r.orig;
   }
 }
 int dec_shard_finish(Ctx& c, const u64* all, int multistream, u8* d_out, size_t out_cap, u64* res) {
@@ -1255,7 +1275,7 @@ int dec_shard_finish(Ctx& c, const u64* all, int multistream, u8* d_out, size_t 
     if (i >= S.lo && i < S.hi) continue;
     const u64* o = all + i * 6;
     CandRes& r = S.hres[i];
-    r.status = (int)(long long)o[0]; r.detail = (u32)o[1]; r.endbit = o[2]; r.n = (u32)o[3]; r.rawlen = (u32)o[4];
+    r.status = (int)(long long)o[0]; r.detail = (u32)o[1]; r.endbit = o[2]; r.n = (u32)o[3]; r.rawlen = (u32)o[4]; r.orig = (u32)o[5];
   }
   size_t out_n = 0;
   struct Closer { ~Closer() { delete g_shard; g_shard = nullptr; } } closer;

@@ -454,6 +454,8 @@ def compress_shares(d_buf, share_len, level=9, group=None, host_out=None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = d_buf.device
     PHASES.clear()
+    if d_buf.is_cuda:
+        torch.cuda.current_stream().synchronize()   # the library works on its own stream: the input must have landed
     t0 = time.perf_counter()
     summ = (C.c_uint64 * 4)()
     rc = L.b2_bzip2_share_summary(d_buf.data_ptr(), share_len, summ)
@@ -517,6 +519,8 @@ def share_bounds(n, rank, world, halo):
 def decode_shard_rows(L, d_in, rank, world):
     """Stage 1 on one rank: returns (info, rows) -- rows = int64 tensor [own candidates, 6] on the CPU."""
     from . import _native
+    if d_in.is_cuda:
+        torch.cuda.current_stream().synchronize()   # the library works on its own stream: the input must have landed
     info = (C.c_uint64 * 3)()
     rc = L.b2_dec_shard_open(d_in.data_ptr(), d_in.numel(), rank, world, info)
     if rc:
@@ -559,6 +563,12 @@ def decompress_file_sharded(d_in, multistream=False, group=None):
     device = d_in.device
     (total, lo, hi), rows = decode_shard_rows(L, d_in, rank, world)
     if world > 1:
+        # every rank scanned the same stream: the candidate counts must agree (a cheap guard against mismatched collectives)
+        chk = torch.tensor([total, d_in.numel()], dtype=torch.int64, device=device)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk, group=group)
+        if any(int(v[0]) != total or int(v[1]) != d_in.numel() for v in allc):
+            raise RuntimeError("decompress_file_sharded: the ranks do not hold the same stream")
         per = max((r + 1) * total // world - r * total // world for r in range(world))
         pad = torch.zeros((max(per, 1), 6), dtype=torch.int64, device=device)
         if hi > lo:

@@ -71,6 +71,20 @@ def test_multistream():
     assert B().decompressFile(z) == O.bzip2_decompress(z)
 
 
+def test_multistream_members_with_different_levels():
+    """`cat a-1.bz2 b-9.bz2 c-3.bz2`: the reference re-reads the level for every member (lib/Bzip2.js:105-124); a block of
+    the level-9 member is far larger than the first member's dbufSize."""
+    a, b, c3 = T.texty(250000, 11), T.ascii_random(1300000, 12), T.runs(200000, 13)
+    z = bz2.compress(a, 1) + bz2.compress(b, 9) + bz2.compress(c3, 3)
+    assert B().decompressFile(z, None, True) == a + b + c3
+    assert B().decompressFile(z, None, True) == O.bzip2_decompress(z, multistream=True)
+    # a block longer than its own member's limit is still a data error: level byte of a level-9 stream patched to 1
+    big = bytearray(bz2.compress(T.ascii_random(400000, 14), 9))
+    big[3] = ord("1")
+    got, exp = _both(bytes(big))
+    assert got == exp and got[0] == "err"
+
+
 def _both(z, **kw):
     from compressjs_b200 import Bzip2Error
     try:
