@@ -164,32 +164,33 @@ __device__ __forceinline__ void bc_enc_code_fast(bc_enc* rc, u32 sy_f, u32 lt_f,
   if (lt_f + sy_f < tot_f) rc->range = r * sy_f; else rc->range -= tmp;
 }
 __global__ void __launch_bounds__(32) k_bwtc_code(BwtcState* st, const u64* __restrict__ triples, const u32* __restrict__ tcount, u32 nblk, u32 tcap) {
+  __shared__ uint4 s_t[2][32];   // (sy, lt, tot, reciprocal) of a batch of 32 symbols, double buffered
   const u32 lane = threadIdx.x;
-  // every lane runs the same recurrence on its own copy of the coder state (one instruction stream, no divergence);
-  // the triple of step j is broadcast from lane j, so the shuffles of later steps issue ahead of the serial chain.
-  // Only lane 0's copy writes bytes.
   bc_enc rc = st->rc;
-  if (lane) rc.cap = 0;  // bc_out of the other lanes stores nothing (their byte counter still advances in step)
   u32 overflow = st->overflow;
   for (u32 b = 0; b < nblk && !overflow; b++) {
     const u32 n = tcount[b];
     if (n > tcap) { overflow = 1; break; }
     const u64* t = triples + (size_t)b * tcap;
     u64 nxt = lane < n ? t[lane] : 0ull;        // one batch ahead: the load latency hides behind the serial steps
-    for (u32 k0 = 0; k0 < n; k0 += 32) {
+    for (u32 k0 = 0, it = 0; k0 < n; k0 += 32, it++) {
       const u64 tr = nxt;
       if (k0 + 32 + lane < n) nxt = t[k0 + 32 + lane];
-      const u32 tot = (u32)(tr >> 42), sy = (u32)(tr & 0x1FFFFF), lt = (u32)((tr >> 21) & 0x1FFFFF);
-      const u32 mg = tot ? 0xFFFFFFFFu / tot : 0u;
-      const u32 cnt = min(32u, n - k0);
-      if (cnt == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-          bc_enc_code_fast(&rc, __shfl_sync(FULL_MASK, sy, j), __shfl_sync(FULL_MASK, lt, j), __shfl_sync(FULL_MASK, tot, j), __shfl_sync(FULL_MASK, mg, j));
-      } else {
-        for (u32 j = 0; j < cnt; j++)
-          bc_enc_code_fast(&rc, __shfl_sync(FULL_MASK, sy, j), __shfl_sync(FULL_MASK, lt, j), __shfl_sync(FULL_MASK, tot, j), __shfl_sync(FULL_MASK, mg, j));
+      const u32 tot = (u32)(tr >> 42);
+      s_t[it & 1][lane] = make_uint4((u32)(tr & 0x1FFFFF), (u32)((tr >> 21) & 0x1FFFFF), tot, tot ? 0xFFFFFFFFu / tot : 0u);
+      __syncwarp();
+      if (lane == 0) {
+        const u32 cnt = min(32u, n - k0);
+        const uint4* q = s_t[it & 1];
+        uint4 cur = q[0];
+        for (u32 j = 0; j < cnt; j++) {
+          const uint4 nx = q[(j + 1) & 31];     // fetched one step ahead of its use
+          bc_enc_code_fast(&rc, cur.x, cur.y, cur.z, cur.w);
+          cur = nx;
+        }
       }
+      // (no second barrier: the next batch goes to the other buffer, and lane 0 is past this one by the time the
+      // buffer is written again two batches later -- all lanes wait for lane 0 at the next __syncwarp)
     }
   }
   if (lane == 0) {

@@ -15,6 +15,7 @@ struct BlkInfo {
 struct Rle1Plan {
   DBuf<u32> tile_carry;   // per raw tile: length (mod 255) of the run entering the tile
   DBuf<u64> tile_prefix;  // per raw tile: W(tile start)
+  DBuf<u8> tile_plain;    // per raw tile: 1 = no four equal bytes in a row in or into the tile (RLE1 copies it byte for byte)
   DBuf<BlkInfo> blocks;   // device block table
   std::vector<BlkInfo> h_blocks;
   size_t nblocks = 0;      // entries of h_blocks

@@ -166,7 +166,7 @@ __device__ void tile_view(const u8* __restrict__ in, u64 N, u64 tstart, u32 carr
 // ---- A ---------------------------------------------------------------------------------
 // Fast path: a tile that contains no four equal consecutive bytes (looking 3 bytes back into the
 // previous tile) emits exactly one output byte per input byte, so its summary needs no scans.
-__global__ void __launch_bounds__(RT_THREADS) k_rle_summary(const u8* __restrict__ in, u64 N, TileSum* __restrict__ sums) {
+__global__ void __launch_bounds__(RT_THREADS) k_rle_summary(const u8* __restrict__ in, u64 N, TileSum* __restrict__ sums, u8* __restrict__ plain) {
   __shared__ TileScratch sc;
   __shared__ u32 lastw[RT_THREADS];
   const u64 t = blockIdx.x;
@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rle_summary(const u8* __restrict
         while (trail < 4 && in[tstart + len - 1 - trail] == s.lc) trail++;
         s.lead = lead; s.trail = trail; s.allsame = 0; s.rest = len - lead; s.pad = 0;
         sums[t] = s;
+        plain[t] = 1;
       }
       return;
     }
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rle_summary(const u8* __restrict
   TileView v;
   tile_view(in, N, tstart, 0, sc, v);
   if (threadIdx.x == 0) {
+    plain[t] = 0;
     TileSum s;
     s.fc = in[tstart];
     s.lc = in[tstart + v.len - 1];
@@ -640,10 +642,11 @@ k_rle_blocks(const u8* __restrict__ in, u64 N, u32 BS, const u32* __restrict__ c
 
 // ---- D ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RT_THREADS)
-k_rle_emit(const u8* __restrict__ in, u64 N, const u32* __restrict__ carry, const u64* __restrict__ prefix,
+k_rle_emit(const u8* __restrict__ in, u64 N, const u32* __restrict__ carry, const u64* __restrict__ prefix, const u8* __restrict__ plain,
            const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u64* __restrict__ tile_base, u8* __restrict__ T) {
   __shared__ TileScratch sc;
   __shared__ u32 s_k;
+  __shared__ __align__(16) u8 stage[RLE_TILE + 32];
   // which block does this CTA work for?  tile_base[k] = first CTA of block (first+k)
   if (threadIdx.x == 0) {
     u32 lo = 0, hi = count;
@@ -658,10 +661,48 @@ k_rle_emit(const u8* __restrict__ in, u64 N, const u32* __restrict__ carry, cons
   const BlkInfo bi = blocks[first + kk];
   const u64 t = bi.s / RLE_TILE + (blockIdx.x - tile_base[kk]);
   const u64 tstart = t * RLE_TILE;
-  TileView v;
-  tile_view(in, N, tstart, carry[t], sc, v);
   u8* Tb = T + ((size_t)kk << SEG_SHIFT);
   const u64 Pt = prefix[t];
+  if (plain[t]) {
+    // No run reaches four bytes in or into this tile: every raw byte emits itself (w = 1), whatever the phase, so the
+    // tile's part of the block is a byte copy to output position (x - x0) + o0.  Staged in shared memory at the
+    // destination's alignment, stored 16 bytes at a time.
+    const u64 remain = N - tstart;
+    const u32 len = remain < RLE_TILE ? (u32)remain : RLE_TILE;
+    const u64 x0 = bi.s > tstart ? bi.s : tstart;                                    // first raw byte of the block in this tile
+    const u64 x1 = (bi.e < tstart + len) ? bi.e : tstart + len;
+    if (x0 >= x1) return;
+    // output position of x0 (same formulas as the general path below, with w = 1 everywhere)
+    const u64 o0 = x0 < bi.b ? (x0 - bi.s) : (u64)bi.ofs + (Pt + (x0 - tstart) - bi.Wb);
+    if (o0 >= bi.n) return;
+    const u32 cnt = (u32)min((u64)(x1 - x0), (u64)bi.n - o0);
+    const u32 fo = (u32)(o0 & 15u);
+    const u8* src = in + x0;
+    for (u32 i = threadIdx.x * 16u; i < cnt; i += RT_THREADS * 16u) {
+      if (i + 16u <= cnt && ((((size_t)src) + i) & 15u) == 0) {
+        const uint4 q = *reinterpret_cast<const uint4*>(src + i);
+        const u32 a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++) stage[fo + i + j] = (u8)(a[j >> 2] >> ((j & 3) * 8));
+      } else {
+        const u32 e = min(i + 16u, cnt);
+        for (u32 x = i; x < e; x++) stage[fo + x] = src[x];
+      }
+    }
+    __syncthreads();
+    const u32 last = fo + cnt;
+    u8* dst = Tb + (o0 - fo);   // 16-byte aligned
+    for (u32 c16 = threadIdx.x * 16u; c16 < last; c16 += RT_THREADS * 16u) {
+      if (c16 >= fo && c16 + 16u <= last) *reinterpret_cast<uint4*>(dst + c16) = *reinterpret_cast<const uint4*>(stage + c16);
+      else {
+        const u32 e = min(c16 + 16u, last);
+        for (u32 x = max(c16, fo); x < e; x++) dst[x] = stage[x];
+      }
+    }
+    return;
+  }
+  TileView v;
+  tile_view(in, N, tstart, carry[t], sc, v);
   u32 run = v.excl;
   for (u32 j = 0; j < v.cnt; j++) {
     const u64 x = tstart + threadIdx.x * RT_PER + j;
@@ -858,7 +899,8 @@ void rle1_plan_ex(Ctx& c, const u8* d_in, size_t n, int level, Rle1Plan& plan, l
     DBuf<u64> dagg(c, 4);
     plan.tile_carry.alloc(c, ntiles);
     plan.tile_prefix.alloc(c, ntiles + 1);
-    k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums);
+    plan.tile_plain.alloc(c, ntiles);
+    k_rle_summary<<<(unsigned)ntiles, RT_THREADS, 0, c.stream>>>(d_in, n, sums, plan.tile_plain);
     KLAUNCH(c); KCHECK();
     static const bool force_groups = getenv("B2_RLE_SCAN_GROUPS") != nullptr;  // test hook: multi-CTA scan on small inputs too
     if (ntiles <= 4 * RG_TILES && !force_groups) {
@@ -960,7 +1002,7 @@ void rle1_materialize(Ctx& c, const u8* d_in, size_t n, const Rle1Plan& plan, si
   c.to_device(dpb, pbase.data(), 8 * (count + 1));
   c.to_device(d_n, hn.data(), 4 * count);
   CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * count, c.stream));
-  k_rle_emit<<<(unsigned)tt, RT_THREADS, 0, c.stream>>>(d_in, n, plan.tile_carry, plan.tile_prefix, plan.blocks, (u32)first, (u32)count, dtb, d_T);
+  k_rle_emit<<<(unsigned)tt, RT_THREADS, 0, c.stream>>>(d_in, n, plan.tile_carry, plan.tile_prefix, plan.tile_plain, plan.blocks, (u32)first, (u32)count, dtb, d_T);
   KLAUNCH(c); KCHECK();
   k_crc_pieces<<<(unsigned)((pp + 255) / 256), 256, 0, c.stream>>>(d_in, plan.blocks, (u32)first, (u32)count, dpb, pp, acc);
   KLAUNCH(c); KCHECK();
