@@ -16,6 +16,8 @@
 //
 // Contract: lib/BWT.js:372-417 (bwtransform2), same result as the LSD path.  Algorithmic HBM bytes per text byte:
 // 1 (histogram) + 1 + 8 (scatter) + 8 + 1 (bucket sort) = 19.
+#include <cstdlib>
+#include <type_traits>
 #include "ctx.h"
 #include "tma.cuh"
 #include "bwt_msd.h"
@@ -65,7 +67,8 @@ __device__ __forceinline__ u32 lut4(const u8* lut, u32 w) {
   return (u32)lut[w & 0xff] | ((u32)lut[(w >> 8) & 0xff] << 8) | ((u32)lut[(w >> 16) & 0xff] << 16) | ((u32)lut[w >> 24] << 24);
 }
 
-__global__ void __launch_bounds__(MSD_THREADS, MSD_CTAS_PER_SM)
+template <int CTAS>
+__global__ void __launch_bounds__(MSD_THREADS, CTAS)
 k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, const u8* __restrict__ lut, const MsdBlk* __restrict__ blk,
               u32* __restrict__ cursor, u64* __restrict__ rec_out, const u32* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -107,6 +110,9 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
   }
   __syncthreads();
   const u32 a = mb.a, a2 = mb.a2, S_lo = (u32)mb.S, S_hi = (u32)(mb.S >> 32);
+  // the rest twice: full tiles (all but the last of a block) carry no per-record bounds checks
+  auto body = [&](auto full_c) {
+  constexpr bool full = decltype(full_c)::value;
   u32 key[MSD_ITEMS], slot[MSD_ITEMS / 2];
   {
     const uint4 k0 = *reinterpret_cast<const uint4*>(s.rk + tid * 16);
@@ -125,7 +131,7 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
       key[j] = k * S_hi + __umulhi(k, S_lo);             // spread over 32 bits (order preserving, injective)
       const u32 d = (rw[j >> 2] >> (8 * (j & 3))) & 0xffu;
       u32 sl = 0;
-      if (tid * MSD_ITEMS + j < count) sl = atomicAdd(&s.cnt[d], 1u);
+      if (full || tid * MSD_ITEMS + j < count) sl = atomicAdd(&s.cnt[d], 1u);
       if (j & 1) slot[j >> 1] |= sl << 16; else slot[j >> 1] = sl;
     }
   }
@@ -148,7 +154,7 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
 #pragma unroll
     for (int j = 0; j < MSD_ITEMS; j++) {
       const u32 d = (rw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-      if (tid * MSD_ITEMS + j < count) {
+      if (full || tid * MSD_ITEMS + j < count) {
         const u32 sl = (j & 1) ? (slot[j >> 1] >> 16) : (slot[j >> 1] & 0xffffu);
         s.rec[s.cnt[d] + sl] = ((u64)key[j] << 32) | (u64)((prev << SEG_SHIFT) | (d << 12) | (tid * MSD_ITEMS + j));
       }
@@ -161,13 +167,15 @@ k_msd_scatter(const u8* __restrict__ T, const u32* __restrict__ seg_n, u32 tps, 
 #pragma unroll
   for (int k = 0; k < MSD_ITEMS; k++) {
     const u32 p = k * MSD_THREADS + tid;
-    if (p < count) {
+    if (full || p < count) {
       const u64 rvv = s.rec[p];
       const u32 lw = (u32)rvv;
       const u32 low = (lw & 0x0ff00000u) | (start + (lw & 0xfffu));
       out[(int)p + s.gdst[(lw >> 12) & 0xffu]] = (rvv & 0xffffffff00000000ull) | low;
     }
   }
+  };
+  if (count == MSD_TILE) body(std::true_type{}); else body(std::false_type{});
 }
 
 // ---------------------------------------------------------------------------------------
@@ -450,10 +458,12 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
 // ---------------------------------------------------------------------------------------
 void bwt_msd_launch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, u32 nblk, u32 n_max, u64 n_total, const u32* d_hist, u64* d_rec,
                     u32* d_pidx, u32* d_tie_head, u32* d_tie_idx, u32* d_ctl) {
-  static int sms = 0;
+  static int sms = 0, scatter_ctas = MSD_CTAS_PER_SM;
   if (!sms) {
     CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
-    CUDA_CHECK(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdScatterSmem)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_msd_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdScatterSmem)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_msd_scatter<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdScatterSmem)));
+    if (const char* e = getenv("B2_MSD_CTAS")) scatter_ctas = atoi(e) == 4 ? 4 : 5;  // tuning knob: registers (64 vs 48) against occupancy
     CUDA_CHECK(cudaFuncSetAttribute(k_msd_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsdBucketSmem)));
   }
   DBuf<u32> bstart(c, (size_t)nblk * 256), cursor(c, (size_t)nblk * 256);
@@ -465,7 +475,8 @@ void bwt_msd_launch(Ctx& c, const u8* d_T, u8* d_U, const u32* d_n, u32 nblk, u3
   const u32 tps = (n_max + MSD_TILE - 1) / MSD_TILE;
   {
     size_t ev = c.begin(ST_MSD_SCATTER);
-    k_msd_scatter<<<tps * nblk, MSD_THREADS, sizeof(MsdScatterSmem), c.stream>>>(d_T, d_n, tps, lut, blk, cursor, d_rec, d_ctl);
+    if (scatter_ctas == 4) k_msd_scatter<4><<<tps * nblk, MSD_THREADS, sizeof(MsdScatterSmem), c.stream>>>(d_T, d_n, tps, lut, blk, cursor, d_rec, d_ctl);
+    else k_msd_scatter<5><<<tps * nblk, MSD_THREADS, sizeof(MsdScatterSmem), c.stream>>>(d_T, d_n, tps, lut, blk, cursor, d_rec, d_ctl);
     c.end(ev);
     KLAUNCH(c); KCHECK();
     ev = c.begin(ST_MSD_BUCKET);

@@ -748,6 +748,7 @@ __host__ __device__ __forceinline__ u32 gf_mulmod(u32 a, u32 b) {
 struct CrcConsts {
   u32 table[256];
   u32 pow[48];  // pow[i] = x^(8 * 2^i) mod P
+  u32 slice[3][256];  // slice[k][i] = table value after k+1 further zero bytes: four bytes per step (slicing by 4)
 };
 static CrcConsts make_crc_consts() {
   CrcConsts c;
@@ -756,6 +757,11 @@ static CrcConsts make_crc_consts() {
     for (int k = 0; k < 8; k++) v = (v & 0x80000000u) ? (v << 1) ^ CRC_POLY : (v << 1);
     c.table[i] = v;
   }
+  for (int k = 0; k < 3; k++)
+    for (u32 i = 0; i < 256; i++) {
+      const u32 prev = k ? c.slice[k - 1][i] : c.table[i];
+      c.slice[k][i] = (prev << 8) ^ c.table[prev >> 24];
+    }
   c.pow[0] = 0x100;  // x^8
   for (int i = 1; i < 48; i++) c.pow[i] = gf_mulmod(c.pow[i - 1], c.pow[i - 1]);
   return c;
@@ -788,8 +794,11 @@ __host__ __device__ __forceinline__ u64 crc_piece_count(u64 s, u64 e, u32 mis) {
 __global__ void __launch_bounds__(256)
 k_crc_pieces(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 first, u32 count, const u64* __restrict__ piece_base,
              u64 total_pieces, u32* __restrict__ acc) {
-  __shared__ u32 tab[256];
+  __shared__ u32 tab[256], t1[256], t2[256], t3[256];
   tab[threadIdx.x] = c_crc.table[threadIdx.x];
+  t1[threadIdx.x] = c_crc.slice[0][threadIdx.x];
+  t2[threadIdx.x] = c_crc.slice[1][threadIdx.x];
+  t3[threadIdx.x] = c_crc.slice[2][threadIdx.x];
   __syncthreads();
   const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total_pieces) return;
@@ -812,9 +821,11 @@ k_crc_pieces(const u8* __restrict__ in, const BlkInfo* __restrict__ blocks, u32 
       uint4 q = *reinterpret_cast<const uint4*>(p + i);
       u32 a[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int w = 0; w < 4; w++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) crc = (crc << 8) ^ tab[((crc >> 24) ^ (a[w] >> (8 * b))) & 0xff];
+      for (int w = 0; w < 4; w++) {
+        // four message bytes per dependent step (the stream is MSB first: byte 0 of the little-endian word comes first)
+        const u32 x = crc ^ __byte_perm(a[w], 0, 0x0123);
+        crc = t3[x >> 24] ^ t2[(x >> 16) & 0xff] ^ t1[(x >> 8) & 0xff] ^ tab[x & 0xff];
+      }
     }
   } else {
     for (u32 i = 0; i < len; i++) crc = (crc << 8) ^ tab[((crc >> 24) ^ p[i]) & 0xff];
