@@ -304,7 +304,7 @@ def bwtc_leg(L, _native, torch, host, mb, check_blocks):
     res = {"workload": "BWTC -9 on the first %d MiB of the config-2 buffer (b2_bwtc_compress, host buffers)" % (n >> 20), "bytes": n,
            "encode_MBps": n / dt / 1e6, "wall_s": round(dt, 3), "compressed_bytes": nn.value, "ms_total_gpu": st["ms_total"],
            "stages_ms": {"bwt": st["ms_bwt"], "mtf": st["ms_mtf"], "model": st["ms_huff"], "coder": st["ms_pack"]},
-           "note": "model = one thread per block (parallel over blocks); coder = ONE thread per file (the range recurrence is serial): stages_ms.coder bounds the path"}
+           "note": "model = one warp per block (Fenwick tree in shared memory; blocks in parallel); coder = ONE serial recurrence per file (one warp, lane 0 carries it): stages_ms.coder bounds the path"}
     if check_blocks:
         from oracle import oracle as O
         k = min(n, check_blocks * 900000)

@@ -599,14 +599,20 @@ static int decode_common(const uint8_t* in, size_t n, int multistream, bool sing
       if (n) CUDA_CHECK(cudaMemcpyAsync(din, in, n, cudaMemcpyHostToDevice, c.stream));
     }
     u8* dres = nullptr;
+    struct DresGuard { Ctx& c; u8*& p; ~DresGuard() { if (p) { c.dfree(p); p = nullptr; } } } dres_guard{c, dres};  // also on exceptions
     rc = bzip2_decompress_device(c, din, n, multistream, nullptr, 0, &produced, single, bitpos, tp, tl, &dres);
     if (rc == 0 && out) {
       host = pinned_alloc(produced);
-      StageScope s(c, ST_D2H);
-      if (produced) CUDA_CHECK(cudaMemcpyAsync(host, dres, produced, cudaMemcpyDeviceToHost, c.stream));
+      try {
+        StageScope s(c, ST_D2H);
+        if (produced) CUDA_CHECK(cudaMemcpyAsync(host, dres, produced, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+      } catch (...) {
+        pinned_release(host);
+        throw;
+      }
     }
     c.sync();
-    if (dres) c.dfree(dres);
   }
   c.sync();
   c.collect();

@@ -992,6 +992,28 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   S.lo = (size_t)rank * nb_all / (size_t)world;
   S.hi = (size_t)(rank + 1) * nb_all / (size_t)world;
   const size_t nb = S.hi - S.lo;
+  {
+    // every block of the own share keeps 2 MiB (L column + count-byte classes) until the stream is assembled, and a batch
+    // of up to 2048 blocks needs ~19 MiB of scratch per block: say so instead of failing inside an allocation
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t need = nb * ((size_t)2 << 20) + std::min<size_t>(nb, std::max(c.bwt_batch, 2048u)) * ((size_t)19 << 20) + n;
+      // memory the stream-ordered pool holds but does not use is available too
+      uint64_t reserved = 0, used = 0;
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+      }
+      cudaGetLastError();
+      if (need > free_b + (size_t)(reserved > used ? reserved - used : 0)) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "stream of %zu blocks needs about %zu MiB of device memory for one call (%zu MiB free): decode it in parts "
+                                  "(Bzip2.table + decompressBlock) or over several GPUs (decompress_file_sharded)", nb, need >> 20, free_b >> 20);
+        throw B2Error{B2_ERR_CUDA, msg};
+      }
+    } else cudaGetLastError();
+  }
   S.dcand.alloc(c, nb_all ? nb_all : 1);
   S.dres.alloc(c, nb ? nb : 1);
   S.rle.alloc(c, (nb ? nb : 1) << SEG_SHIFT);

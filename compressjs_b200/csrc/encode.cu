@@ -568,6 +568,12 @@ void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, 
     // block on the next chunk we need, then take every further chunk that has landed meanwhile
     if (have < nch) { CUDA_CHECK(cudaEventSynchronize(ev[have])); have++; }
     while (have < nch && cudaEventQuery(ev[have]) == cudaSuccess) have++;
+    // a batch wants to be full (the per-block kernels run one CTA per block): unless the upload is over, wait until a
+    // whole batch worth of input is here -- the copy engine delivers it faster than the GPU encodes it
+    while (have < nch && have * CH - resume < (size_t)c.bwt_batch * (size_t)level * 100000u) {
+      CUDA_CHECK(cudaEventSynchronize(ev[have]));
+      have++;
+    }
     const size_t avail = have == nch ? n : have * CH;
     const bool last = avail == n;
     mark("chunks arrived", have);

@@ -45,7 +45,9 @@ void b2_free(void* p);
 /* ---- compressjs.Bzip2 (lib/Bzip2.js) -------------------------------------------- */
 /* Bzip2.compressFile(input, output, level)            lib/Bzip2.js:879-929 */
 int b2_bzip2_compress(const uint8_t* in, size_t n, int level, uint8_t** out, size_t* out_n);
-/* Bzip2.decompressFile(input, output, multistream)    lib/Bzip2.js:454-481 */
+/* Bzip2.decompressFile(input, output, multistream)    lib/Bzip2.js:454-481
+ * Members of a multistream file may have different levels.  On an error nothing is returned (the reference hands the
+ * blocks in front of the error to its output stream first); one call keeps ~2 MiB per block of the file on the device. */
 int b2_bzip2_decompress(const uint8_t* in, size_t n, int multistream, uint8_t** out, size_t* out_n);
 /* Bzip2.decompressBlock(input, bitPos, output)        lib/Bzip2.js:482-503 */
 int b2_bzip2_decompress_block(const uint8_t* in, size_t n, uint64_t bitpos, uint8_t** out, size_t* out_n);
@@ -54,7 +56,8 @@ int b2_bzip2_decompress_block(const uint8_t* in, size_t n, uint64_t bitpos, uint
 int b2_bzip2_table(const uint8_t* in, size_t n, int multistream, uint64_t** bitpos, uint32_t** sizes, size_t* count);
 
 /* ---- compressjs.BWT (lib/BWT.js) ------------------------------------------------- */
-/* BWT.bwtransform2(T, U, n, 256) -> pidx  (cyclic)    lib/BWT.js:372-417 */
+/* BWT.bwtransform2(T, U, n, 256) -> pidx  (cyclic)    lib/BWT.js:372-417
+ * n is limited to 900 000 (the largest bzip2 block; the reference has no limit): longer strings return B2_ERR_BAD_ARG. */
 int32_t b2_bwt_cyclic(const uint8_t* T, uint8_t* U, int32_t n);
 /* many independent blocks at once (what compressFile does per block, batched):
  * block k is T + offs[k], length lens[k] (each <= 900000); U gets the same layout;
