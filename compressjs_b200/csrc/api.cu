@@ -24,8 +24,8 @@ void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out);
 size_t bwtc_bound(size_t n);
 void bwtc_compress_device(Ctx& c, const u8* d_in, size_t n, int level, u8* d_out, size_t out_cap, size_t* out_n);
 void bwtc_decompress_device(Ctx& c, const u8* d_in, size_t n, const u8* h_head, size_t head_n, u8* d_out, size_t out_cap, size_t* out_n);
-void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, u8* d_out, size_t out_cap, u8* h_out, size_t* out_n,
-                         bool pinned_in);
+void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, size_t win, u8* d_out, size_t out_cap, u8* h_out,
+                         size_t h_out_cap, size_t* out_n, bool pinned_in);
 void dec_shard_open(Ctx& c, const u8* d_in, size_t n, int rank, int world, u64* info);
 void dec_shard_export(u64* buf);
 int dec_shard_finish(Ctx& c, const u64* all, int multistream, u8* d_out, size_t out_cap, u64* res);
@@ -465,12 +465,18 @@ int b2_bzip2_compress(const uint8_t* in, size_t n, int level, uint8_t** out, siz
     void* host = pinned_alloc(cap);
     try {
       StageScope tot(c, ST_TOTAL);
-      DBuf<u8> din(c, n ? n : 1), dout(c, cap);
+      // Inputs above the streaming window pass through the device in windows (bounded device memory: files larger than
+      // HBM); $B2_STREAM_WINDOW sets the window in bytes (default 8 GiB, at least 64 MiB -- a test hook allows less).
+      size_t win = (size_t)8 << 30;
+      if (const char* e = getenv("B2_STREAM_WINDOW")) { const long long v = atoll(e); if (v >= (1 << 20)) win = (size_t)v; }
+      if (win > n) win = n;
+      const size_t dcap = win < n ? b2_bzip2_bound(win) + 64 : cap;
+      DBuf<u8> din(c, win ? win : 1), dout(c, dcap);
       c.sync();  // the buffers are used from the copy streams as well
       cudaPointerAttributes pa;
       const bool pinned_in = n && cudaPointerGetAttributes(&pa, in) == cudaSuccess && pa.type == cudaMemoryTypeHost;
       cudaGetLastError();
-      bzip2_compress_host(c, in, n, level, din, dout, cap, (u8*)host, &produced, pinned_in);
+      bzip2_compress_host(c, in, n, level, din, win, dout, dcap, (u8*)host, cap, &produced, pinned_in);
     } catch (...) {
       pinned_release(host);
       throw;

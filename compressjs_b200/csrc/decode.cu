@@ -616,13 +616,6 @@ __global__ void k_ibwt_keys(const u8* __restrict__ tt, const u32* __restrict__ s
   if (g >= nslots) return;
   if ((g & SEG_MASK) < seg_n[g >> SEG_SHIFT]) key[g] = tt[g];
 }
-// P[j] = T[j] << 8 | L[j]   (lib/Bzip2.js:370-381: dbuf[j] low byte = L column, high bits = next row)
-__global__ void k_ibwt_pack(const u8* __restrict__ tt, const u32* __restrict__ tvec, const u32* __restrict__ seg_n, u32 nslots, u32* __restrict__ P) {
-  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nslots) return;
-  if ((g & SEG_MASK) < seg_n[g >> SEG_SHIFT]) P[g] = ((tvec[g] & SEG_MASK) << 8) | tt[g];
-}
-
 #define IB_SHIFT 7
 #define IB_STEP (1u << IB_SHIFT)
 #define IB_SEGS (SEG_SIZE / IB_STEP + 1)  // sampled rows per block + the start row
@@ -1072,14 +1065,12 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
       if (nmax) {
         StageScope ss(c, ST_IBWT);
         CUDA_CHECK(cudaMemcpyAsync(dn, hn.data(), cnt * 4, cudaMemcpyHostToDevice, c.stream));
-        const u32 nslots = cnt << SEG_SHIFT;
-        u32 *kin = keyA, *kout = keyB, *vin = valA, *vout = valB;
-        k_ibwt_keys<<<(nslots + 255) / 256, 256, 0, c.stream>>>(tt, dn, nslots, kin);
-        KLAUNCH(c); KCHECK();
-        radix_sort<u32>(c, kin, vin, kout, vout, dn, cnt, SEG_SHIFT, nmax, 0, 1, true, ntot);
-        u32* Pp = kout;  // the other key buffer is free now
-        k_ibwt_pack<<<(nslots + 255) / 256, 256, 0, c.stream>>>(tt, vin, dn, nslots, Pp);
-        KLAUNCH(c); KCHECK();
+        // T-vector: one stable counting-sort pass over the L column itself (byte keys, the values are the row numbers);
+        // the pass writes P[row] = successor << 8 | L[row] directly (radix.cuh: pack epilogue)
+        u8* kin = tt.p; u8* kout = nullptr;
+        u32 *vin = valA, *vout = valB;
+        u32* Pp = keyB;
+        radix_sort<u8>(c, kin, vin, kout, vout, dn, cnt, SEG_SHIFT, nmax, 0, 1, true, ntot, nullptr, tt.p, Pp);
         // all blocks of the batch walk together: the launch lasts as long as its longest segment walk, so fewer,
         // bigger launches win over keeping the packed T-vectors L2 resident (measured: 75 ms -> 36 ms per GiB)
         const u32 ib_sub = cnt;

@@ -302,6 +302,12 @@ __global__ void k_file_trailer(u32* out, const u64* state) {
   gput(out, p, 32, (u32)state[1]);
 }
 
+__global__ void k_rebase(u32* out, u64 word_index, u64* state, u32 bits_in_word) {
+  if (threadIdx.x || blockIdx.x) return;
+  out[0] = word_index ? out[word_index] : out[0];
+  state[0] = bits_in_word;
+}
+
 // compressFile on device buffers.  whole_file: header + all blocks + trailer.  Otherwise encodes
 // blocks [first_block, first_block+block_count) starting at bit `bit_phase` of d_out.
 // One output stream being written: the running bit position lives on the device (state[0]); blocks of one or more
@@ -321,7 +327,9 @@ struct EncSession {
   std::vector<u32> hn, hm, hp;
   std::vector<HuffBlk> hhb;
   std::vector<u64> hoff;
-  std::function<void(u64)> on_batch;  // called after every batch with the bit position reached (host synchronised)
+  std::function<void(u64)> on_batch;  // called after every batch with the bit position reached inside the window (host synchronised)
+  u64 bit_base = 0;    // bits of the stream in front of d_out[0] (streaming: the output buffer is a window that is drained and rebased)
+  u64 last_bit_end = 32;  // bit position (inside the window) behind the last block packed
 
   EncSession(Ctx& c_, int level_, u8* d_out_, size_t out_cap, bool whole_file_, int bit_phase_)
       : c(c_), level(level_), d_out(d_out_), cap_words(out_cap / 4), whole_file(whole_file_), bit_phase(bit_phase_) {
@@ -400,11 +408,25 @@ struct EncSession {
         const BlkInfo& bi = plan.h_blocks[first + k0 + b];
         t.n = (int32_t)bi.n; t.pidx = (int32_t)hp[b]; t.m = (int32_t)hm[b]; t.alpha = (int32_t)hhb[b].alpha;
         t.ngroups = (int32_t)hhb[b].ngroups; t.nsel = (int32_t)hhb[b].nsel; t.crc = all_crc[done0 + k0 + b]; t.pad = 0;
-        t.raw_start = raw_base + bi.s; t.raw_len = bi.e - bi.s; t.bit_start = hoff[b]; t.bit_len = hhb[b].body_bits;
+        t.raw_start = raw_base + bi.s; t.raw_len = bi.e - bi.s; t.bit_start = bit_base + hoff[b]; t.bit_len = hhb[b].body_bits;
       }
       c.stats.blocks += nb;
-      if (on_batch) on_batch(hoff[nb - 1] + hhb[nb - 1].body_bits);
+      last_bit_end = hoff[nb - 1] + hhb[nb - 1].body_bits;
+      if (on_batch) on_batch(last_bit_end);
     }
+  }
+  // Streaming: everything in front of the word that is still being filled has been handed out; that word moves to the
+  // start of the window, the rest of the window is cleared and the device cursor restarts behind the carried bits.
+  // `used_bytes` = how much of the window the batches since the last rebase may have touched.
+  void rebase(size_t used_bytes) {
+    const u64 wi = last_bit_end >> 5;
+    k_rebase<<<1, 32, 0, c.stream>>>(reinterpret_cast<u32*>(d_out), wi, state, (u32)(last_bit_end & 31));
+    KLAUNCH(c); KCHECK();
+    const size_t clear = std::min(cap_words * 4, (used_bytes + 7) & ~(size_t)3);
+    if (clear > 4) CUDA_CHECK(cudaMemsetAsync(d_out + 4, 0, clear - 4, c.stream));
+    bit_base += wi * 32;
+    last_bit_end &= 31;
+    c.sync();
   }
   // file trailer (whole files), final size; returns the bit position reached
   u64 finish(size_t* out_n) {
@@ -419,9 +441,9 @@ struct EncSession {
     c.sync();
     if (h_flag) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
     // whole files: trailer 48 + 32 bits, zero padded (lib/BitStream.js:68-73)
-    *out_n = whole_file ? (size_t)((h_state[0] + 80 + 7) / 8) : (size_t)((h_state[0] + 7) / 8);
+    *out_n = whole_file ? (size_t)((bit_base + h_state[0] + 80 + 7) / 8) : (size_t)((bit_base + h_state[0] + 7) / 8);
     c.trace = tr;
-    return h_state[0];
+    return bit_base + h_state[0];
   }
 };
 
@@ -520,8 +542,13 @@ void bzip2_plan_share(Ctx& c, const u8* d_buf, size_t n, int level, u64 st0, u64
 // input strictly forward), so every block but the last of a plan over the prefix that has arrived is final
 // and is encoded while the rest is still in flight.  Finished words of the output go back on a second copy
 // stream after every batch.  h_out must hold out_cap bytes (pinned).
-void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, u8* d_out, size_t out_cap, u8* h_out, size_t* out_n,
-                         bool pinned_in) {
+void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, size_t win, u8* d_out, size_t out_cap, u8* h_out,
+                         size_t h_out_cap, size_t* out_n, bool pinned_in) {
+  // d_in holds `win` bytes, d_out `out_cap` bytes (>= b2_bzip2_bound(win)).  win >= n: the whole file in one window (the
+  // usual case).  win < n: the input STREAMS through the device in windows -- every window is uploaded, planned and
+  // encoded like a small file whose last block is kept back (it may go on in the next window), the next window starts at
+  // the first raw byte that has not been consumed, and the output window is drained and rebased in between: device
+  // memory is bounded by the window, not by the file (lib/Bzip2.js:879-929 reads its input strictly forward, too).
   size_t CH = (size_t)64 << 20;
   if (const char* e = getenv("B2_H2D_CHUNK")) {  // test hook: small chunks exercise the prefix planning on small inputs
     const long long v = atoll(e);
@@ -532,8 +559,8 @@ void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, 
   auto mark = [&](const char* what, size_t v) {
     if (trace_host) fprintf(stderr, "[b2 host] %8.2f ms  %s %zu\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what, v);
   };
-  const size_t nch = (pinned_in && n > CH) ? (n + CH - 1) / CH : (n ? 1 : 0);
-  std::vector<cudaEvent_t> ev(nch);
+  const size_t max_ch = (std::min(win, n) + CH - 1) / CH + 1;
+  std::vector<cudaEvent_t> ev(max_ch);
   struct Cleanup {
     std::vector<cudaEvent_t>& ev; Ctx& c;
     ~Cleanup() {
@@ -542,59 +569,82 @@ void bzip2_compress_host(Ctx& c, const u8* h_in, size_t n, int level, u8* d_in, 
     }
   } cleanup{ev, c};
   for (auto& e : ev) { e = nullptr; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
-  c.copy_begin(c.h2d_stream, 0);
-  for (size_t i = 0; i < nch; i++) {
-    const size_t o = nch == 1 ? 0 : i * CH, len = nch == 1 ? n : std::min(CH, n - o);
-    CUDA_CHECK(cudaMemcpyAsync(d_in + o, h_in + o, len, cudaMemcpyHostToDevice, c.h2d_stream));
-    CUDA_CHECK(cudaEventRecord(ev[i], c.h2d_stream));
-  }
-  c.copy_end(c.h2d_stream, 0);
-  mark("uploads queued, chunks", nch);
   c.trace.clear();
   EncSession S(c, level, d_out, out_cap, true, 0);
   mark("session ready", 0);
-  size_t copied = 0;  // bytes of the output already on their way to the host
-  bool d2h_started = false;
+  size_t copied = 0;       // bytes of the current output window already on their way to the host
+  size_t host_base = 0;    // offset in h_out of the window's byte 0
+  bool d2h_started = false, h2d_started = false;
   S.on_batch = [&](u64 bit_end) {
     const size_t ready = (size_t)(bit_end / 32) * 4;  // whole words below the one still being filled
     if (ready > copied) {
+      if (host_base + ready > h_out_cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
       if (!d2h_started) { c.copy_begin(c.d2h_stream, 1); d2h_started = true; }
-      CUDA_CHECK(cudaMemcpyAsync(h_out + copied, d_out + copied, ready - copied, cudaMemcpyDeviceToHost, c.d2h_stream));
+      CUDA_CHECK(cudaMemcpyAsync(h_out + host_base + copied, d_out + copied, ready - copied, cudaMemcpyDeviceToHost, c.d2h_stream));
       copied = ready;
     }
   };
-  size_t resume = 0, have = 0;  // raw bytes planned so far / chunks known to have arrived
-  while (resume < n) {
-    // block on the next chunk we need, then take every further chunk that has landed meanwhile
-    if (have < nch) { CUDA_CHECK(cudaEventSynchronize(ev[have])); have++; }
-    while (have < nch && cudaEventQuery(ev[have]) == cudaSuccess) have++;
-    // a batch wants to be full (the per-block kernels run one CTA per block): unless the upload is over, wait until a
-    // whole batch worth of input is here -- the copy engine delivers it faster than the GPU encodes it
-    while (have < nch && have * CH - resume < (size_t)c.bwt_batch * (size_t)level * 100000u) {
-      CUDA_CHECK(cudaEventSynchronize(ev[have]));
-      have++;
+  size_t file_pos = 0;  // raw bytes consumed by finished blocks
+  for (bool first_window = true; first_window || file_pos < n; first_window = false) {
+    const size_t wlen = std::min(win, n - file_pos);
+    const bool last_window = file_pos + wlen == n;
+    if (!first_window) {
+      // the previous window's output is on its way: wait for it, then reuse both windows
+      CUDA_CHECK(cudaStreamSynchronize(c.d2h_stream));
+      S.rebase(copied + 8);
+      host_base += copied;
+      copied = 0;
     }
-    const size_t avail = have == nch ? n : have * CH;
-    const bool last = avail == n;
-    mark("chunks arrived", have);
-    Rle1Plan plan;
-    {
-      StageScope s(c, ST_RLE1);
-      rle1_plan(c, d_in + resume, avail - resume, level, plan);
+    const size_t nch = (pinned_in && wlen > CH) ? (wlen + CH - 1) / CH : (wlen ? 1 : 0);
+    if (!h2d_started) { c.copy_begin(c.h2d_stream, 0); h2d_started = true; }
+    for (size_t i = 0; i < nch; i++) {
+      const size_t o = nch == 1 ? 0 : i * CH, len = nch == 1 ? wlen : std::min(CH, wlen - o);
+      CUDA_CHECK(cudaMemcpyAsync(d_in + o, h_in + file_pos + o, len, cudaMemcpyHostToDevice, c.h2d_stream));
+      CUDA_CHECK(cudaEventRecord(ev[i], c.h2d_stream));
     }
-    const size_t nfinal = last ? plan.nblocks : (plan.nblocks ? plan.nblocks - 1 : 0);
-    mark("planned, final blocks", nfinal);
-    if (!nfinal) continue;  // the prefix holds less than one full block: wait for more
-    S.encode(d_in + resume, avail - resume, plan, 0, nfinal, resume);
-    mark("encoded", nfinal);
-    resume += plan.h_blocks[nfinal - 1].e;
+    c.copy_end(c.h2d_stream, 0);
+    mark("uploads queued, chunks", nch);
+    size_t resume = 0, have = 0;  // raw bytes of the window planned so far / chunks known to have arrived
+    bool progressed = false;
+    while (resume < wlen) {
+      // block on the next chunk we need, then take every further chunk that has landed meanwhile
+      if (have < nch) { CUDA_CHECK(cudaEventSynchronize(ev[have])); have++; }
+      while (have < nch && cudaEventQuery(ev[have]) == cudaSuccess) have++;
+      const size_t avail = have == nch ? wlen : have * CH;
+      const bool last = avail == wlen;
+      mark("chunks arrived", have);
+      Rle1Plan plan;
+      {
+        StageScope s(c, ST_RLE1);
+        rle1_plan(c, d_in + resume, avail - resume, level, plan);
+      }
+      // only the very end of the FILE closes a short block; the last block of any other prefix may still grow
+      const size_t nfinal = (last && last_window) ? plan.nblocks : (plan.nblocks ? plan.nblocks - 1 : 0);
+      mark("planned, final blocks", nfinal);
+      if (!nfinal) {
+        if (last) break;  // the rest of this window is less than one block: it opens the next window
+        continue;         // the prefix holds less than one full block: wait for more
+      }
+      S.encode(d_in + resume, avail - resume, plan, 0, nfinal, file_pos + resume);
+      mark("encoded", nfinal);
+      resume += plan.h_blocks[nfinal - 1].e;
+      progressed = true;
+      if (last && !last_window) break;
+    }
+    if (!last_window && !progressed) throw B2Error{B2_ERR_BAD_ARG, "streaming window too small: it does not hold one whole block (raise B2_STREAM_WINDOW)"};
+    file_pos += resume;
+    if (last_window) break;
+    CUDA_CHECK(cudaStreamSynchronize(c.h2d_stream));  // the next window overwrites d_in
   }
-  S.finish(out_n);
-  if (*out_n > out_cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
+  size_t total = 0;
+  S.finish(&total);
+  *out_n = total;
+  if (*out_n > h_out_cap) throw B2Error{B2_ERR_BAD_ARG, "output buffer too small for the compressed stream"};
   if (!d2h_started) c.copy_begin(c.d2h_stream, 1);
-  CUDA_CHECK(cudaMemcpyAsync(h_out + copied, d_out + copied, *out_n - copied, cudaMemcpyDeviceToHost, c.d2h_stream));
+  const size_t tail = *out_n - host_base;  // bytes of the last window, trailer included
+  CUDA_CHECK(cudaMemcpyAsync(h_out + host_base + copied, d_out + copied, tail - copied, cudaMemcpyDeviceToHost, c.d2h_stream));
   c.copy_end(c.d2h_stream, 1);
-  mark("finished, bytes left to download", *out_n - copied);
+  mark("finished, bytes left to download", tail - copied);
   CUDA_CHECK(cudaStreamSynchronize(c.d2h_stream));
   mark("download done", *out_n);
 }

@@ -90,7 +90,8 @@ template <typename KeyT, bool HAS_VALS>
 __global__ void __launch_bounds__(RP_THREADS)
 k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __restrict__ kout,
              u32* __restrict__ vout, const u32* __restrict__ seg_n, u32 tiles_per_seg, u32 seg_shift,
-             const u32* __restrict__ hist, u32 hist_seg_stride, u32 hist_off, u32 shift, u32* ticket, u32* status, int iota) {
+             const u32* __restrict__ hist, u32 hist_seg_stride, u32 hist_off, u32 shift, u32* ticket, u32* status, int iota,
+             const u8* __restrict__ pack_L = nullptr, u32* __restrict__ pack_P = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RadixSmem<KeyT, HAS_VALS>& s = *reinterpret_cast<RadixSmem<KeyT, HAS_VALS>*>(smem_raw);
   const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -210,8 +211,15 @@ k_radix_pass(const KeyT* __restrict__ kin, const u32* __restrict__ vin, KeyT* __
       const KeyT kk = s.key[p];
       const u32 d = (u32)(kk >> shift) & (RADIX - 1);
       const u32 dst = (u32)((int)p + s.gbase[d]);
-      ko[dst] = kk;
-      if (HAS_VALS) vo[dst] = s.val[p];
+      if (HAS_VALS && pack_P) {
+        // inverse-BWT epilogue (decode.cu): the record that sorts to row `dst` is the successor pointer of that row;
+        // P[row] = successor << 8 | L[row] (lib/Bzip2.js:370-381) -- the sorted keys and values themselves are not needed
+        const size_t row = ((size_t)seg << seg_shift) + dst;
+        pack_P[row] = ((s.val[p] & ((1u << seg_shift) - 1u)) << 8) | pack_L[row];
+      } else {
+        ko[dst] = kk;
+        if (HAS_VALS) vo[dst] = s.val[p];
+      }
     }
   }
 }

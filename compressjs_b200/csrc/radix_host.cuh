@@ -7,7 +7,8 @@
 // otherwise the per-pass histograms are computed by k_radix_hist from the keys.
 template <typename KeyT, bool HAS_VALS = true>
 static void radix_sort(Ctx& c, KeyT*& kin, u32*& vin, KeyT*& kout, u32*& vout, const u32* d_seg_n, u32 nseg, u32 seg_shift,
-                       u32 max_seg_n, u32 begin_bit, u32 npass, bool iota_first, u64 total_elems, const u32* shared_hist = nullptr) {
+                       u32 max_seg_n, u32 begin_bit, u32 npass, bool iota_first, u64 total_elems, const u32* shared_hist = nullptr,
+                       const u8* pack_L = nullptr, u32* pack_P = nullptr) {
   if (npass == 0 || total_elems == 0) return;
   static bool attr_set = false;  // per translation unit (kernels are instantiated per TU)
   if (!attr_set) {
@@ -34,7 +35,8 @@ static void radix_sort(Ctx& c, KeyT*& kin, u32*& vin, KeyT*& kout, u32*& vout, c
     size_t ev = c.begin(ST_RADIX);
     k_radix_pass<KeyT, HAS_VALS><<<(unsigned)ntiles, RP_THREADS, sizeof(RadixSmem<KeyT, HAS_VALS>), c.stream>>>(
         kin, vin, kout, vout, d_seg_n, tps, seg_shift, shared_hist ? shared_hist : hist.p, shared_hist ? RADIX : npass * RADIX,
-        shared_hist ? 0 : p * RADIX, begin_bit + p * RADIX_BITS, ticket.p + p, status.p + (size_t)p * ntiles * RADIX, iota);
+        shared_hist ? 0 : p * RADIX, begin_bit + p * RADIX_BITS, ticket.p + p, status.p + (size_t)p * ntiles * RADIX, iota,
+        (p + 1 == npass) ? pack_L : nullptr, (p + 1 == npass) ? pack_P : nullptr);
     c.end(ev);
     KLAUNCH(c); KCHECK();
     const u64 bytes = total_elems * (2 * sizeof(KeyT) + (HAS_VALS ? (iota ? 4 : 8) : 0));

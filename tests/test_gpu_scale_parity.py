@@ -94,3 +94,34 @@ def test_thousands_of_tiny_blocks_and_members():
     member = bz2.compress(b"hello, world\n", 9)
     cat = member * 1500
     assert Bzip2.decompressFile(cat, None, True) == b"hello, world\n" * 1500
+
+
+@pytest.mark.parametrize("level,window,pinned", [(1, 4 << 20, True), (9, 4 << 20, False), (5, 3 << 20, True)])
+def test_streaming_windows_reproduce_the_one_shot_stream(level, window, pinned, monkeypatch):
+    """b2_bzip2_compress with an input larger than its streaming window (B2_STREAM_WINDOW; production default 8 GiB): the
+    input passes through the device window by window, the output window is drained and rebased in between -- the stream
+    must be the reference stream (lib/Bzip2.js:879-929 reads its input strictly forward, block cuts do not care)."""
+    import ctypes as C
+    import torch
+    from compressjs_b200 import _native
+    L = _native.lib()
+    monkeypatch.setenv("B2_STREAM_WINDOW", str(window))
+    monkeypatch.setenv("B2_H2D_CHUNK", str(1 << 20))
+    data = T.ascii_random(9 << 20, 51) + T.runs(3 << 20, 52) + T.texty(7 << 20, 53) + b"q" * 700000 + T.ascii_random(2500000, 54)
+    if pinned:
+        buf = torch.empty(len(data), dtype=torch.uint8, pin_memory=True)
+        buf.numpy()[:] = np.frombuffer(data, dtype=np.uint8)
+        ptr = buf.data_ptr()
+    else:
+        arr = np.frombuffer(data, dtype=np.uint8)
+        ptr = arr.ctypes.data
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = L.b2_bzip2_compress(ptr, len(data), level, C.byref(out), C.byref(n))
+    assert rc == 0, _native.last_error()
+    got = bytes(np.ctypeslib.as_array(out, (n.value,)))
+    L.b2_free(out)
+    exp = O.bzip2_compress(data, level, threads=min(os.cpu_count() or 1, 16))
+    assert got == exp
+    tr = _native.last_trace()
+    assert sum(t.raw_len for t in tr) == len(data) and tr[0].raw_start == 0 and tr[0].bit_start == 32
+    assert all(a.bit_start + a.bit_len == b.bit_start for a, b in zip(tr, tr[1:]))
