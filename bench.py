@@ -366,7 +366,8 @@ def main():
     HALO = 4 << 20
     # weak scaling: the job is ONE stream of world x shard bytes.  One GPU: the whole input.  Several: every rank
     # holds (and uploads) only its own share plus a halo of the next share; the ranks exchange share summaries, cut
-    # and encode their blocks, and the fragments travel over NCCL straight into place on rank 0 (sharded.py).
+    # and encode their blocks; the finished fragments stay on their GPUs at their final bit positions (value), travel
+    # over NCCL straight into place on rank 0 (gathered) or into one shared host buffer (e2e) -- sharded.py.
     if world == 1:
         host = gen_ascii(shard, SEED)
     else:
@@ -386,12 +387,18 @@ def main():
             _check(L.b2_bzip2_compress_dev(d_in.data_ptr(), nbytes, LEVEL, d_out.data_ptr(), cap, C.byref(out_n)), "compress_dev", _native)
             state["comp"] = out_n.value
             return _native.stats()
-        out = SH.compress_shares(d_in, shard, LEVEL)
+        # the stream stays sharded like the input: every rank ends with its fragment at its final bit position
+        ss = SH.compress_shares(d_in, shard, LEVEL, keep_sharded=True)
         st = _native.stats()
-        if out is not None:
-            state["comp"] = out.numel()
-            state["out"] = out
+        state["ss"] = ss
+        state["comp"] = ss.total_bytes
         return st
+
+    def step_gathered():
+        # the same step followed by the NVLink gather of the pieces into one buffer on rank 0
+        out = SH.compress_shares(d_in, shard, LEVEL, keep_sharded=True).gather()
+        if out is not None:
+            state["out"] = out
 
     def step_e2e(check=False):
         if world == 1:
@@ -443,7 +450,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     if world > 1:
-        dev_ms = ev0.elapsed_time(ev1)  # includes the NCCL gather and the assembly on rank 0
+        dev_ms = ev0.elapsed_time(ev1)  # includes the summary / size exchanges and the shift to the final bit position
     clocks = sampler.stop(t0, t0 + wall) if rank == 0 else None
     comp_bytes = state["comp"]
     trace = _native.last_trace() if world == 1 else []
@@ -453,6 +460,22 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = t.tolist()
+
+    # ---- the same step with the pieces gathered on rank 0 (secondary figure; also feeds the parity check below) ----
+    gathered_ms = None
+    if world > 1:
+        step_gathered()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gsteps = max(1, min(args.steps, 3))
+        for _ in range(gsteps):
+            step_gathered()
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / gsteps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gathered_ms = float(tg.item())
 
     # ---- multi-rank parity: the stream assembled from the ranks' fragments == the one-GPU stream of the same input ----
     sharded_parity = None
@@ -572,6 +595,11 @@ def main():
         if world > 1:
             line["sharded_phases_ms_last_step_rank0"] = {k: round(v, 2) for k, v in SH.PHASES.items()}
             line["sharded_parity"] = sharded_parity
+            line["config"]["output"] = ("the finished stream stays sharded in HBM like the input: every rank holds its fragment at its final bit "
+                                        "position (sharded.ShardedStream); 'gathered' repeats the step with the pieces moved to rank 0 over NVLink, "
+                                        "e2e assembles them in one host buffer")
+            line["gathered"] = {"value": total_raw / (gathered_ms / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": gathered_ms,
+                                "what": "value's step + ShardedStream.gather(): one contiguous .bz2 in rank 0's HBM"}
             line["decode"] = sharded_decode
         if world == 1:
             if not args.no_cpu:

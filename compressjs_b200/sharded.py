@@ -174,12 +174,13 @@ class SharedHostBuffer:
             pass
 
 
-def place_fragments(frag, nbits, count, crcs, level, device, group=None, host_out=None):
+def place_fragments(frag, nbits, count, crcs, level, device, group=None, host_out=None, keep_sharded=False):
     """Every rank contributes a fragment (uint8 tensor starting at bit 0, nbits long) with `count` blocks and their
     CRCs; returns the complete .bz2 stream on rank 0 (None elsewhere).  The interior bytes of every fragment are
     received directly at their final byte offset of the output.  With host_out (a SharedHostBuffer's tensor, the same
     memory on every rank) the stream is assembled in host memory instead: every rank downloads its own fragment into
-    place and rank 0 gets the stream's length back."""
+    place and rank 0 gets the stream's length back.  With keep_sharded nothing moves: every rank gets a ShardedStream
+    (its piece at its final bit position; .gather() finishes the job when one GPU wants the whole stream)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     t0 = time.perf_counter()
@@ -244,51 +245,73 @@ def place_fragments(frag, nbits, count, crcs, level, device, group=None, host_ou
         hb[:4] = np.frombuffer(b"BZh" + bytes([0x30 + level]), dtype=np.uint8)
         _tick("edges_trailer", t0)
         return (total_bits + 7) // 8
-    # 3. interiors: point to point into the output
-    ops, out = [], None
-    if rank == 0:
-        nbytes_out = (total_bits + 7) // 8
-        out = torch.empty(nbytes_out, dtype=torch.uint8, device=device)
-        for r in range(1, world):
-            if nbs[r] > 2:
+    st = ShardedStream(shifted, nb, offs, nbs, alle, meta, o, total_bits, level, rank, world, group, device)
+    if keep_sharded:
+        return st
+    return st.gather()
+
+
+class ShardedStream:
+    """The finished stream, left where it was produced: every rank holds its fragment already shifted to its final bit
+    position (`piece`, whose byte 0 is byte `offset` of the stream; neighbours share at most their edge bytes, which
+    combine by OR) and everything needed to finish it (edge bytes of all fragments, block counts and CRC folds).
+    gather() moves the pieces to rank 0 and returns the complete .bz2 there."""
+
+    def __init__(self, shifted, nb, offs, nbs, alle, meta, o, total_bits, level, rank, world, group, device):
+        self.piece, self.nb, self.offs, self.nbs, self.alle, self.meta = shifted, nb, offs, nbs, alle, meta
+        self.end_bit, self.total_bits, self.level = o, total_bits, level
+        self.rank, self.world, self.group, self.device = rank, world, group, device
+        self.offset = offs[rank] // 8
+        self.total_bytes = (total_bits + 7) // 8
+
+    def gather(self):
+        rank, world, group, device = self.rank, self.world, self.group, self.device
+        shifted, nb, offs, nbs, alle, meta, o = self.piece, self.nb, self.offs, self.nbs, self.alle, self.meta, self.end_bit
+        t0 = time.perf_counter()
+        # 3. interiors: point to point into the output
+        ops, out = [], None
+        if rank == 0:
+            out = torch.empty(self.total_bytes, dtype=torch.uint8, device=device)
+            for r in range(1, world):
+                if nbs[r] > 2:
+                    b0 = offs[r] // 8
+                    ops.append(dist.P2POp(dist.irecv, out[b0 + 1: b0 + nbs[r] - 1], r, group))
+            if nbs[0] > 2:
+                b0 = offs[0] // 8
+                out[b0 + 1: b0 + nbs[0] - 1] = shifted[1: nbs[0] - 1]
+        elif nb > 2:
+            ops.append(dist.P2POp(dist.isend, shifted[1: nb - 1].contiguous(), 0, group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        t0 = _tick("p2p_place", t0)
+        if rank != 0:
+            return None
+        # 4. header, edge bytes, trailer
+        edge = {}
+        for r in range(world):
+            if nbs[r]:
                 b0 = offs[r] // 8
-                ops.append(dist.P2POp(dist.irecv, out[b0 + 1: b0 + nbs[r] - 1], r, group))
-        if nbs[0] > 2:
-            b0 = offs[0] // 8
-            out[b0 + 1: b0 + nbs[0] - 1] = shifted[1: nbs[0] - 1]
-    elif nb > 2:
-        ops.append(dist.P2POp(dist.isend, shifted[1: nb - 1].contiguous(), 0, group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    t0 = _tick("p2p_place", t0)
-    if rank != 0:
-        return None
-    # 4. header, edge bytes, trailer
-    edge = {}
-    for r in range(world):
-        if nbs[r]:
-            b0 = offs[r] // 8
-            e0, e1 = int(alle[r][0]), int(alle[r][1])
-            edge[b0] = edge.get(b0, 0) | e0
-            edge[b0 + nbs[r] - 1] = edge.get(b0 + nbs[r] - 1, 0) | e1
-    scrc = 0
-    for m in meta:
-        scrc = rotl32(scrc, m[1]) ^ m[2]
-    b0t, tb = trailer_bytes(o, scrc)
-    tail = {}
-    for k, v in enumerate(tb):
-        tail[b0t + k] = v
-    fix = dict(tail)
-    for k, v in edge.items():
-        if k >= 4:
-            fix[k] = fix.get(k, 0) | v
-    hdr = list(b"BZh" + bytes([0x30 + level]))
-    idx = torch.tensor(list(range(4)) + list(fix.keys()), dtype=torch.int64, device=device)
-    val = torch.tensor(hdr + list(fix.values()), dtype=torch.uint8, device=device)
-    out[idx] = val
-    _tick("edges_trailer", t0)
-    return out
+                e0, e1 = int(alle[r][0]), int(alle[r][1])
+                edge[b0] = edge.get(b0, 0) | e0
+                edge[b0 + nbs[r] - 1] = edge.get(b0 + nbs[r] - 1, 0) | e1
+        scrc = 0
+        for m in meta:
+            scrc = rotl32(scrc, m[1]) ^ m[2]
+        b0t, tb = trailer_bytes(o, scrc)
+        tail = {}
+        for k, v in enumerate(tb):
+            tail[b0t + k] = v
+        fix = dict(tail)
+        for k, v in edge.items():
+            if k >= 4:
+                fix[k] = fix.get(k, 0) | v
+        hdr = list(b"BZh" + bytes([0x30 + self.level]))
+        idx = torch.tensor(list(range(4)) + list(fix.keys()), dtype=torch.int64, device=device)
+        val = torch.tensor(hdr + list(fix.values()), dtype=torch.uint8, device=device)
+        out[idx] = val
+        _tick("edges_trailer", t0)
+        return out
 
 
 def compress_sharded(encode_range, nblocks, level, device, group=None):
@@ -444,10 +467,11 @@ def _u64(v):
     return v + (1 << 64) if v < 0 else v
 
 
-def compress_shares(d_buf, share_len, level=9, group=None, host_out=None):
+def compress_shares(d_buf, share_len, level=9, group=None, host_out=None, keep_sharded=False):
     """Whole-file bzip2 encode when every rank holds only ITS share of the input: d_buf = CUDA uint8 tensor with the
     share (share_len bytes) followed by a halo (the first bytes of the next shares; empty on the last rank).  The shares
-    are contiguous in rank order.  Returns the stream on rank 0 (None elsewhere)."""
+    are contiguous in rank order.  Returns the stream on rank 0 (None elsewhere); with keep_sharded a ShardedStream on
+    every rank (the output stays sharded like the input; .gather() assembles it on rank 0)."""
     from . import _native
     L = _native.lib()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -505,7 +529,7 @@ def compress_shares(d_buf, share_len, level=9, group=None, host_out=None):
     enc = _range_encoder(L, d_buf, d_buf.numel(), level)
     frag, nbits, crcs = enc(first, count)
     _tick("encode_range", t0)
-    return place_fragments(frag, nbits, count, crcs, level, dev, group, host_out)
+    return place_fragments(frag, nbits, count, crcs, level, dev, group, host_out, keep_sharded)
 
 
 def share_bounds(n, rank, world, halo):

@@ -76,6 +76,45 @@ def _worker_host(rank, world, port, level, n, seed, q):
     dist.destroy_process_group()
 
 
+def _worker_kept(rank, world, port, level, n, seed, q):
+    """The stream is left sharded (ShardedStream): every rank's piece already sits at its final bit position; gather()
+    then assembles the same bytes on rank 0."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = T.texty(n, seed)
+    enc, nblocks, z = _oracle_encoder(data, level)
+    first, count = S.block_range(nblocks, rank, world)
+    frag, nbits, crcs = enc(first, count)
+    ss = S.place_fragments(frag, nbits, count, crcs, level, torch.device("cpu"), None, None, True)
+    ok = ss.total_bytes == len(z)
+    piece = ss.piece[: ss.nb].numpy()
+    ref = np.frombuffer(z, dtype=np.uint8)[ss.offset: ss.offset + ss.nb]
+    if ss.nb > 2:
+        ok = ok and bool((piece[1:-1] == ref[1:-1]).all())       # interior bytes are final
+    if ss.nb:
+        ok = ok and not (piece[0] & ~ref[0]) and not (piece[-1] & ~ref[-1])   # edge bytes: only bits of the stream
+    out = ss.gather()
+    if rank == 0:
+        ok = ok and bytes(out.numpy().tobytes()) == z
+    q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 450000), (3, 520000)])
+def test_stream_left_sharded_then_gathered(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_kept, args=(r, world, port, 1, n, 11, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    oks = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(oks)
+
+
 @pytest.mark.parametrize("world,n", [(2, 450000), (3, 520000)])
 def test_sharded_assembly_in_a_shared_host_buffer(world, n):
     ctx = mp.get_context("spawn")
