@@ -184,7 +184,7 @@ struct MsdBucketSmem {
   __align__(16) u32 cnt[MB_CELLS / 2];  // two 16-bit cell counters per word
   __align__(16) u8 outb[MB_BUF + 16];   // the bucket's slice of the BWT column, at the alignment (mod 16) it has in global memory
   u32 multi[MB_BUF / 2];                // queued cells, four lists (2, 3, 4, more records): first row | size << 16
-  __align__(8) u64 ws64[MB_THREADS / 32 + 1];
+  __align__(8) u64 ws64[MB_THREADS / 32];
   __align__(8) u64 bar[2];
   u32 w[2], M[2], off[2], st[2];
   u32 nl[4];  // queued cells of 2, 3, 4 records / of more
@@ -279,6 +279,21 @@ __device__ __forceinline__ void big_cell(const u64* __restrict__ cb, u32 size, u
   __syncwarp();
 }
 
+// Exclusive add scan over the CTA's 1024 threads with ONE barrier: every warp publishes its total, then every warp scans
+// the 32 totals itself.  `ws` (32 entries) is not reused before the next barrier of the caller.
+__device__ __forceinline__ u64 scan_excl_1barrier(u64 v, u64* ws, u64* total) {
+  static_assert(MB_THREADS == 1024, "one lane per warp total");
+  const u64 inc = warp_incl_add(v);
+  const u32 w = threadIdx.x >> 5, l = threadIdx.x & 31u;
+  if (l == 31) ws[w] = inc;
+  __syncthreads();
+  const u64 x = ws[l];
+  const u64 xi = warp_incl_add(x);
+  const u64 before = __shfl_sync(FULL_MASK, xi - x, (int)w);
+  *total = __shfl_sync(FULL_MASK, xi, 31);
+  return before + inc - v;
+}
+
 __global__ void __launch_bounds__(MB_THREADS, 1)
 k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __restrict__ U, u32* __restrict__ pidx,
              u32* __restrict__ tie_head, u32* __restrict__ tie_idx, u32* ctl) {
@@ -304,6 +319,13 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
     issue(0, blockIdx.x < nw ? work[blockIdx.x] : dnext);
     if (inext < nw) dnext = work[inext];
   }
+  auto clear_cells = [&]() {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* c4 = reinterpret_cast<uint4*>(s.cnt);
+#pragma unroll
+    for (u32 k = 0; k < MB_CELLS / 8 / MB_THREADS; k++) c4[tid + k * MB_THREADS] = z;
+  };
+  clear_cells();
   __syncthreads();
   for (u32 it = 0;; it++) {
     const u32 i = it & 1u;
@@ -316,12 +338,6 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
     }
     const u32 M = s.M[i], off = s.off[i], ust = s.st[i], blockb = w >> 8;
     u64* buf = s.buf[i];
-    {
-      uint4 z = make_uint4(0, 0, 0, 0);
-      uint4* c4 = reinterpret_cast<uint4*>(s.cnt);
-#pragma unroll
-      for (u32 k = 0; k < MB_CELLS / 8 / MB_THREADS; k++) c4[tid + k * MB_THREADS] = z;
-    }
     mbar_wait(&s.bar[i], (it >> 1) & 1u);
     u64 r[MB_ITEMS];
 #pragma unroll
@@ -329,8 +345,7 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
       const u32 p = tid + k * MB_THREADS;
       r[k] = p < M ? buf[off + p] : 0ull;
     }
-    __syncthreads();
-    // ---- cell histogram ----
+    // ---- cell histogram (the counters were cleared behind the barrier that ended the last round) ----
 #pragma unroll
     for (int k = 0; k < MB_ITEMS; k++) {
       const u32 p = tid + k * MB_THREADS;
@@ -365,8 +380,8 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
       const u32 g2 = (a2 & 0xffffu) + (a2 >> 16), g3 = (a3 & 0xffffu) + (a3 >> 16), g4 = (a4 & 0xffffu) + (a4 >> 16), g5 = (a5 & 0xffffu) + (a5 >> 16);
       // records | cells of 2 << 14 | cells of 3 << 27 | cells of 4 << 39 | larger cells << 51
       u64 tot;
-      const u64 ex = block_excl_add<MB_THREADS, u64>((u64)sum | ((u64)(g2 - g3) << 14) | ((u64)(g3 - g4) << 27) | ((u64)(g4 - g5) << 39) | ((u64)g5 << 51),
-                                                      s.ws64, &tot);
+      const u64 ex = scan_excl_1barrier((u64)sum | ((u64)(g2 - g3) << 14) | ((u64)(g3 - g4) << 27) | ((u64)(g4 - g5) << 39) | ((u64)g5 << 51),
+                                        s.ws64, &tot);
       const u32 t2 = (u32)(tot >> 14) & 0x1fffu, t3 = (u32)(tot >> 27) & 0xfffu, t4 = (u32)(tot >> 39) & 0xfffu, tN = (u32)(tot >> 51);
       if (tid == 0) { s.nl[0] = t2; s.nl[1] = t3; s.nl[2] = t4; s.nl[3] = tN; }
       u32 run = (u32)ex & 0x3fffu;
@@ -450,6 +465,7 @@ k_msd_bucket(const u64* __restrict__ rec, const uint4* __restrict__ work, u8* __
         }
       }
     }
+    clear_cells();       // the ordering passes are done with their scratch in the counters
     fence_async_smem();  // the generic-proxy writes to this buffer are ordered before the bulk copy that refills it
     __syncthreads();
   }

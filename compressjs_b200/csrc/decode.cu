@@ -434,15 +434,15 @@ struct ChunkSum {
 
 // One THREAD per 4 Ki-symbol chunk: the serial list pass of the reference (lib/Bzip2.js:355-360) on a private list that
 // starts as the identity, so what comes out are POSITIONS IN THE CHUNK'S START LIST (k_unmtf_map turns them into bytes
-// once k_unmtf_scan has composed the chunks' final lists).  The list lives in shared memory as 32-bit words, word k of
-// thread t at [k][t]: every lane owns a bank, whatever word it touches.  Moving list[idx] to the front shifts idx/4
+// once k_unmtf_scan has composed the chunks' final lists).  The list lives in shared memory as 64-bit words, word k of
+// thread t at [k][t]: no bank conflicts, whatever word a lane touches.  Moving list[idx] to the front shifts idx/8
 // words by one byte: a short loop whose length follows the rank (small on anything compressible), against the 48
 // warp instructions per symbol of a warp-wide register list.
 #define UA_THREADS 128
 __global__ void __launch_bounds__(UA_THREADS)
 k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncand, u32 cps, ChunkSum* __restrict__ sums, u8* __restrict__ perms,
           u8* __restrict__ symb) {
-  __shared__ u32 W[64][UA_THREADS];
+  __shared__ u64 W[32][UA_THREADS];
   const u32 t = threadIdx.x;
   const u32 gchunk = blockIdx.x * UA_THREADS + t;
   const u32 ci = gchunk / cps, ch = gchunk % cps;
@@ -456,7 +456,7 @@ k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncan
   const u16* s = sym + ((size_t)ci << SEG_SHIFT) + start;
   const u32 symTotal = r->sym_total;
 #pragma unroll 8
-  for (u32 k = 0; k < 64; k++) W[k][t] = 0x03020100u + k * 0x04040404u;  // identity list
+  for (u32 k = 0; k < 32; k++) W[k][t] = 0x0706050403020100ull + k * 0x0808080808080808ull;  // identity list
   u64 leadval = 0; u32 nlead = 0, rest = 0, krun = 0, bad = 0;
   bool seen_lit = false;
   u8* sb = symb + ((size_t)ci << SEG_SHIFT) + start;
@@ -481,16 +481,16 @@ k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncan
         } else {
           seen_lit = true; krun = 0;
           if (sy <= symTotal) {
-            const u32 idx = sy - 1, wq = idx >> 2, bp = idx & 3u;
-            const u32 x = W[wq][t];
-            const u32 b = (x >> (8 * bp)) & 0xffu;
-            u32 carry = b;
+            const u32 idx = sy - 1, wq = idx >> 3, bp = idx & 7u;
+            const u64 x = W[wq][t];
+            const u32 b = (u32)(x >> (8 * bp)) & 0xffu;
+            u64 carry = b;
             for (u32 k = 0; k < wq; k++) {
-              const u32 y = W[k][t];
+              const u64 y = W[k][t];
               W[k][t] = (y << 8) | carry;
-              carry = y >> 24;
+              carry = y >> 56;
             }
-            const u32 msk = bp == 3 ? 0xffffffffu : ((1u << (8 * (bp + 1))) - 1u);
+            const u64 msk = bp == 7 ? ~0ull : ((1ull << (8 * (bp + 1))) - 1ull);
             W[wq][t] = (((x << 8) | carry) & msk) | (x & ~msk);
             front = b;
             rest++;
@@ -507,9 +507,9 @@ k_unmtf_a(const u16* __restrict__ sym, const CandRes* __restrict__ res, u32 ncan
     cs.nsyms = count; cs.bad = bad;
     sums[gchunk] = cs;
   }
-  u32* p = reinterpret_cast<u32*>(perms + (size_t)gchunk * 256);
+  u64* p = reinterpret_cast<u64*>(perms + (size_t)gchunk * 256);
 #pragma unroll 8
-  for (u32 k = 0; k < 64; k++) p[k] = W[k][t];
+  for (u32 k = 0; k < 32; k++) p[k] = W[k][t];
 }
 
 struct ChunkStart {
@@ -621,11 +621,21 @@ __global__ void k_ibwt_keys(const u8* __restrict__ tt, const u32* __restrict__ s
 #define IB_SEGS (SEG_SIZE / IB_STEP + 1)  // sampled rows per block + the start row
 #define IB_VCAP 16384
 
+#define IB_CAP 512u   // bytes a walk records on its way (four sampling steps); 1.8 % of the bytes lie behind that and are re-walked
+
 struct Seg { u32 len, next; };
 struct Visit { u32 row, off, len; };
 
+// The bytes a walk passes are kept in a slot of IB_CAP bytes per sampled row (slotA: the 8192 multiples of 2^IB_SHIFT of
+// every block, 4 MiB per block; slotB: the start row's slot at the head of the block's 4 MiB), so that once the order of
+// the walks is known the block is assembled by copying instead of walking it a second time.
+__device__ __forceinline__ u8* ib_slot(u8* slotA, u8* slotB, u32 ci, u32 sid) {
+  return sid < IB_SEGS - 1 ? slotA + ((size_t)ci << (SEG_SHIFT + 2)) + (size_t)sid * IB_CAP : slotB + ((size_t)ci << (SEG_SHIFT + 2));
+}
+
 // walk from every sampled row (multiples of 2^IB_SHIFT and the start row) to the next sampled row
-__global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, Seg* __restrict__ segs) {
+__global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, Seg* __restrict__ segs, u32* __restrict__ capr,
+                             u8* __restrict__ slotA, u8* __restrict__ slotB) {
   const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 ci = gid / IB_SEGS, sid = gid % IB_SEGS;
   if (ci >= ncand) return;
@@ -637,28 +647,46 @@ __global__ void k_ibwt_walk1(const u32* __restrict__ P, const CandRes* __restric
   u32 a;
   if (sid == IB_SEGS - 1) { if ((r0 & (IB_STEP - 1)) == 0) return; a = r0; }
   else { a = sid << IB_SHIFT; if (a >= n) return; }
-  u32 row = a, steps = 0;
-  do {
-    row = p[row] >> 8;
-    steps++;
-  } while ((row & (IB_STEP - 1)) != 0 && row != r0 && steps < n);
+  uint4* slot = reinterpret_cast<uint4*>(ib_slot(slotA, slotB, ci, sid));
+  u32 row = a, steps = 0, rowcap = 0;
+  // 32 steps at a time: the bytes of one chunk go out as ONE 32-byte sector (a sector written four bytes at a time is
+  // evicted half full while 300 000 walks stream through the L2)
+  for (bool more = true; more;) {
+    u32 w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (u32 k = 0; k < 32; k++) {
+      const u32 e = p[row];
+      w[k >> 2] |= (e & 0xffu) << (8u * (k & 3u));
+      row = e >> 8;
+      steps++;
+      if (steps == IB_CAP) rowcap = row;
+      if (!((row & (IB_STEP - 1)) != 0 && row != r0 && steps < n)) { more = false; break; }
+    }
+    const u32 chunk = (steps - 1) >> 5;
+    if (chunk < IB_CAP / 32) {
+      slot[2 * chunk] = make_uint4(w[0], w[1], w[2], w[3]);
+      slot[2 * chunk + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
   Seg sg;
   sg.len = steps;
   sg.next = ((row & (IB_STEP - 1)) == 0) ? (row >> IB_SHIFT) : (IB_SEGS - 1);
   segs[(size_t)ci * IB_SEGS + sid] = sg;
+  capr[(size_t)ci * IB_SEGS + sid] = rowcap;
 }
 
 // order the segments along the chain that starts at the start row.  One CTA per block: the segment
-// table (32 KB) is staged in shared memory so that the serial walk costs a shared-memory load per step.
+// table (64 KB) is staged in shared memory so that the serial walk costs a shared-memory load per step.
+// tails: the visits that are longer than their slot (indices into the block's visit list).
 __global__ void __launch_bounds__(128)
 k_ibwt_chain(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Seg* __restrict__ segs,
-             Visit* __restrict__ visits, u32* __restrict__ nvisits) {
+             Visit* __restrict__ visits, u32* __restrict__ nvisits, u32* __restrict__ tails, u32* __restrict__ ntails) {
   extern __shared__ __align__(8) unsigned char chain_smem[];
   Seg* ss = reinterpret_cast<Seg*>(chain_smem);
   const u32 ci = blockIdx.x;
   if (ci >= ncand) return;
   const CandRes* r = res + ci;
-  if (r->status != 0) { if (threadIdx.x == 0) nvisits[ci] = 0; return; }
+  if (r->status != 0) { if (threadIdx.x == 0) { nvisits[ci] = 0; ntails[ci] = 0; } return; }
   const u32 n = r->n;
   const u32 nseg = min((u32)IB_SEGS, (n >> IB_SHIFT) + 2);
   for (u32 i = threadIdx.x; i < nseg; i += blockDim.x) ss[i] = segs[(size_t)ci * IB_SEGS + i];
@@ -668,26 +696,71 @@ k_ibwt_chain(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 nca
   const u32* p = P + ((size_t)ci << SEG_SHIFT);
   const u32 r0 = p[r->orig] >> 8;
   u32 cur = ((r0 & (IB_STEP - 1)) == 0) ? (r0 >> IB_SHIFT) : (IB_SEGS - 1);
-  u32 off = 0, nv = 0;
+  u32 off = 0, nv = 0, nt = 0;
   Visit* v = visits + (size_t)ci * IB_VCAP;
+  u32* tl = tails + (size_t)ci * IB_VCAP;
   while (off < n) {
     const Seg sg = ss[cur];
     const u32 len = min(sg.len, n - off);
-    if (nv >= IB_VCAP) { nv = 0xffffffffu; break; }  // degenerate (periodic) block: fall back to one serial walk
+    if (nv >= IB_VCAP) { nv = 0xffffffffu; nt = 0; break; }  // degenerate (periodic) block: fall back to one serial walk
     Visit vv;
     vv.row = (cur == IB_SEGS - 1) ? r0 : (cur << IB_SHIFT);
     vv.off = off; vv.len = len;
+    if (len > IB_CAP) tl[nt++] = nv;
     v[nv++] = vv;
     off += len;
     cur = sg.next;
   }
   nvisits[ci] = nv;
+  ntails[ci] = nt;
 }
 
-__global__ void k_ibwt_walk2(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Visit* __restrict__ visits,
-                             const u32* __restrict__ nvisits, u8* __restrict__ out) {
+// Every visit's recorded bytes are copied to their place in the block: one warp per visit, aligned 32-bit words in the
+// middle (realigned from the slot with a funnel shift), single bytes at the two ends (the neighbouring visits own the
+// rest of those words).  IB_PLACE_CTAS CTAs share the visits of a block.
+#define IB_PLACE_CTAS 4
+#define IB_PLACE_THREADS 256
+__global__ void __launch_bounds__(IB_PLACE_THREADS)
+k_ibwt_place(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Visit* __restrict__ visits,
+             const u32* __restrict__ nvisits, const u8* __restrict__ slotA, const u8* __restrict__ slotB, u8* __restrict__ out) {
+  const u32 ci = blockIdx.x / IB_PLACE_CTAS;
+  if (ci >= ncand) return;
+  if (res[ci].status != 0) return;
+  const u32 nv = nvisits[ci];
+  if (nv == 0xffffffffu) return;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 wstride = IB_PLACE_CTAS * (IB_PLACE_THREADS / 32);
+  const u32* p = P + ((size_t)ci << SEG_SHIFT);
+  const u32 r0 = p[res[ci].orig] >> 8;
+  const bool r0_own = (r0 & (IB_STEP - 1)) != 0;
+  u8* ob = out + ((size_t)ci << SEG_SHIFT);
+  for (u32 vi = (blockIdx.x % IB_PLACE_CTAS) * (IB_PLACE_THREADS / 32) + (threadIdx.x >> 5); vi < nv; vi += wstride) {
+    const Visit v = visits[(size_t)ci * IB_VCAP + vi];
+    const u32 sid = (r0_own && v.row == r0) ? (IB_SEGS - 1) : (v.row >> IB_SHIFT);
+    const u8* srcb = ib_slot(const_cast<u8*>(slotA), const_cast<u8*>(slotB), ci, sid);
+    const u32* src = reinterpret_cast<const u32*>(srcb);
+    u8* o = ob + v.off;
+    const u32 len = min(v.len, IB_CAP);
+    const u32 head = min(len, (4u - ((u32)(size_t)o & 3u)) & 3u);   // bytes in front of the first aligned word
+    const u32 nwords = (len - head) >> 2;
+    if (lane < head) o[lane] = srcb[lane];
+    u32* ow = reinterpret_cast<u32*>(o + head);
+    const u32 sh = 8u * head;                                        // word w of the destination = source bytes head + 4w ..
+    for (u32 w = lane; w < nwords; w += 32) {
+      const u32 lo = src[w], hi = head ? src[w + 1] : 0u;           // src[w + 1] stays inside the slot: head + 4w + 3 < len <= IB_CAP
+      ow[w] = __funnelshift_r(lo, hi, sh);
+    }
+    const u32 done = head + 4u * nwords;
+    if (lane < len - done) o[done + lane] = srcb[done + lane];
+  }
+}
+
+// what lies behind the recorded part of a long walk is walked again; so is a whole degenerate block
+__global__ void k_ibwt_tail(const u32* __restrict__ P, const CandRes* __restrict__ res, u32 ncand, const Visit* __restrict__ visits,
+                            const u32* __restrict__ nvisits, const u32* __restrict__ tails, const u32* __restrict__ ntails,
+                            const u32* __restrict__ capr, u8* __restrict__ out) {
   const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 ci = gid / IB_VCAP, vi = gid % IB_VCAP;
+  const u32 ci = gid / IB_VCAP, ti = gid % IB_VCAP;
   if (ci >= ncand) return;
   const CandRes* r = res + ci;
   if (r->status != 0) return;
@@ -696,12 +769,14 @@ __global__ void k_ibwt_walk2(const u32* __restrict__ P, const CandRes* __restric
   u8* o = out + ((size_t)ci << SEG_SHIFT);
   u32 row, off, len;
   if (nv == 0xffffffffu) {
-    if (vi != 0) return;
+    if (ti != 0) return;
     row = p[r->orig] >> 8; off = 0; len = r->n;
   } else {
-    if (vi >= nv) return;
-    const Visit v = visits[(size_t)ci * IB_VCAP + vi];
-    row = v.row; off = v.off; len = v.len;
+    if (ti >= ntails[ci]) return;
+    const Visit v = visits[(size_t)ci * IB_VCAP + tails[(size_t)ci * IB_VCAP + ti]];
+    const u32 r0 = p[r->orig] >> 8;
+    const u32 sid = (v.row == r0 && (r0 & (IB_STEP - 1)) != 0) ? (IB_SEGS - 1) : (v.row >> IB_SHIFT);
+    row = capr[(size_t)ci * IB_SEGS + sid]; off = v.off + IB_CAP; len = v.len - IB_CAP;
   }
   for (u32 t = 0; t < len; t++) {
     const u32 e = p[row];
@@ -746,6 +821,8 @@ void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out) {
   DBuf<CandRes> res(c, 1);
   DBuf<Seg> segs(c, IB_SEGS);
   DBuf<Visit> visits(c, IB_VCAP);
+  DBuf<u32> capr(c, IB_SEGS), tails(c, IB_VCAP), ntails(c, 1);
+  DBuf<u8> slots(c, (size_t)SEG_SIZE * 4 + IB_CAP);  // slotA; the start row's slot sits behind it
   c.to_device(dn, &n, 4);
   k_ibwt_keys<<<(SEG_SIZE + 255) / 256, 256, 0, c.stream>>>(d_L, dn, SEG_SIZE, keyA);
   KLAUNCH(c); KCHECK();
@@ -757,11 +834,14 @@ void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out) {
   KLAUNCH(c); KCHECK();
   k_unbwt_setup<<<1, 1, 0, c.stream>>>(res, n);
   KLAUNCH(c); KCHECK();
-  k_ibwt_walk1<<<(IB_SEGS + 127) / 128, 128, 0, c.stream>>>(P, res, 1, segs);
+  u8* slotA = slots.p; u8* slotB = slots.p + (size_t)SEG_SIZE * 4;
+  k_ibwt_walk1<<<(IB_SEGS + 127) / 128, 128, 0, c.stream>>>(P, res, 1, segs, capr, slotA, slotB);
   KLAUNCH(c); KCHECK();
-  k_ibwt_chain<<<1, 128, sizeof(Seg) * IB_SEGS, c.stream>>>(P, res, 1, segs, visits, nvis);
+  k_ibwt_chain<<<1, 128, sizeof(Seg) * IB_SEGS, c.stream>>>(P, res, 1, segs, visits, nvis, tails, ntails);
   KLAUNCH(c); KCHECK();
-  k_ibwt_walk2<<<(IB_VCAP + 127) / 128, 128, 0, c.stream>>>(P, res, 1, visits, nvis, tmp);
+  k_ibwt_place<<<IB_PLACE_CTAS, IB_PLACE_THREADS, 0, c.stream>>>(P, res, 1, visits, nvis, slotA, slotB, tmp);
+  KLAUNCH(c); KCHECK();
+  k_ibwt_tail<<<(IB_VCAP + 127) / 128, 128, 0, c.stream>>>(P, res, 1, visits, nvis, tails, ntails, capr, tmp);
   KLAUNCH(c); KCHECK();
   k_reverse_bytes<<<(n + 255) / 256, 256, 0, c.stream>>>(tmp, n, d_out);
   KLAUNCH(c); KCHECK();
@@ -779,17 +859,8 @@ __device__ __forceinline__ bool unrle_sync(const u8* b, u32 i) {
   if (i >= 4 && b[i - 1] == b[i - 2] && b[i - 2] == b[i - 3] && b[i - 3] == b[i - 4]) return false;
   return true;
 }
-// cls[i] = 1 when byte i is a repeat count (lib/Bzip2.js:424-436)
-__global__ void __launch_bounds__(256) k_unrle_classify(const u8* __restrict__ rle, const CandRes* __restrict__ res, u32 ncand, u8* __restrict__ cls) {
-  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 ci = g >> SEG_SHIFT, i = g & SEG_MASK;
-  if (ci >= ncand) return;
-  const CandRes* r = res + ci;
-  if (r->status != 0 || i >= r->n) return;
-  const u32 n = r->n;
-  const u8* b = rle + ((size_t)ci << SEG_SHIFT);
-  u8* c = cls + ((size_t)ci << SEG_SHIFT);
-  if (!unrle_sync(b, i)) return;
+// the reference's loop (lib/Bzip2.js:424-436) from a synchronisation point i to the next one: cls[j] = 1 for repeat counts
+__device__ __noinline__ void unrle_walk(const u8* __restrict__ b, u8* __restrict__ c, u32 i, u32 n) {
   u32 j = i, run = 0;
   int prev = -1;
   for (;;) {
@@ -806,6 +877,56 @@ __global__ void __launch_bounds__(256) k_unrle_classify(const u8* __restrict__ r
       if (j >= n) break;
     }
     if (unrle_sync(b, j)) break;
+  }
+}
+// cls[i] = 1 when byte i is a repeat count.  A byte that differs from its predecessor and does not follow four equal
+// bytes is certainly a literal that starts a new run (a synchronisation point); the bytes between two such points are
+// classified by the serial loop.  One thread per 8 bytes: the 13 bytes that decide its synchronisation points sit in
+// registers, a literal followed by another synchronisation point is final at once (all 8 of them: one 8-byte store),
+// and only real run starts walk.
+__global__ void __launch_bounds__(256) k_unrle_classify(const u8* __restrict__ rle, const CandRes* __restrict__ res, u32 ncand, u8* __restrict__ cls) {
+  const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 ci = g >> (SEG_SHIFT - 3), i0 = (g & (SEG_MASK >> 3)) << 3;
+  if (ci >= ncand) return;
+  const CandRes* r = res + ci;
+  if (r->status != 0 || i0 >= r->n) return;
+  const u32 n = r->n;
+  const u8* b = rle + ((size_t)ci << SEG_SHIFT);
+  u8* c = cls + ((size_t)ci << SEG_SHIFT);
+  const u64 prev = i0 ? *reinterpret_cast<const u64*>(b + i0 - 8) : 0ull;
+  const u64 cur = *reinterpret_cast<const u64*>(b + i0);
+  const u64 next = (i0 + 8 < SEG_SIZE) ? *reinterpret_cast<const u64*>(b + i0 + 8) : 0ull;
+  // E bit (j + 3): byte i0 + j equals its predecessor, j = -3 .. 8 (bytes past n only make a position look like a run: it walks)
+  u32 E = 0;
+#pragma unroll
+  for (int j = -3; j <= 8; j++) {
+    const u32 x = j < 0 ? (u32)(prev >> (8 * (j + 8))) : (j < 8 ? (u32)(cur >> (8 * j)) : (u32)(next >> (8 * (j - 8))));
+    const u32 y = (j - 1) < 0 ? (u32)(prev >> (8 * (j - 1 + 8))) : ((j - 1) < 8 ? (u32)(cur >> (8 * (j - 1))) : (u32)(next >> (8 * (j - 1 - 8))));
+    if (((x ^ y) & 0xffu) == 0 && (int)i0 + j >= 1) E |= 1u << (j + 3);
+  }
+  // S bit k: position i0 + k is a synchronisation point, k = 0 .. 8
+  u32 S = 0;
+#pragma unroll
+  for (int k = 0; k <= 8; k++) {
+    const bool e0 = (E >> (k + 3)) & 1u, run4 = ((E >> k) & 7u) == 7u && i0 + k >= 4;  // E(i-3), E(i-2), E(i-1)
+    if (!e0 && !run4) S |= 1u << k;
+  }
+  if ((S & 0xffu) == 0xffu && i0 + 8 <= n) {
+    // eight literals, each followed by a synchronisation point or the end... unless the ninth position continues a run of
+    // the eighth: then position 7 starts a walk
+    if ((S >> 8) & 1u || i0 + 8 >= n) { *reinterpret_cast<u64*>(c + i0) = 0ull; return; }
+    *reinterpret_cast<u32*>(c + i0) = 0u;
+    c[i0 + 4] = 0; c[i0 + 5] = 0; c[i0 + 6] = 0;
+    unrle_walk(b, c, i0 + 7, n);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const u32 i = i0 + k;
+    if (i < n && ((S >> k) & 1u)) {
+      if (((S >> (k + 1)) & 1u) || i + 1 >= n) c[i] = 0;
+      else unrle_walk(b, c, i, n);
+    }
   }
 }
 
@@ -827,10 +948,12 @@ k_unrle_scan(const u8* __restrict__ rle, const u8* __restrict__ cls, CandRes* __
   const u8* c = cls + ((size_t)ci << SEG_SHIFT);
   u32 sum = 0;
   const u32 p0 = start + tid * UR_ITEMS;
+  static_assert(UR_ITEMS == 8, "one 8-byte load per array");
+  if (p0 < n) {
+    const u64 bv = *reinterpret_cast<const u64*>(b + p0), cv = *reinterpret_cast<const u64*>(c + p0);
 #pragma unroll
-  for (int j = 0; j < UR_ITEMS; j++) {
-    const u32 p = p0 + j;
-    if (p < n) sum += c[p] ? (u32)b[p] : 1u;
+    for (int j = 0; j < UR_ITEMS; j++)
+      if (p0 + j < n) sum += ((u32)(cv >> (8 * j)) & 0xffu) ? ((u32)(bv >> (8 * j)) & 0xffu) : 1u;
   }
   u32 total;
   block_excl_add<UR_THREADS, u32>(sum, ws, &total);
@@ -862,10 +985,12 @@ k_unrle_emit(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandR
   u32 len[UR_ITEMS];
   u32 sum = 0;
   const u32 p0 = start + tid * UR_ITEMS;
+  u64 bv = 0, cv = 0;
+  if (p0 < n) { bv = *reinterpret_cast<const u64*>(b + p0); cv = *reinterpret_cast<const u64*>(c + p0); }
 #pragma unroll
   for (int j = 0; j < UR_ITEMS; j++) {
     const u32 p = p0 + j;
-    len[j] = (p < n) ? (c[p] ? (u32)b[p] : 1u) : 0u;
+    len[j] = (p < n) ? (((u32)(cv >> (8 * j)) & 0xffu) ? ((u32)(bv >> (8 * j)) & 0xffu) : 1u) : 0u;
     sum += len[j];
   }
   u32 total;
@@ -875,11 +1000,11 @@ k_unrle_emit(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandR
   for (int j = 0; j < UR_ITEMS; j++) {
     const u32 p = p0 + j;
     if (p < n) {
-      if (c[p]) {
+      if ((u32)(cv >> (8 * j)) & 0xffu) {
         const u8 v = b[p - 1];
         for (u32 x = 0; x < len[j]; x++) o[x] = v;
       } else {
-        o[0] = b[p];
+        o[0] = (u8)(bv >> (8 * j));
       }
       o += len[j];
     }
@@ -1037,6 +1162,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
     DBuf<u32> dn(c, nbm), nvis(c, nbm), ticket(c, 1);
     DBuf<Seg> segs(c, (size_t)nbm * IB_SEGS);
     DBuf<Visit> visits(c, (size_t)nbm * IB_VCAP);
+    DBuf<u32> capr(c, (size_t)nbm * IB_SEGS), tails(c, (size_t)nbm * IB_VCAP), ntails(c, nbm);
     DBuf<u64> lbst(c, (size_t)nbm * ur_tps);
     std::vector<u32> hn(nbm);
     for (size_t k0 = 0; k0 < nb; k0 += DB) {
@@ -1077,19 +1203,26 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
         for (u32 s0 = 0; s0 < cnt; s0 += ib_sub) {
           const u32 sc = std::min<u32>(ib_sub, cnt - s0);
           const u32* Ps = Pp + ((size_t)s0 << SEG_SHIFT);
-          k_ibwt_walk1<<<(sc * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS);
+          // the walks record into the free key / value buffers of the sort (4 MiB per block each)
+          u8* slotA = reinterpret_cast<u8*>(keyA.p) + ((size_t)s0 << (SEG_SHIFT + 2));
+          u8* slotB = reinterpret_cast<u8*>(valA.p) + ((size_t)s0 << (SEG_SHIFT + 2));
+          k_ibwt_walk1<<<(sc * IB_SEGS + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, capr.p + (size_t)s0 * IB_SEGS, slotA, slotB);
           KLAUNCH(c); KCHECK();
-          k_ibwt_chain<<<sc, 128, sizeof(Seg) * IB_SEGS, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0);
+          k_ibwt_chain<<<sc, 128, sizeof(Seg) * IB_SEGS, c.stream>>>(Ps, rb + s0, sc, segs.p + (size_t)s0 * IB_SEGS, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0,
+                                                                   tails.p + (size_t)s0 * IB_VCAP, ntails.p + s0);
           KLAUNCH(c); KCHECK();
-          k_ibwt_walk2<<<(sc * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0,
-                                                                       rle.p + ((k0 + s0) << SEG_SHIFT));
+          u8* ob = rle.p + ((k0 + s0) << SEG_SHIFT);
+          k_ibwt_place<<<sc * IB_PLACE_CTAS, IB_PLACE_THREADS, 0, c.stream>>>(Ps, rb + s0, sc, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0, slotA, slotB, ob);
+          KLAUNCH(c); KCHECK();
+          k_ibwt_tail<<<(sc * IB_VCAP + 127) / 128, 128, 0, c.stream>>>(Ps, rb + s0, sc, visits.p + (size_t)s0 * IB_VCAP, nvis.p + s0,
+                                                                      tails.p + (size_t)s0 * IB_VCAP, ntails.p + s0, capr.p + (size_t)s0 * IB_SEGS, ob);
           KLAUNCH(c); KCHECK();
         }
       }
       if (nmax) {
         StageScope ss(c, ST_UNRLE);
         const u32 nslots = cnt << SEG_SHIFT;
-        k_unrle_classify<<<(nslots + 255) / 256, 256, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), rb, cnt, cls.p + (k0 << SEG_SHIFT));
+        k_unrle_classify<<<(nslots / 8 + 255) / 256, 256, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), rb, cnt, cls.p + (k0 << SEG_SHIFT));
         KLAUNCH(c); KCHECK();
         CUDA_CHECK(cudaMemsetAsync(lbst, 0, (size_t)cnt * ur_tps * 8, c.stream));
         CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
