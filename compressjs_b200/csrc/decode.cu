@@ -17,10 +17,14 @@
 //                    lane-parallel pass that maps positions to bytes and expands the runs
 //   inverse BWT    : T-vector by one onesweep radix pass on the L column (lib/Bzip2.js:370-381),
 //                    then the n-step pointer chase (lib/Bzip2.js:418-423) is broken into ~7000
-//                    independent walks per block between sampled rows (walk, chain, walk+emit)
+//                    independent walks per block between sampled rows; every walk records the bytes
+//                    it passes, a serial pass over the 7000 walk summaries orders them, and the block
+//                    is assembled by copies (only what lies behind a walk's 512-byte record is
+//                    walked again)
 //   bwt_inverse_sentinel: BWT.unbwtransform (lib/BWT.js:352-363) on the same walk kernels
 //   k_unrle_*      : RLE1 decode (lib/Bzip2.js:424-436): count bytes are identified from local
-//                    synchronisation points, output offsets by chained scan, CRC32 per block
+//                    synchronisation points (8 bytes per thread, decided in registers), output
+//                    offsets by chained scan, tiles expanded in shared memory, CRC32 per block
 //   host           : walks the block chain (a block must start exactly where the previous one
 //                    ended), folds/validates CRCs and raises the reference's errors in stream order.
 #include <algorithm>
@@ -852,6 +856,7 @@ void bwt_inverse_sentinel(Ctx& c, const u8* d_L, u32 n, u32 pidx, u8* d_out) {
 #define UR_THREADS 256
 #define UR_ITEMS 8
 #define UR_TILE (UR_THREADS * UR_ITEMS)
+#define UE_STAGE 6144u   // bytes of expanded output a tile stages in shared memory
 
 __device__ __forceinline__ bool unrle_sync(const u8* b, u32 i) {
   if (i == 0) return true;
@@ -972,6 +977,7 @@ __global__ void __launch_bounds__(UR_THREADS)
 k_unrle_emit(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandRes* __restrict__ res, u32 tps, const u32* __restrict__ tileoff,
              const u64* __restrict__ outbase, u8* __restrict__ out) {
   __shared__ u32 ws[UR_THREADS / 32 + 1];
+  __shared__ __align__(16) u8 stg[UE_STAGE + 32];
   const u32 tid = threadIdx.x;
   const u32 ci = blockIdx.x / tps, lt = blockIdx.x % tps;
   const u64 ob = outbase[ci];
@@ -995,7 +1001,12 @@ k_unrle_emit(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandR
   }
   u32 total;
   const u32 ex = block_excl_add<UR_THREADS, u32>(sum, ws, &total);
-  u8* o = out + ob + tileoff[(size_t)ci * tps + lt] + ex;
+  u8* otile = out + ob + tileoff[(size_t)ci * tps + lt];
+  // A tile that expands to at most UE_STAGE bytes (every tile of run-free data, most others) is put together in shared
+  // memory, at the alignment (mod 16) it has in the output, and leaves in 16-byte stores; longer ones go out directly.
+  const bool staged = total <= UE_STAGE;
+  const u32 mis = (u32)(size_t)otile & 15u;
+  u8* o = staged ? stg + mis + ex : otile + ex;
 #pragma unroll
   for (int j = 0; j < UR_ITEMS; j++) {
     const u32 p = p0 + j;
@@ -1007,6 +1018,20 @@ k_unrle_emit(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandR
         o[0] = (u8)(bv >> (8 * j));
       }
       o += len[j];
+    }
+  }
+  if (!staged) return;
+  __syncthreads();
+  {
+    const u32 last = mis + total;
+    u8* og = otile - mis;  // 16-byte aligned
+    for (u32 c16 = tid * 16u; c16 < last; c16 += UR_THREADS * 16u) {
+      if (c16 >= mis && c16 + 16u <= last) {
+        *reinterpret_cast<uint4*>(og + c16) = *reinterpret_cast<const uint4*>(stg + c16);
+      } else {
+        const u32 e = min(c16 + 16u, last);
+        for (u32 x = max(c16, mis); x < e; x++) og[x] = stg[x];
+      }
     }
   }
 }
@@ -1113,24 +1138,28 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   {
     // every block of the own share keeps 2 MiB (L column + count-byte classes) until the stream is assembled, and a batch
     // of up to 2048 blocks needs ~19 MiB of scratch per block: say so instead of failing inside an allocation
+    const size_t need = nb * ((size_t)2 << 20) + std::min<size_t>(nb, std::max(c.bwt_batch, 2048u)) * ((size_t)19 << 20) + n;
+    // memory the stream-ordered pool holds but does not use is available too: when that covers the call (every call
+    // after the first of a kind) the driver is not asked at all -- cudaMemGetInfo takes milliseconds on a busy context
+    uint64_t reserved = 0, used = 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    cudaGetLastError();
+    const size_t spare = (size_t)(reserved > used ? reserved - used : 0);
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const size_t need = nb * ((size_t)2 << 20) + std::min<size_t>(nb, std::max(c.bwt_batch, 2048u)) * ((size_t)19 << 20) + n;
-      // memory the stream-ordered pool holds but does not use is available too
-      uint64_t reserved = 0, used = 0;
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-      }
-      cudaGetLastError();
-      if (need > free_b + (size_t)(reserved > used ? reserved - used : 0)) {
-        char msg[256];
-        snprintf(msg, sizeof msg, "stream of %zu blocks needs about %zu MiB of device memory for one call (%zu MiB free): decode it in parts "
-                                  "(Bzip2.table + decompressBlock) or over several GPUs (decompress_file_sharded)", nb, need >> 20, free_b >> 20);
-        throw B2Error{B2_ERR_CUDA, msg};
-      }
-    } else cudaGetLastError();
+    if (need > spare) {
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        if (need > free_b + spare) {
+          char msg[256];
+          snprintf(msg, sizeof msg, "stream of %zu blocks needs about %zu MiB of device memory for one call (%zu MiB free): decode it in parts "
+                                    "(Bzip2.table + decompressBlock) or over several GPUs (decompress_file_sharded)", nb, need >> 20, free_b >> 20);
+          throw B2Error{B2_ERR_CUDA, msg};
+        }
+      } else cudaGetLastError();
+    }
   }
   S.dcand.alloc(c, nb_all ? nb_all : 1);
   S.dres.alloc(c, nb ? nb : 1);
