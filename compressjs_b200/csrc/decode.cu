@@ -121,7 +121,11 @@ struct BitReader {
 };
 
 // ---- header + Huffman decode: one CTA per candidate ------------------------------------------
-#define HD_THREADS 128   // one CTA per block: the per-group phases are spread over four warps
+// One CTA per block.  The per-group phases are spread over the CTA's warps, and a block's ~18 000 groups are strictly
+// serial, so a launch lasts as long as one block takes: with all SM slots taken (9 x 128 threads: ~1300 blocks, a 1 GiB
+// file) four warps per block give the best throughput; with fewer blocks the same thread budget goes to fewer, wider CTAs
+// (256 or 512 threads: fewer window offsets per thread, a shorter group).
+#define HD_THREADS 128
 #define HD_LUT_BITS 9   // 6 tables x 512 entries: keeps a warp's state under 19 KB so that 12 blocks fit per SM
 #define HD_WIN 512
 #define HD_STAGE 64
@@ -161,13 +165,14 @@ __device__ __noinline__ u32 hdec_slow(const HdecWarp& s, u32 g, u32 bits20, int 
   return 0;
 }
 
-// 9 CTAs per SM (56 registers, 19 KB of shared memory each): a 1 GiB file's ~1200 blocks are resident at once
-__global__ void __launch_bounds__(HD_THREADS, 9)
+// 128 threads: 9 CTAs per SM (56 registers, 19 KB of shared memory each): a 1 GiB file's ~1200 blocks are resident at once
+template <int HD_T>
+__global__ void __launch_bounds__(HD_T, 1152 / HD_T)
 k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u32 first, u32 count, u32 dbuf_size, u8* __restrict__ sel_buf,
        u16* __restrict__ sym_out, CandRes* __restrict__ res) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HdecWarp& s = *reinterpret_cast<HdecWarp*>(smem_raw);
-  const u32 lane = threadIdx.x;  // 0..HD_THREADS-1: one CTA per candidate block
+  const u32 lane = threadIdx.x;  // 0..HD_T-1: one CTA per candidate block
   const u32 ci = blockIdx.x;
   if (ci >= count) return;
   const Cand cd = cands[first + ci];
@@ -265,7 +270,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
   }
   __syncthreads();
   // ---- LUT (HD_LUT_BITS bits) derived from the reference's decode loop (lib/Bzip2.js:296-307) ----
-  for (u32 e = lane; e < gc << HD_LUT_BITS; e += HD_THREADS) {
+  for (u32 e = lane; e < gc << HD_LUT_BITS; e += HD_T) {
     const u32 g = e >> HD_LUT_BITS, p = e & ((1u << HD_LUT_BITS) - 1);
     const int minLen = s.minlen[g], maxLen = s.maxlen[g];
     u16 ent = 0;  // 0 = needs more than HD_LUT_BITS bits (or fails): take the slow path
@@ -316,7 +321,7 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
         const u64 w0 = P >> 5;
         if (stage_w0 == ~0ull || w0 < stage_w0 || w0 + 18 > stage_w0 + HD_STAGE + 18) {
           __syncthreads();
-          for (u32 i = lane; i < HD_STAGE + 18; i += HD_THREADS) {
+          for (u32 i = lane; i < HD_STAGE + 18; i += HD_T) {
             const u64 wi = w0 + i;
             const u32 wv = wi < nwords ? words[wi] : 0u;
             s.win[i] = __byte_perm(wv, 0, 0x0123);
@@ -325,17 +330,17 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
           __syncthreads();
         }
         const u32 shiftbase = (u32)(P & 31);
-        u32 j1r[HD_WIN / HD_THREADS], j2r[HD_WIN / HD_THREADS];  // this thread's jump targets, kept in registers between the passes
+        u32 j1r[HD_WIN / HD_T], j2r[HD_WIN / HD_T];  // this thread's jump targets, kept in registers between the passes
         {
           // thread t decodes offsets t, t+128, ...: same bit shift every time
           const u32 sh = (shiftbase + lane) & 31;
           const u32* wp = s.win + (u32)(w0 - stage_w0) + ((shiftbase + lane) >> 5);
 #pragma unroll
-          for (u32 k = 0; k < HD_WIN / HD_THREADS; k++) {
-            const u32 o = lane + HD_THREADS * k;
+          for (u32 k = 0; k < HD_WIN / HD_T; k++) {
+            const u32 o = lane + HD_T * k;
             j1r[k] = o;
             if (o < wlim) {
-              const u32 hiw = wp[(HD_THREADS / 32) * k], low = wp[(HD_THREADS / 32) * k + 1];
+              const u32 hiw = wp[(HD_T / 32) * k], low = wp[(HD_T / 32) * k + 1];
               const u32 bits20 = __funnelshift_l(low, hiw, sh) >> 12;
               u32 ent = lut[bits20 >> (20 - HD_LUT_BITS)];
               if (!ent) ent = hdec_slow(s, g, bits20, minLen, maxLen);
@@ -356,18 +361,18 @@ k_hdec(const u8* __restrict__ in, u64 nbytes, const Cand* __restrict__ cands, u3
         }
         __syncthreads();
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
-          if (lane + HD_THREADS * k < wlim) j2r[k] = s.J1[j1r[k]];
+        for (u32 k = 0; k < HD_WIN / HD_T; k++)
+          if (lane + HD_T * k < wlim) j2r[k] = s.J1[j1r[k]];
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
-          if (lane + HD_THREADS * k < wlim) s.J2[lane + HD_THREADS * k] = (u16)j2r[k];
+        for (u32 k = 0; k < HD_WIN / HD_T; k++)
+          if (lane + HD_T * k < wlim) s.J2[lane + HD_T * k] = (u16)j2r[k];
         __syncthreads();
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
-          if (lane + HD_THREADS * k < wlim) j1r[k] = s.J2[j2r[k]];
+        for (u32 k = 0; k < HD_WIN / HD_T; k++)
+          if (lane + HD_T * k < wlim) j1r[k] = s.J2[j2r[k]];
 #pragma unroll
-        for (u32 k = 0; k < HD_WIN / HD_THREADS; k++)
-          if (lane + HD_THREADS * k < wlim) s.J4[lane + HD_THREADS * k] = (u16)j1r[k];
+        for (u32 k = 0; k < HD_WIN / HD_T; k++)
+          if (lane + HD_T * k < wlim) s.J4[lane + HD_T * k] = (u16)j1r[k];
         __syncthreads();
         if (lane == 0) {
           // the only serial part: 13 dependent shared-memory loads cover 52 symbols
@@ -813,7 +818,9 @@ __global__ void k_reverse_bytes(const u8* __restrict__ in, u32 n, u8* __restrict
 static void dec_attr_once() {
   static bool attr = false;
   if (attr) return;
-  CUDA_CHECK(cudaFuncSetAttribute(k_hdec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HdecWarp)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_hdec<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HdecWarp)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_hdec<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HdecWarp)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_hdec<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HdecWarp)));
   CUDA_CHECK(cudaFuncSetAttribute(k_ibwt_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Seg) * IB_SEGS)));
   attr = true;
 }
@@ -1199,8 +1206,11 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
       CandRes* rb = dres.p + k0;
       {
         StageScope ss(c, ST_HDEC);
-        k_hdec<<<cnt, HD_THREADS, sizeof(HdecWarp), c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size,
-                                                                                                       selbuf, sym, rb);
+        static int sms = 0;
+        if (!sms) CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+        if (cnt <= 2u * (u32)sms) k_hdec<512><<<cnt, 512, sizeof(HdecWarp), c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size, selbuf, sym, rb);
+        else if (cnt <= 4u * (u32)sms) k_hdec<256><<<cnt, 256, sizeof(HdecWarp), c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size, selbuf, sym, rb);
+        else k_hdec<HD_THREADS><<<cnt, HD_THREADS, sizeof(HdecWarp), c.stream>>>(din, n, dcand, (u32)k0, cnt, dbuf_size, selbuf, sym, rb);
         KLAUNCH(c); KCHECK();
       }
       {
