@@ -24,7 +24,8 @@
 //   bwt_inverse_sentinel: BWT.unbwtransform (lib/BWT.js:352-363) on the same walk kernels
 //   k_unrle_*      : RLE1 decode (lib/Bzip2.js:424-436): count bytes are identified from local
 //                    synchronisation points (8 bytes per thread, decided in registers), output
-//                    offsets by chained scan, tiles expanded in shared memory, CRC32 per block
+//                    offsets from tile sums + one warp scan per block, tiles expanded in shared
+//                    memory, CRC32 per block
 //   host           : walks the block chain (a block must start exactly where the previous one
 //                    ended), folds/validates CRCs and raises the reference's errors in stream order.
 #include <algorithm>
@@ -942,16 +943,13 @@ __global__ void __launch_bounds__(256) k_unrle_classify(const u8* __restrict__ r
   }
 }
 
+// expanded size of every tile (no chain between tiles: the per-block scan below is a separate, tiny kernel)
 __global__ void __launch_bounds__(UR_THREADS)
-k_unrle_scan(const u8* __restrict__ rle, const u8* __restrict__ cls, CandRes* __restrict__ res, u32 tps, u32* ticket, u64* status, u32* __restrict__ tileoff) {
-  __shared__ u32 ws[UR_THREADS / 32 + 1];
-  __shared__ u32 s_tile, s_carry;
+k_unrle_tilesum(const u8* __restrict__ rle, const u8* __restrict__ cls, const CandRes* __restrict__ res, u32 tps, u32* __restrict__ tilesum) {
+  __shared__ u32 ws[UR_THREADS / 32];
   const u32 tid = threadIdx.x;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const u32 tile = s_tile;
-  const u32 ci = tile / tps, lt = tile % tps;
-  CandRes* r = res + ci;
+  const u32 ci = blockIdx.x / tps, lt = blockIdx.x % tps;
+  const CandRes* r = res + ci;
   if (r->status != 0) return;
   const u32 n = r->n;
   const u32 start = lt * UR_TILE;
@@ -967,17 +965,32 @@ k_unrle_scan(const u8* __restrict__ rle, const u8* __restrict__ cls, CandRes* __
     for (int j = 0; j < UR_ITEMS; j++)
       if (p0 + j < n) sum += ((u32)(cv >> (8 * j)) & 0xffu) ? ((u32)(bv >> (8 * j)) & 0xffu) : 1u;
   }
-  u32 total;
-  block_excl_add<UR_THREADS, u32>(sum, ws, &total);
-  if (tid < 32) {
-    u32 cr = lookback_warp(status + (size_t)ci * tps, lt, total, OpAdd());
-    if (tid == 0) s_carry = cr;
-  }
+  sum = warp_reduce_add(sum);
+  if ((tid & 31u) == 0) ws[tid >> 5] = sum;
   __syncthreads();
-  if (tid == 0) {
-    tileoff[(size_t)ci * tps + lt] = s_carry;
-    if (start + UR_TILE >= n) r->rawlen = s_carry + total;
+  if (tid < 32) {
+    u32 v = tid < UR_THREADS / 32 ? ws[tid] : 0u;
+    v = warp_reduce_add(v);
+    if (tid == 0) tilesum[(size_t)ci * tps + lt] = v;
   }
+}
+// one warp per block: output offset of every tile, decoded size of the block
+__global__ void __launch_bounds__(32)
+k_unrle_tileoff(CandRes* __restrict__ res, u32 tps, const u32* __restrict__ tilesum, u32* __restrict__ tileoff) {
+  const u32 ci = blockIdx.x, lane = threadIdx.x;
+  CandRes* r = res + ci;
+  if (r->status != 0) return;
+  const u32 n = r->n;
+  const u32 nt = (n + UR_TILE - 1) / UR_TILE;
+  u32 run = 0;
+  for (u32 t0 = 0; t0 < nt; t0 += 32) {
+    const u32 t = t0 + lane;
+    const u32 v = t < nt ? tilesum[(size_t)ci * tps + t] : 0u;
+    const u32 inc = warp_incl_add(v);
+    if (t < nt) tileoff[(size_t)ci * tps + t] = run + inc - v;
+    run += __shfl_sync(FULL_MASK, inc, 31);
+  }
+  if (lane == 0) r->rawlen = run;
 }
 
 __global__ void __launch_bounds__(UR_THREADS)
@@ -1069,12 +1082,23 @@ struct DecSession {
   bool single = false, eos_single = false;
   DBuf<Cand> dcand;
   DBuf<CandRes> dres;              // own share only
-  DBuf<u8> rle, cls;
+  DBuf<u8> rle, cls;               // cls (count-byte classes) is kept for the whole share only while that is cheap (keep_cls)
+  bool keep_cls = true;
   DBuf<u32> tileoff;
   int err_event = -1;              // index of the first failing event (sharded mode)
 };
 
 static const u32 UR_TPS = SEG_SIZE / UR_TILE;
+#define DEC_KEEP_CLS 16384u
+// blocks per decode batch ($B2_DEC_BATCH: test hook, small batches exercise the batch seams on small inputs)
+static u32 dec_batch_blocks(const Ctx& c) {
+  if (const char* e = getenv("B2_DEC_BATCH")) { const int v = atoi(e); if (v >= 1) return (u32)v; }
+  return std::max(c.bwt_batch, 2048u);
+}
+static u32 dec_keep_cls_limit() {
+  if (const char* e = getenv("B2_DEC_KEEP_CLS")) { const int v = atoi(e); if (v >= 0) return (u32)v; }  // test hook
+  return DEC_KEEP_CLS;
+}
 
 static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool single_block, u64 bitpos, int rank, int world) {
   S.c = &c; S.n = n; S.single = single_block;
@@ -1143,9 +1167,10 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   S.hi = (size_t)(rank + 1) * nb_all / (size_t)world;
   const size_t nb = S.hi - S.lo;
   {
-    // every block of the own share keeps 2 MiB (L column + count-byte classes) until the stream is assembled, and a batch
-    // of up to 2048 blocks needs ~19 MiB of scratch per block: say so instead of failing inside an allocation
-    const size_t need = nb * ((size_t)2 << 20) + std::min<size_t>(nb, std::max(c.bwt_batch, 2048u)) * ((size_t)19 << 20) + n;
+    // every block of the own share keeps 2 MiB (L column + count-byte classes; 1 MiB beyond DEC_KEEP_CLS blocks) until the
+    // stream is assembled, and a batch of up to 2048 blocks needs ~20 MiB of scratch per block: say so instead of failing
+    // inside an allocation
+    const size_t need = nb * ((size_t)(nb <= dec_keep_cls_limit() ? 2 : 1) << 20) + std::min<size_t>(nb, dec_batch_blocks(c)) * ((size_t)20 << 20) + n;
     // memory the stream-ordered pool holds but does not use is available too: when that covers the call (every call
     // after the first of a kind) the driver is not asked at all -- cudaMemGetInfo takes milliseconds on a busy context
     uint64_t reserved = 0, used = 0;
@@ -1171,7 +1196,12 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   S.dcand.alloc(c, nb_all ? nb_all : 1);
   S.dres.alloc(c, nb ? nb : 1);
   S.rle.alloc(c, (nb ? nb : 1) << SEG_SHIFT);
-  S.cls.alloc(c, (nb ? nb : 1) << SEG_SHIFT);
+  // The count-byte classes of a block are needed twice (length scan here, expansion in dec_finish).  Up to DEC_KEEP_CLS
+  // blocks they stay on the device in between; a stream of more blocks (tens of GB of level-1 data) keeps only the L
+  // columns (1 MiB per block) and classifies a second time, batch by batch, when it expands them.
+  S.keep_cls = nb <= dec_keep_cls_limit();
+  const u32 DBc = dec_batch_blocks(c);
+  S.cls.alloc(c, (size_t)(S.keep_cls ? (nb ? nb : 1) : std::min<size_t>(nb, DBc)) << SEG_SHIFT);
   S.tileoff.alloc(c, (nb ? nb : 1) * (size_t)UR_TPS);
   if (nb_all) CUDA_CHECK(cudaMemcpyAsync(S.dcand, S.bc.data(), sizeof(Cand) * nb_all, cudaMemcpyHostToDevice, c.stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
@@ -1184,7 +1214,7 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
   // ---- 2. decode the own share of the candidate blocks, in batches ----
   // the per-block Huffman stage is one CTA per block and latency bound: give it every block at once
   // (about 19 MB of scratch per block; 180 GB of HBM take thousands)
-  const u32 DB = std::max(c.bwt_batch, 2048u);
+  const u32 DB = dec_batch_blocks(c);
   dec_attr_once();
   if (nb) {
     const u32 nbm = (u32)std::min<size_t>(DB, nb);
@@ -1195,11 +1225,10 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
     DBuf<u8> perms(c, (size_t)nbm * cps * 256), lists(c, (size_t)nbm * cps * 256);
     DBuf<ChunkStart> starts(c, (size_t)nbm * cps);
     DBuf<u32> keyA(c, (size_t)nbm << SEG_SHIFT), keyB(c, (size_t)nbm << SEG_SHIFT), valA(c, (size_t)nbm << SEG_SHIFT), valB(c, (size_t)nbm << SEG_SHIFT);
-    DBuf<u32> dn(c, nbm), nvis(c, nbm), ticket(c, 1);
+    DBuf<u32> dn(c, nbm), nvis(c, nbm), tilesum(c, (size_t)nbm * ur_tps);
     DBuf<Seg> segs(c, (size_t)nbm * IB_SEGS);
     DBuf<Visit> visits(c, (size_t)nbm * IB_VCAP);
     DBuf<u32> capr(c, (size_t)nbm * IB_SEGS), tails(c, (size_t)nbm * IB_VCAP), ntails(c, nbm);
-    DBuf<u64> lbst(c, (size_t)nbm * ur_tps);
     std::vector<u32> hn(nbm);
     for (size_t k0 = 0; k0 < nb; k0 += DB) {
       const u32 cnt = (u32)std::min<size_t>(DB, nb - k0);
@@ -1261,12 +1290,12 @@ static void dec_open(Ctx& c, DecSession& S, const u8* d_in_user, size_t n, bool 
       if (nmax) {
         StageScope ss(c, ST_UNRLE);
         const u32 nslots = cnt << SEG_SHIFT;
-        k_unrle_classify<<<(nslots / 8 + 255) / 256, 256, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), rb, cnt, cls.p + (k0 << SEG_SHIFT));
+        u8* clsb = cls.p + (S.keep_cls ? (k0 << SEG_SHIFT) : 0);
+        k_unrle_classify<<<(nslots / 8 + 255) / 256, 256, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), rb, cnt, clsb);
         KLAUNCH(c); KCHECK();
-        CUDA_CHECK(cudaMemsetAsync(lbst, 0, (size_t)cnt * ur_tps * 8, c.stream));
-        CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, c.stream));
-        k_unrle_scan<<<cnt * ur_tps, UR_THREADS, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), cls.p + (k0 << SEG_SHIFT), rb, ur_tps, ticket, lbst,
-                                                               tileoff.p + k0 * ur_tps);
+        k_unrle_tilesum<<<cnt * ur_tps, UR_THREADS, 0, c.stream>>>(rle.p + (k0 << SEG_SHIFT), clsb, rb, ur_tps, tilesum);
+        KLAUNCH(c); KCHECK();
+        k_unrle_tileoff<<<cnt, 32, 0, c.stream>>>(rb, ur_tps, tilesum, tileoff.p + k0 * ur_tps);
         KLAUNCH(c); KCHECK();
         CUDA_CHECK(cudaMemcpyAsync(hres + k0, rb, sizeof(CandRes) * cnt, cudaMemcpyDeviceToHost, c.stream));
       }
@@ -1386,8 +1415,20 @@ static int dec_finish(Ctx& c, DecSession& S, int multistream, u8* d_out, size_t 
     for (size_t i = 0; i < nb; i++) ob[i] = outbase[S.lo + i] == ~0ull ? ~0ull : outbase[S.lo + i] - my_off;
     DBuf<u64> dob(c, nb);
     CUDA_CHECK(cudaMemcpyAsync(dob, ob.data(), 8 * nb, cudaMemcpyHostToDevice, c.stream));
-    k_unrle_emit<<<(unsigned)(nb * ur_tps), UR_THREADS, 0, c.stream>>>(S.rle, S.cls, S.dres, ur_tps, S.tileoff, dob, dout);
-    KLAUNCH(c); KCHECK();
+    if (S.keep_cls) {
+      k_unrle_emit<<<(unsigned)(nb * ur_tps), UR_THREADS, 0, c.stream>>>(S.rle, S.cls, S.dres, ur_tps, S.tileoff, dob, dout);
+      KLAUNCH(c); KCHECK();
+    } else {
+      const size_t DBc = dec_batch_blocks(c);
+      for (size_t k0 = 0; k0 < nb; k0 += DBc) {
+        const u32 cnt = (u32)std::min<size_t>(DBc, nb - k0);
+        k_unrle_classify<<<(unsigned)((((size_t)cnt << SEG_SHIFT) / 8 + 255) / 256), 256, 0, c.stream>>>(S.rle.p + (k0 << SEG_SHIFT), S.dres.p + k0, cnt, S.cls);
+        KLAUNCH(c); KCHECK();
+        k_unrle_emit<<<(unsigned)(cnt * ur_tps), UR_THREADS, 0, c.stream>>>(S.rle.p + (k0 << SEG_SHIFT), S.cls, S.dres.p + k0, ur_tps, S.tileoff.p + k0 * ur_tps,
+                                                                            dob.p + k0, dout);
+        KLAUNCH(c); KCHECK();
+      }
+    }
     std::vector<BlkInfo> ranges(nb);
     for (size_t i = 0; i < nb; i++) {
       memset(&ranges[i], 0, sizeof(BlkInfo));

@@ -96,6 +96,33 @@ def test_thousands_of_tiny_blocks_and_members():
     assert Bzip2.decompressFile(cat, None, True) == b"hello, world\n" * 1500
 
 
+def test_decode_batch_seams_and_reclassified_blocks():
+    """Streams of more than one decode batch, and of more blocks than the decoder keeps count-byte classes for (production:
+    2048 / 16384 blocks; $B2_DEC_BATCH / $B2_DEC_KEEP_CLS shrink both): the batch seams and the second classification pass
+    must not change a byte.  Runs in a child process because the library reads the hooks per call but the tests share it."""
+    code = r"""
+import bz2, sys
+sys.path.insert(0, %r)
+from tests import util as T
+from compressjs_b200 import Bzip2
+data = T.runs(1300000, 61) + T.texty(900000, 62) + b"z" * 300000 + T.ascii_random(700000, 63) + bytes(range(256)) * 1200
+z1 = bz2.compress(data, 1)                       # ~35 blocks of 100k
+assert Bzip2.decompressFile(z1) == data
+z2 = Bzip2.compressFile(data, None, 2)
+assert Bzip2.decompressFile(z2) == data
+cat = z1 + bz2.compress(b"tail member " * 5000, 3)
+assert Bzip2.decompressFile(cat, None, True) == data + b"tail member " * 5000
+rows = []
+Bzip2.table(z1, lambda pos, size: rows.append((pos, size)))
+assert sum(sz for _, sz in rows) == len(data), (sum(sz for _, sz in rows), len(data))
+assert len(rows) >= 15, len(rows)
+print("ok", len(rows))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2_DEC_BATCH="7", B2_DEC_KEEP_CLS="5")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("level,window,pinned", [(1, 4 << 20, True), (9, 4 << 20, False), (5, 3 << 20, True)])
 def test_streaming_windows_reproduce_the_one_shot_stream(level, window, pinned, monkeypatch):
     """b2_bzip2_compress with an input larger than its streaming window (B2_STREAM_WINDOW; production default 8 GiB): the
