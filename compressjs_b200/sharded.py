@@ -264,6 +264,50 @@ class ShardedStream:
         self.offset = offs[rank] // 8
         self.total_bytes = (total_bits + 7) // 8
 
+    def _fixups(self):
+        """Header, shared edge bytes and trailer: {byte offset: value} (the same on every rank)."""
+        edge = {}
+        for r in range(self.world):
+            if self.nbs[r]:
+                b0 = self.offs[r] // 8
+                e0, e1 = int(self.alle[r][0]), int(self.alle[r][1])
+                edge[b0] = edge.get(b0, 0) | e0
+                edge[b0 + self.nbs[r] - 1] = edge.get(b0 + self.nbs[r] - 1, 0) | e1
+        scrc = 0
+        for m in self.meta:
+            scrc = rotl32(scrc, m[1]) ^ m[2]
+        b0t, tb = trailer_bytes(self.end_bit, scrc)
+        fix = {b0t + k: v for k, v in enumerate(tb)}
+        for k, v in edge.items():
+            if k >= 4:
+                fix[k] = fix.get(k, 0) | v
+        for k, v in enumerate(b"BZh" + bytes([0x30 + self.level])):
+            fix[k] = v
+        return fix
+
+    def write_file(self, path):
+        """Every rank writes the interior bytes of its piece at their offset of `path` (one file, visible to all ranks);
+        rank 0 sizes the file first and adds the header, the bytes neighbours share and the trailer.  Returns the
+        stream length.  The consumer-side counterpart of leaving the stream sharded: no rank ever holds the whole file."""
+        import os
+        if self.rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(self.total_bytes)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        fd = os.open(path, os.O_WRONLY)
+        try:
+            if self.nb > 2:
+                os.pwrite(fd, self.piece[1: self.nb - 1].cpu().numpy().tobytes(), self.offset + 1)
+            if self.rank == 0:
+                for k, v in sorted(self._fixups().items()):
+                    os.pwrite(fd, bytes([v]), k)
+        finally:
+            os.close(fd)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return self.total_bytes
+
     def gather(self):
         rank, world, group, device = self.rank, self.world, self.group, self.device
         shifted, nb, offs, nbs, alle, meta, o = self.piece, self.nb, self.offs, self.nbs, self.alle, self.meta, self.end_bit
@@ -288,27 +332,9 @@ class ShardedStream:
         if rank != 0:
             return None
         # 4. header, edge bytes, trailer
-        edge = {}
-        for r in range(world):
-            if nbs[r]:
-                b0 = offs[r] // 8
-                e0, e1 = int(alle[r][0]), int(alle[r][1])
-                edge[b0] = edge.get(b0, 0) | e0
-                edge[b0 + nbs[r] - 1] = edge.get(b0 + nbs[r] - 1, 0) | e1
-        scrc = 0
-        for m in meta:
-            scrc = rotl32(scrc, m[1]) ^ m[2]
-        b0t, tb = trailer_bytes(o, scrc)
-        tail = {}
-        for k, v in enumerate(tb):
-            tail[b0t + k] = v
-        fix = dict(tail)
-        for k, v in edge.items():
-            if k >= 4:
-                fix[k] = fix.get(k, 0) | v
-        hdr = list(b"BZh" + bytes([0x30 + self.level]))
-        idx = torch.tensor(list(range(4)) + list(fix.keys()), dtype=torch.int64, device=device)
-        val = torch.tensor(hdr + list(fix.values()), dtype=torch.uint8, device=device)
+        fix = self._fixups()
+        idx = torch.tensor(list(fix.keys()), dtype=torch.int64, device=device)
+        val = torch.tensor(list(fix.values()), dtype=torch.uint8, device=device)
         out[idx] = val
         _tick("edges_trailer", t0)
         return out

@@ -76,7 +76,7 @@ def _worker_host(rank, world, port, level, n, seed, q):
     dist.destroy_process_group()
 
 
-def _worker_kept(rank, world, port, level, n, seed, q):
+def _worker_kept(rank, world, port, level, n, seed, q, path):
     """The stream is left sharded (ShardedStream): every rank's piece already sits at its final bit position; gather()
     then assembles the same bytes on rank 0."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -97,16 +97,22 @@ def _worker_kept(rank, world, port, level, n, seed, q):
     out = ss.gather()
     if rank == 0:
         ok = ok and bytes(out.numpy().tobytes()) == z
+    # ... or every rank writes its own byte range of one file
+    ln = ss.write_file(path)
+    if rank == 0:
+        with open(path, "rb") as f:
+            ok = ok and ln == len(z) and f.read() == z
     q.put(bool(ok))
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world,n", [(2, 450000), (3, 520000)])
-def test_stream_left_sharded_then_gathered(world, n):
+def test_stream_left_sharded_then_gathered(world, n, tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_kept, args=(r, world, port, 1, n, 11, q)) for r in range(world)]
+    path = str(tmp_path / "sharded.bz2")
+    procs = [ctx.Process(target=_worker_kept, args=(r, world, port, 1, n, 11, q, path)) for r in range(world)]
     for p in procs:
         p.start()
     oks = [q.get(timeout=300) for _ in range(world)]
